@@ -1,0 +1,315 @@
+/*
+ * wva_b200.h — C-ABI of the B200-native WVA optimization hot path.
+ *
+ * This is the drop-in boundary a cgo shim binds (see INTEGRATION.md and
+ * llm-d-workload-variant-autoscaler_b200/go/).  The reference
+ * (llm-d/llm-d-workload-variant-autoscaler @ b08b1c77) has NO FFI boundary of
+ * its own — it is 100 % Go — so every entry point below cites the Go
+ * function(s) it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - the CALLER owns every host buffer; the library copies before returning
+ *     and never retains a caller pointer (cgo pointer rule)
+ *   - every function returns an int32 status (WVA_OK == 0); an infeasible
+ *     (server, accelerator) candidate is DATA (feasible == 0, the Go nil
+ *     *Allocation, pkg/core/allocation.go:118-122), never an error
+ *   - strings never cross: the shim keeps name<->index maps built from SORTED
+ *     names (Go map iteration order is random; sorted-name index order is the
+ *     canonical order wherever the reference iterates a map)
+ *   - a ctx is single-caller (the reference's math runs on one goroutine,
+ *     internal/engines/executor/polling.go:50-54); distinct ctxs are
+ *     independent and may be used concurrently
+ *   - there is NO CPU fallback: without a usable CUDA device wva_create fails
+ */
+#ifndef WVA_B200_H
+#define WVA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------- */
+enum {
+  WVA_OK = 0,
+  WVA_ERR_ARG = 1,        /* null pointer / negative size / inconsistent index */
+  WVA_ERR_CUDA = 2,       /* a CUDA runtime call or kernel failed              */
+  WVA_ERR_NO_DEVICE = 3,  /* no usable sm_100 device (no CPU fallback exists)  */
+  WVA_ERR_STATE = 4,      /* call order violated (e.g. solve before calculate) */
+  WVA_ERR_NOMEM = 5,      /* host or device allocation failed                  */
+  WVA_ERR_LIMIT = 6       /* a size exceeds what the kernels support           */
+};
+
+/* saturation policy: pkg/config/config.go:4-41 (SaturatedAllocationPolicy) */
+enum {
+  WVA_POLICY_NONE = 0,
+  WVA_POLICY_PRIORITY_EXHAUSTIVE = 1,
+  WVA_POLICY_PRIORITY_ROUND_ROBIN = 2,
+  WVA_POLICY_ROUND_ROBIN = 3
+};
+
+/* candidate / solution state */
+enum {
+  WVA_ALLOC_NONE = 0,   /* Go nil *Allocation                                     */
+  WVA_ALLOC_ACC = 1,    /* allocation on accelerator index `acc`                  */
+  WVA_ALLOC_EMPTY = 2   /* zero-load allocation with accelerator "" and 0 replicas
+                           (pkg/core/allocation.go:255-260)                       */
+};
+
+/* current-accelerator sentinels (srv_cur_acc) */
+#define WVA_CUR_ACC_EMPTY (-1)   /* curAllocation.accelerator == ""               */
+#define WVA_CUR_ACC_UNKNOWN (-2) /* non-empty name that matches no accelerator    */
+
+typedef struct wva_ctx wva_ctx;
+
+/*
+ * Index-keyed SoA image of config.SystemSpec (pkg/config/types.go:11-149) after
+ * System.SetFromSpec (pkg/core/system.go:82-89) resolved the string keys.
+ * Sizes: A = n_acc, T = n_types, M = n_models, S = n_servers.
+ */
+typedef struct wva_system {
+  /* accelerators: AcceleratorSpec (types.go:29-37) */
+  int32_t n_acc;
+  int32_t n_types;
+  const float* acc_cost;            /* [A] Cost, cents/hr                         */
+  const int32_t* acc_multiplicity;  /* [A] Multiplicity                           */
+  const int32_t* acc_type;          /* [A] index of Type in [0,T)                 */
+  const int32_t* type_count;        /* [T] CapacityData count (0 when absent)     */
+
+  /* ModelAcceleratorPerfData (types.go:66-73), row-major [M][A] */
+  int32_t n_models;
+  const float* perf_alpha;          /* [M*A] ServiceParms.Alpha                   */
+  const float* perf_beta;           /* [M*A]                                      */
+  const float* perf_gamma;          /* [M*A]                                      */
+  const int32_t* perf_max_batch;    /* [M*A] MaxBatchSize                         */
+  const int32_t* perf_at_tokens;    /* [M*A] AtTokens                             */
+  const int32_t* perf_acc_count;    /* [M*A] AccCount (<=0 -> 1, model.go:52-55)  */
+  const uint8_t* perf_present;      /* [M*A] 1 if model has perf data on acc      */
+
+  /* servers: ServerSpec (types.go:108-117) with class/target resolved */
+  int32_t n_servers;
+  const int32_t* srv_model;         /* [S] model index, -1 = unknown model        */
+  const int32_t* srv_priority;      /* [S] Server.Priority() (server.go:92-97)    */
+  const int32_t* srv_min_replicas;  /* [S] MinNumReplicas                         */
+  const int32_t* srv_max_batch;     /* [S] MaxBatchSize override (0 = derive)     */
+  const uint8_t* srv_keep_acc;      /* [S] KeepAccelerator                        */
+  const uint8_t* srv_target_present;/* [S] class exists and has a target for the model */
+  const float* srv_slo_ttft;        /* [S] Target.TTFT ms (0 = no target)         */
+  const float* srv_slo_itl;         /* [S] Target.ITL ms                          */
+  const float* srv_slo_tps;         /* [S] Target.TPS tokens/s                    */
+  const float* srv_arrival;         /* [S] ServerLoadSpec.ArrivalRate, req/min    */
+  const int32_t* srv_in_tokens;     /* [S] AvgInTokens                            */
+  const int32_t* srv_out_tokens;    /* [S] AvgOutTokens                           */
+  const int32_t* srv_cur_acc;       /* [S] CurrentAlloc accelerator index / sentinel */
+  const int32_t* srv_cur_replicas;  /* [S] CurrentAlloc.NumReplicas               */
+  const float* srv_cur_cost;        /* [S] CurrentAlloc.Cost                      */
+
+  /* OptimizerSpec (types.go:145-149) */
+  uint8_t unlimited;
+  uint8_t delayed_best_effort;
+  int32_t saturation_policy;        /* WVA_POLICY_*                               */
+} wva_system;
+
+/*
+ * Per-(server, accelerator) candidates = Server.AllAllocations() after
+ * Server.Calculate (pkg/core/server.go:55-67); row-major [S][A].
+ * Fields mirror core.Allocation (pkg/core/allocation.go:13-24).
+ */
+typedef struct wva_candidates {
+  uint8_t* state;          /* [S*A] WVA_ALLOC_*                                   */
+  int32_t* num_replicas;   /* [S*A]                                               */
+  int32_t* batch_size;     /* [S*A]                                               */
+  float* cost;             /* [S*A]                                               */
+  float* value;            /* [S*A] TransitionPenalty(cur -> candidate)           */
+  float* itl;              /* [S*A]                                               */
+  float* ttft;             /* [S*A] AvgWaitTime + AvgPrefillTime (allocation.go:148) */
+  float* rho;              /* [S*A]                                               */
+  float* max_arrv_rate;    /* [S*A] maxArrvRatePerReplica, req/msec               */
+  int32_t* n_solves;       /* [S*A] chain solves spent on the pair (may be NULL)  */
+} wva_candidates;
+
+/*
+ * Solution = Server.Allocation() for every server after Manager.Optimize
+ * (pkg/manager/manager.go:21-27) + System.AllocateByType (system.go:271-299).
+ */
+typedef struct wva_solution {
+  uint8_t* state;          /* [S] WVA_ALLOC_*                                     */
+  int32_t* acc;            /* [S] accelerator index (-1 unless state==ACC)        */
+  int32_t* num_replicas;   /* [S]                                                 */
+  int32_t* batch_size;     /* [S]                                                 */
+  float* cost;             /* [S]                                                 */
+  float* value;            /* [S]                                                 */
+  float* itl;              /* [S]                                                 */
+  float* ttft;             /* [S]                                                 */
+  float* rho;              /* [S]                                                 */
+  float* max_arrv_rate;    /* [S]                                                 */
+  int64_t* type_count;     /* [T] AllocationByType.count                          */
+  double* type_cost;       /* [T] AllocationByType.cost (summed in f64)           */
+} wva_solution;
+
+/* per-call device timings, milliseconds (CUDA events on the ctx stream) */
+typedef struct wva_timing {
+  float h2d_ms;
+  float calculate_ms;
+  float solve_ms;
+  float grid_ms;
+  float saturation_ms;
+  float limit_ms;
+  float d2h_ms;
+  int64_t chain_solves;    /* chain solves executed by the last calculate/grid    */
+  int64_t chain_states;    /* birth-death states visited by the last calculate/grid */
+  int64_t overflow_pairs;  /* pairs that took the float64 overflow-rescale slow path  */
+} wva_timing;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+int32_t wva_create(int32_t device, wva_ctx** out);
+int32_t wva_destroy(wva_ctx* ctx);
+const char* wva_strerror(int32_t code);
+/* text of the last CUDA error seen by this ctx ("" if none) */
+const char* wva_last_error(const wva_ctx* ctx);
+/* number of kernel launches issued by this ctx since creation */
+int64_t wva_launch_count(const wva_ctx* ctx);
+
+/* ---- queueing sizing + allocator ---------------------------------------- */
+/* System.SetFromSpec (pkg/core/system.go:82-89): copies the SoA to HBM. */
+int32_t wva_load_system(wva_ctx* ctx, const wva_system* sys);
+/* System.Calculate (pkg/core/system.go:258-268) -> Server.Calculate (server.go:55-67)
+ * -> CreateAllocation (allocation.go:27-155) for every (server, accelerator). */
+int32_t wva_calculate(wva_ctx* ctx);
+/* Manager.Optimize (pkg/manager/manager.go:21-27): Optimizer.Optimize
+ * (pkg/solver/optimizer.go:24-36) -> Solver.Solve (solver.go:32-60) — SolveUnlimited
+ * (solver.go:63-79) or SolveGreedy (greedy.go:35-105) — then AllocateByType. */
+int32_t wva_solve(wva_ctx* ctx);
+/* Server.AllAllocations() of every server (server.go:138-140). */
+int32_t wva_get_candidates(wva_ctx* ctx, wva_candidates* out);
+/* System.GenerateSolution (system.go:303-319) + allocationByType. */
+int32_t wva_get_solution(wva_ctx* ctx, wva_solution* out);
+
+/*
+ * Replica-grid evaluator: for every (server, accelerator, r in 1..R) one
+ * QueueAnalyzer.Analyze(totalRate / r) (pkg/analyzer/queueanalyzer.go:127-167),
+ * i.e. exactly the call CreateAllocation makes at allocation.go:140-148 with
+ * numReplicas = r.  Outputs (any may be NULL), row-major [S][A][R]:
+ *   ok    1 if Analyze returned metrics (rate in range), else 0
+ *   ttft  AvgWaitTime + AvgPrefillTime;  itl AvgTokenTime;  rho;  tput Throughput
+ * frontier [S*A]: smallest r whose metrics meet every non-zero SLO of the server
+ *   (ttft <= slo_ttft, itl <= slo_itl), 0 if none in 1..R — the per-(model,
+ *   variant) feasible frontier the north-star design reduces to.
+ */
+int32_t wva_analyze_grid(wva_ctx* ctx, int32_t R, uint8_t* ok, float* ttft,
+                         float* itl, float* rho, float* tput, int32_t* frontier);
+/* The same in two steps, so a caller can keep the grid resident in HBM:
+ * wva_grid_run evaluates it on the loaded system (full != 0 materialises the
+ * per-level arrays, the frontier is always produced); wva_grid_fetch copies the
+ * requested arrays to host buffers (NULL = skip). */
+int32_t wva_grid_run(wva_ctx* ctx, int32_t R, int32_t full);
+int32_t wva_grid_fetch(wva_ctx* ctx, uint8_t* ok, float* ttft, float* itl,
+                       float* rho, float* tput, int32_t* frontier);
+
+/*
+ * Closed-form M/M/1/K leg: MM1KModel.Solve (pkg/analyzer/mm1kmodel.go:30-92).
+ * n independent (lambda, mu, K) triples -> valid flag + 6 float32 statistics.
+ */
+int32_t wva_mm1k_eval(wva_ctx* ctx, int64_t n, const float* lambda,
+                      const float* mu, const int32_t* K, uint8_t* valid,
+                      float* avg_resp, float* avg_wait, float* avg_serv,
+                      float* avg_num, float* avg_queue, float* throughput,
+                      float* rho);
+
+/* ---- V1 saturation capacity model --------------------------------------- */
+/*
+ * Saturation inputs: M models, V variants (CSR by model), P replicas (CSR by
+ * variant, in the order the reference's metric slice lists them).
+ * Replaces saturation.Analyzer.AnalyzeModelSaturation
+ * (internal/saturation/analyzer.go:31-131) and CalculateSaturationTargets
+ * (analyzer.go:290-439) for a whole batch of models in one call.
+ * Variants of a model must be indexed in ascending VariantName order.
+ */
+typedef struct wva_saturation_in {
+  int64_t n_models, n_variants, n_replicas;
+  const int32_t* model_variant_off;  /* [M+1]                                     */
+  const int32_t* variant_replica_off;/* [V+1] (int64 not needed below 2^31 replicas) */
+  /* ReplicaMetrics (internal/interfaces/saturation_analyzer.go:12-22) */
+  const double* rep_kv;              /* [P] KvCacheUsage                          */
+  const int64_t* rep_queue;          /* [P] QueueLength (Go int)                  */
+  /* VariantReplicaState (saturation_analyzer.go:228-243) + Cost */
+  const double* var_cost;            /* [V]                                       */
+  const int32_t* var_current;        /* [V] CurrentReplicas                       */
+  const int32_t* var_desired;        /* [V] DesiredReplicas                       */
+  const int32_t* var_pending;        /* [V] PendingReplicas                       */
+  const uint8_t* var_has_state;      /* [V] 0 = no VariantReplicaState for the variant
+                                        (stateMap lookup yields the zero value); may be NULL = all 1 */
+  /* SaturationScalingConfig per model (saturation_scaling.go:8-47) */
+  const double* cfg_kv_threshold;    /* [M]                                       */
+  const double* cfg_queue_threshold; /* [M]                                       */
+  const double* cfg_kv_trigger;      /* [M]                                       */
+  const double* cfg_queue_trigger;   /* [M]                                       */
+} wva_saturation_in;
+
+typedef struct wva_saturation_out {  /* any pointer may be NULL (skipped)         */
+  int32_t* var_target;               /* [V] CalculateSaturationTargets result     */
+  /* VariantSaturationAnalysis (saturation_analyzer.go:98-109) */
+  int32_t* var_replica_count;        /* [V]                                       */
+  int32_t* var_non_saturated;        /* [V]                                       */
+  double* var_max_kv;                /* [V]                                       */
+  int64_t* var_max_queue;            /* [V]                                       */
+  double* var_avg_spare_kv;          /* [V]                                       */
+  double* var_avg_spare_queue;       /* [V]                                       */
+  uint8_t* rep_saturated;            /* [P] 1 if the replica is in SaturatedReplicas */
+  /* ModelSaturationAnalysis (saturation_analyzer.go:74-95) */
+  int32_t* mod_total_replicas;       /* [M]                                       */
+  int32_t* mod_non_saturated;        /* [M]                                       */
+  double* mod_avg_spare_kv;          /* [M]                                       */
+  double* mod_avg_spare_queue;       /* [M]                                       */
+  uint8_t* mod_flags;                /* [M] bit0 ShouldScaleUp, bit1 ScaleDownSafe,
+                                            bit2 model in transition, bit3 kv trigger,
+                                            bit4 queue trigger                    */
+  int64_t* partials;                 /* [4] n_scale_up, n_scale_down, n_transition,
+                                            sum of targets (shard partials for the
+                                            all-reduce across GPUs)               */
+} wva_saturation_out;
+
+#define WVA_SAT_SCALE_UP 1
+#define WVA_SAT_SCALE_DOWN_SAFE 2
+#define WVA_SAT_IN_TRANSITION 4
+#define WVA_SAT_KV_TRIGGERED 8
+#define WVA_SAT_QUEUE_TRIGGERED 16
+
+int32_t wva_saturation_v1(wva_ctx* ctx, const wva_saturation_in* in,
+                          const wva_saturation_out* out);
+/* The same in three steps (inputs / results stay resident in HBM between them):
+ * upload = host -> HBM copy of the metric batch; run = the analysis + targets
+ * kernel (detail == 0 writes only var_target, mod_flags and partials); fetch =
+ * HBM -> host copy of the requested outputs (NULL = skip). */
+int32_t wva_saturation_upload(wva_ctx* ctx, const wva_saturation_in* in);
+int32_t wva_saturation_run(wva_ctx* ctx, int32_t detail);
+int32_t wva_saturation_fetch(wva_ctx* ctx, const wva_saturation_out* out);
+
+/* ---- GPU-count limiter ---------------------------------------------------- */
+/*
+ * DefaultLimiter.Limit (internal/engines/pipeline/default_limiter.go:42-81) with
+ * TypeInventory.CreateAllocator / typeAllocator.TryAllocate
+ * (type_inventory.go:222-243,347-373) and GreedyBySaturation.Allocate
+ * (greedy_saturation_algorithm.go:34-108).  D decisions, T accelerator types.
+ * acc_type[d] = -1 encodes AcceleratorName == "".  Outputs are the mutated
+ * VariantDecision fields.
+ */
+int32_t wva_limit(wva_ctx* ctx, int64_t n_decisions, int32_t n_types,
+                  const int32_t* acc_type, const int32_t* current,
+                  const int32_t* target, const int32_t* gpus_per_replica,
+                  const double* spare_capacity, const double* cost,
+                  const int32_t* type_limit, int32_t* out_target,
+                  int32_t* out_gpus_allocated, uint8_t* out_was_limited);
+
+/* ---- observability -------------------------------------------------------- */
+int32_t wva_last_timing(const wva_ctx* ctx, wva_timing* out);
+
+/* microbenchmarks used by bench.py for the compute roofline (ops/s on device) */
+int32_t wva_microbench_fp64(wva_ctx* ctx, double* dfma_per_s, double* ddiv_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WVA_B200_H */

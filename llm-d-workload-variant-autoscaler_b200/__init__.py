@@ -1,0 +1,10 @@
+"""B200-native WVA optimization hot path (queueing sizer, allocator, saturation model, limiter).
+
+The compute lives in csrc/ (hand-written sm_100a CUDA behind the C-ABI of
+include/wva_b200.h).  This package is the Python binding used by tests/ and
+bench.py; the Go binding a maintainer would add is shown in INTEGRATION.md.
+There is no CPU fallback: constructing an Engine without the built CUDA library
+or without a GPU raises.
+"""
+from . import _abi, synth  # noqa: F401
+from .engine import Engine, WvaError, lib_path, load_library  # noqa: F401

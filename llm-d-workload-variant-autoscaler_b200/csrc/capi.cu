@@ -1,0 +1,453 @@
+// capi.cu — implementation of the C-ABI declared in include/wva_b200.h.
+// Host-side plumbing only (context, device arenas, launches, timing); all of the
+// arithmetic lives in the kernels included below.  No CPU fallback exists: every
+// entry point either runs CUDA kernels or returns an error status.
+#include "../../include/wva_b200.h"
+#include "wva_core.cuh"
+#include "sizer_kernel.cuh"
+#include "solve_kernels.cuh"
+#include "grid_kernel.cuh"
+#include "saturation_kernel.cuh"
+#include "limiter_kernel.cuh"
+#include "greedy_kernel.cuh"
+#include "mm1k_kernel.cuh"
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace wva;
+
+// ------------------------------------------------------------------ small helpers
+struct DevBuf {  // growable device allocation
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {  // growable pinned host staging
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// bump allocator over one arena: every sub-array 256-byte aligned
+struct Layout {
+  size_t off = 0;
+  size_t take(size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; }
+};
+
+struct GridState {   // results of the last wva_grid_run, resident in HBM
+  int R = 0;
+  bool full = false, ran = false;
+  DevBuf buf;
+  GridOut view = {};
+  GridCounters* ctr = nullptr;
+};
+struct SatState {    // resident inputs / outputs of the saturation model
+  bool uploaded = false, ran = false;
+  long long M = 0, V = 0, P = 0;
+  DevBuf in, out;
+  SatIn vin = {};
+  SatOut vout = {};
+  size_t out_bytes = 0;
+};
+
+struct wva_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::string last_error;
+  long long launches = 0;
+  wva_timing timing = {};
+
+  // queueing system
+  bool loaded = false, calculated = false, solved = false;
+  int A = 0, T = 0, M = 0, S = 0;
+  uint8_t unlimited = 1, delayed = 0;
+  int policy = 0;
+  DevBuf sys_arena, cand_arena, sol_arena, scratch, gtab, greedy_ws;
+  PinBuf stage_in, stage_out;
+  SysView sys = {};
+  CandView cand = {};
+  SolView sol = {};
+  long long* d_type_count = nullptr;
+  double* d_type_cost = nullptr;
+  SizerCounters* d_ctr = nullptr;   // in scratch
+  // generic io arenas for saturation / limiter / grid / mm1k
+  DevBuf io_in, io_out;
+  PinBuf io_stage_in, io_stage_out;
+  GridState grid;
+  SatState sat;
+};
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(e__);             \
+      return (e__ == cudaErrorMemoryAllocation) ? WVA_ERR_NOMEM : WVA_ERR_CUDA;          \
+    }                                                                                    \
+  } while (0)
+
+static float elapsed(wva_ctx* ctx, int a, int b) {
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
+  return ms;
+}
+
+extern "C" {
+
+const char* wva_strerror(int32_t code) {
+  switch (code) {
+    case WVA_OK: return "ok";
+    case WVA_ERR_ARG: return "invalid argument";
+    case WVA_ERR_CUDA: return "CUDA error";
+    case WVA_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case WVA_ERR_STATE: return "call order violated";
+    case WVA_ERR_NOMEM: return "out of memory";
+    case WVA_ERR_LIMIT: return "size exceeds kernel limits";
+    default: return "unknown status";
+  }
+}
+
+int32_t wva_create(int32_t device, wva_ctx** out) {
+  if (!out) return WVA_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return WVA_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return WVA_ERR_NO_DEVICE;
+  if (prop.major < 10) return WVA_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+  if (cudaSetDevice(device) != cudaSuccess) return WVA_ERR_NO_DEVICE;
+  wva_ctx* ctx = new (std::nothrow) wva_ctx();
+  if (!ctx) return WVA_ERR_NOMEM;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return WVA_ERR_CUDA; }
+  for (auto& e : ctx->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return WVA_ERR_CUDA; }
+  *out = ctx;
+  return WVA_OK;
+}
+
+int32_t wva_destroy(wva_ctx* ctx) {
+  if (!ctx) return WVA_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->sys_arena.release(); ctx->cand_arena.release(); ctx->sol_arena.release(); ctx->scratch.release();
+  ctx->gtab.release(); ctx->greedy_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->io_in.release(); ctx->io_out.release();
+  ctx->stage_in.release(); ctx->stage_out.release(); ctx->io_stage_in.release(); ctx->io_stage_out.release();
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return WVA_OK;
+}
+
+const char* wva_last_error(const wva_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+int64_t wva_launch_count(const wva_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t wva_last_timing(const wva_ctx* ctx, wva_timing* out) {
+  if (!ctx || !out) return WVA_ERR_ARG;
+  *out = ctx->timing;
+  return WVA_OK;
+}
+
+// ------------------------------------------------------------------ load
+int32_t wva_load_system(wva_ctx* ctx, const wva_system* s) {
+  if (!ctx || !s) return WVA_ERR_ARG;
+  if (s->n_acc < 0 || s->n_types < 0 || s->n_models < 0 || s->n_servers < 0) return WVA_ERR_ARG;
+  if (s->n_types > WVA_MAX_TYPES) return WVA_ERR_LIMIT;
+  CK(cudaSetDevice(ctx->device));
+  const size_t A = s->n_acc, T = s->n_types, M = s->n_models, S = s->n_servers, MA = M * A;
+  // validate indices the kernels dereference
+  for (size_t a = 0; a < A; a++)
+    if (s->acc_type[a] < 0 || s->acc_type[a] >= (int)T) return WVA_ERR_ARG;
+  for (size_t i = 0; i < S; i++) {
+    if (s->srv_model[i] >= (int)M) return WVA_ERR_ARG;
+    if (s->srv_cur_acc[i] >= (int)A || s->srv_cur_acc[i] < WVA_CUR_ACC_UNKNOWN) return WVA_ERR_ARG;
+  }
+  struct Item { const void* src; size_t bytes; size_t off; };
+  Layout L;
+  std::vector<Item> items;
+  auto add = [&](const void* p, size_t bytes) { Item it{p, bytes, L.take(bytes)}; items.push_back(it); return it.off; };
+  size_t o_acc_cost = add(s->acc_cost, A * 4), o_acc_mult = add(s->acc_multiplicity, A * 4),
+         o_acc_type = add(s->acc_type, A * 4), o_type_count = add(s->type_count, T * 4);
+  size_t o_pa = add(s->perf_alpha, MA * 4), o_pb = add(s->perf_beta, MA * 4), o_pg = add(s->perf_gamma, MA * 4),
+         o_pmb = add(s->perf_max_batch, MA * 4), o_pat = add(s->perf_at_tokens, MA * 4),
+         o_pac = add(s->perf_acc_count, MA * 4), o_pp = add(s->perf_present, MA);
+  size_t o_sm = add(s->srv_model, S * 4), o_sp = add(s->srv_priority, S * 4), o_smr = add(s->srv_min_replicas, S * 4),
+         o_smb = add(s->srv_max_batch, S * 4), o_sk = add(s->srv_keep_acc, S), o_stp = add(s->srv_target_present, S),
+         o_st = add(s->srv_slo_ttft, S * 4), o_si = add(s->srv_slo_itl, S * 4), o_sps = add(s->srv_slo_tps, S * 4),
+         o_sa = add(s->srv_arrival, S * 4), o_sin = add(s->srv_in_tokens, S * 4), o_sout = add(s->srv_out_tokens, S * 4),
+         o_sca = add(s->srv_cur_acc, S * 4), o_scr = add(s->srv_cur_replicas, S * 4), o_scc = add(s->srv_cur_cost, S * 4);
+  for (auto& it : items) if (it.bytes && !it.src) return WVA_ERR_ARG;
+  const size_t total = L.off + 256;
+  CK(ctx->stage_in.reserve(total));
+  CK(ctx->sys_arena.reserve(total));
+  char* h = (char*)ctx->stage_in.p;
+  for (auto& it : items) if (it.bytes) memcpy(h + it.off, it.src, it.bytes);
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CK(cudaMemcpyAsync(ctx->sys_arena.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  char* d = (char*)ctx->sys_arena.p;
+  SysView& v = ctx->sys;
+  v.n_acc = (int)A; v.n_types = (int)T; v.n_models = (int)M; v.n_servers = (int)S;
+  v.acc_cost = (const float*)(d + o_acc_cost); v.acc_multiplicity = (const int*)(d + o_acc_mult);
+  v.acc_type = (const int*)(d + o_acc_type); v.type_count = (const int*)(d + o_type_count);
+  v.perf_alpha = (const float*)(d + o_pa); v.perf_beta = (const float*)(d + o_pb); v.perf_gamma = (const float*)(d + o_pg);
+  v.perf_max_batch = (const int*)(d + o_pmb); v.perf_at_tokens = (const int*)(d + o_pat);
+  v.perf_acc_count = (const int*)(d + o_pac); v.perf_present = (const unsigned char*)(d + o_pp);
+  v.srv_model = (const int*)(d + o_sm); v.srv_priority = (const int*)(d + o_sp);
+  v.srv_min_replicas = (const int*)(d + o_smr); v.srv_max_batch = (const int*)(d + o_smb);
+  v.srv_keep_acc = (const unsigned char*)(d + o_sk); v.srv_target_present = (const unsigned char*)(d + o_stp);
+  v.srv_slo_ttft = (const float*)(d + o_st); v.srv_slo_itl = (const float*)(d + o_si); v.srv_slo_tps = (const float*)(d + o_sps);
+  v.srv_arrival = (const float*)(d + o_sa); v.srv_in_tokens = (const int*)(d + o_sin); v.srv_out_tokens = (const int*)(d + o_sout);
+  v.srv_cur_acc = (const int*)(d + o_sca); v.srv_cur_replicas = (const int*)(d + o_scr); v.srv_cur_cost = (const float*)(d + o_scc);
+  ctx->A = (int)A; ctx->T = (int)T; ctx->M = (int)M; ctx->S = (int)S;
+  ctx->unlimited = s->unlimited; ctx->delayed = s->delayed_best_effort; ctx->policy = s->saturation_policy;
+
+  // candidate + solution arenas
+  const size_t P = S * A;
+  {
+    Layout C;
+    size_t o_state = C.take(P), o_nr = C.take(P * 4), o_bs = C.take(P * 4), o_cost = C.take(P * 4), o_val = C.take(P * 4),
+           o_itl = C.take(P * 4), o_ttft = C.take(P * 4), o_rho = C.take(P * 4), o_mar = C.take(P * 4), o_ns = C.take(P * 4);
+    CK(ctx->cand_arena.reserve(C.off + 256));
+    char* c = (char*)ctx->cand_arena.p;
+    CandView& cv = ctx->cand;
+    cv.state = (unsigned char*)(c + o_state); cv.num_replicas = (int*)(c + o_nr); cv.batch_size = (int*)(c + o_bs);
+    cv.cost = (float*)(c + o_cost); cv.value = (float*)(c + o_val); cv.itl = (float*)(c + o_itl);
+    cv.ttft = (float*)(c + o_ttft); cv.rho = (float*)(c + o_rho); cv.max_arrv_rate = (float*)(c + o_mar);
+    cv.n_solves = (int*)(c + o_ns);
+  }
+  {
+    Layout C;
+    size_t o_state = C.take(S), o_acc = C.take(S * 4), o_nr = C.take(S * 4), o_bs = C.take(S * 4), o_cost = C.take(S * 4),
+           o_val = C.take(S * 4), o_itl = C.take(S * 4), o_ttft = C.take(S * 4), o_rho = C.take(S * 4), o_mar = C.take(S * 4),
+           o_tc = C.take(T * 8), o_tk = C.take(T * 8);
+    CK(ctx->sol_arena.reserve(C.off + 256));
+    char* c = (char*)ctx->sol_arena.p;
+    SolView& sv = ctx->sol;
+    sv.state = (unsigned char*)(c + o_state); sv.acc = (int*)(c + o_acc); sv.num_replicas = (int*)(c + o_nr);
+    sv.batch_size = (int*)(c + o_bs); sv.cost = (float*)(c + o_cost); sv.value = (float*)(c + o_val);
+    sv.itl = (float*)(c + o_itl); sv.ttft = (float*)(c + o_ttft); sv.rho = (float*)(c + o_rho);
+    sv.max_arrv_rate = (float*)(c + o_mar);
+    ctx->d_type_count = (long long*)(c + o_tc); ctx->d_type_cost = (double*)(c + o_tk);
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.h2d_ms = elapsed(ctx, 0, 1);
+  ctx->loaded = true; ctx->calculated = false; ctx->solved = false;
+  return WVA_OK;
+}
+
+// ------------------------------------------------------------------ calculate
+}  // extern "C" (templates need C++ linkage)
+template <int THREADS, bool SMEM>
+static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned long long n_pairs, int nmax, float* gtab,
+                                int* ovf_list) {
+  auto k = sizer_kernel<THREADS, SMEM>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+extern "C" {
+
+int32_t wva_calculate(wva_ctx* ctx) {
+  if (!ctx) return WVA_ERR_ARG;
+  if (!ctx->loaded) { ctx->last_error = "wva_calculate before wva_load_system"; return WVA_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  const unsigned long long n_pairs = (unsigned long long)ctx->S * ctx->A;
+  // scratch: counters + overflow list + nmax reduction
+  size_t need = 256 + 256 + (size_t)n_pairs * 4 + 1024;
+  CK(ctx->scratch.reserve(need));
+  ctx->d_ctr = (SizerCounters*)ctx->scratch.p;
+  int* d_nmax = (int*)((char*)ctx->scratch.p + 256);
+  int* d_ovf = (int*)((char*)ctx->scratch.p + 512);
+  CK(cudaMemsetAsync(ctx->scratch.p, 0, 512, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (n_pairs > 0) {
+    // 1) largest batch size any pair will use -> table geometry
+    int blocks = (int)((n_pairs + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    max_batch_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->sys, n_pairs, d_nmax);
+    ctx->launches++;
+    int nmax = 0;
+    CK(cudaMemcpyAsync(&nmax, d_nmax, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nmax < 1) nmax = 1;
+    const int NLIMIT = 1 << 16;
+    if (nmax > NLIMIT) nmax = NLIMIT;  // pairs beyond it are flagged through limit_hit
+    // 2) pick geometry: the head table (4 B x nmax per lane) lives in shared memory when at
+    //    least 64 lanes fit on an SM; lanes per SM are maximised over CTA sizes {256,192,128,64}
+    //    (1 KB per CTA is reserved by the driver).  Otherwise the table goes to global memory.
+    const size_t SMEM_PER_SM = 224 * 1024;
+    const size_t per_lane = (size_t)nmax * 4;
+    const int sizes[4] = {256, 192, 128, 64};
+    int best_threads = 0, best_per_sm = 0;
+    for (int i = 0; i < 4; i++) {
+      size_t cta = per_lane * sizes[i] + 1024;
+      int per_sm = (int)(SMEM_PER_SM / cta);
+      if (per_sm * sizes[i] > 1024) per_sm = 1024 / sizes[i];
+      if (per_sm * sizes[i] > best_threads * best_per_sm) { best_threads = sizes[i]; best_per_sm = per_sm; }
+    }
+    cudaError_t e;
+    if (best_per_sm >= 1) {
+      int blocks = ctx->sm_count * best_per_sm;
+      size_t smem = per_lane * best_threads;
+      switch (best_threads) {
+        case 256: e = launch_sizer<256, true>(ctx, blocks, smem, n_pairs, nmax, nullptr, d_ovf); break;
+        case 192: e = launch_sizer<192, true>(ctx, blocks, smem, n_pairs, nmax, nullptr, d_ovf); break;
+        case 128: e = launch_sizer<128, true>(ctx, blocks, smem, n_pairs, nmax, nullptr, d_ovf); break;
+        default: e = launch_sizer<64, true>(ctx, blocks, smem, n_pairs, nmax, nullptr, d_ovf); break;
+      }
+    } else {
+      int blk = ctx->sm_count * 2;
+      CK(ctx->gtab.reserve((size_t)blk * 256 * per_lane));
+      e = launch_sizer<256, false>(ctx, blk, 0, n_pairs, nmax, (float*)ctx->gtab.p, d_ovf);
+    }
+    if (e != cudaSuccess) { ctx->last_error = std::string("sizer launch: ") + cudaGetErrorString(e); return WVA_ERR_CUDA; }
+  }
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  SizerCounters hc;
+  CK(cudaMemcpyAsync(&hc, ctx->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.calculate_ms = elapsed(ctx, 2, 3);
+  ctx->timing.chain_solves = (int64_t)hc.solves;
+  ctx->timing.chain_states = (int64_t)hc.states;
+  ctx->timing.overflow_pairs = (int64_t)hc.overflow_pairs;
+  if (hc.limit_hit) { ctx->last_error = "a (server, accelerator) pair needs a max batch size above 65536"; return WVA_ERR_LIMIT; }
+  if (hc.overflow_pairs) {
+    // float64 overflow-rescale branch (mm1modelstatedependent.go:84-89,96-104): exact slow path
+    int32_t rc = run_overflow_slow_path(ctx->sys, ctx->cand, d_ovf, (int)hc.overflow_pairs, ctx->stream, &ctx->launches);
+    if (rc != 0) { ctx->last_error = "overflow slow path failed"; return WVA_ERR_CUDA; }
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->calculated = true; ctx->solved = false;
+  return WVA_OK;
+}
+
+// ------------------------------------------------------------------ solve
+int32_t wva_solve(wva_ctx* ctx) {
+  if (!ctx) return WVA_ERR_ARG;
+  if (!ctx->calculated) { ctx->last_error = "wva_solve before wva_calculate"; return WVA_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  const int S = ctx->S, T = ctx->T;
+  if (S > 0) {
+    if (ctx->unlimited) {
+      int blocks = (int)(((size_t)S * 32 + 255) / 256);
+      solve_unlimited_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->sys, ctx->cand, ctx->sol);
+      ctx->launches++;
+    } else {
+      int32_t rc = run_solve_greedy(ctx->sys, ctx->cand, ctx->sol, ctx->delayed, ctx->policy, &ctx->greedy_ws.p,
+                                    &ctx->greedy_ws.cap, ctx->stream, &ctx->launches);
+      if (rc != 0) { ctx->last_error = "SolveGreedy failed"; return rc; }
+    }
+  }
+  // AllocateByType
+  int nparts = (S + 255) / 256;
+  if (nparts < 1) nparts = 1;
+  size_t need = (size_t)nparts * (T > 0 ? T : 1) * 16 + 512;
+  // reuse scratch beyond its first 512 bytes (counters)
+  CK(ctx->scratch.reserve(1024 + need));
+  long long* pc = (long long*)((char*)ctx->scratch.p + 1024);
+  double* pd = (double*)((char*)ctx->scratch.p + 1024 + (size_t)nparts * (T > 0 ? T : 1) * 8);
+  if (T > 0) {
+    if (S > 0) {
+      by_type_partial_kernel<<<nparts, 256, 0, ctx->stream>>>(ctx->sys, ctx->sol, pc, pd);
+      ctx->launches++;
+    } else {
+      CK(cudaMemsetAsync(pc, 0, need - 512, ctx->stream));
+    }
+    by_type_final_kernel<<<T, 256, 0, ctx->stream>>>(T, S > 0 ? nparts : 0, pc, pd, ctx->d_type_count, ctx->d_type_cost);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.solve_ms = elapsed(ctx, 4, 5);
+  ctx->solved = true;
+  return WVA_OK;
+}
+
+// ------------------------------------------------------------------ readback
+int32_t wva_get_candidates(wva_ctx* ctx, wva_candidates* out) {
+  if (!ctx || !out) return WVA_ERR_ARG;
+  if (!ctx->calculated) { ctx->last_error = "wva_get_candidates before wva_calculate"; return WVA_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  const size_t P = (size_t)ctx->S * ctx->A;
+  if (P == 0) return WVA_OK;
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const CandView& c = ctx->cand;
+  struct { void* dst; const void* src; size_t b; } cp[] = {
+      {out->state, c.state, P}, {out->num_replicas, c.num_replicas, P * 4}, {out->batch_size, c.batch_size, P * 4},
+      {out->cost, c.cost, P * 4}, {out->value, c.value, P * 4}, {out->itl, c.itl, P * 4}, {out->ttft, c.ttft, P * 4},
+      {out->rho, c.rho, P * 4}, {out->max_arrv_rate, c.max_arrv_rate, P * 4}, {out->n_solves, c.n_solves, P * 4}};
+  for (auto& x : cp)
+    if (x.dst) CK(cudaMemcpyAsync(x.dst, x.src, x.b, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.d2h_ms = elapsed(ctx, 6, 7);
+  return WVA_OK;
+}
+
+int32_t wva_get_solution(wva_ctx* ctx, wva_solution* out) {
+  if (!ctx || !out) return WVA_ERR_ARG;
+  if (!ctx->solved) { ctx->last_error = "wva_get_solution before wva_solve"; return WVA_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  const size_t S = ctx->S, T = ctx->T;
+  // one contiguous D2H of the solution arena into pinned staging, then scatter to the caller
+  size_t bytes = ctx->sol_arena.cap;
+  CK(ctx->stage_out.reserve(bytes));
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  CK(cudaMemcpyAsync(ctx->stage_out.p, ctx->sol_arena.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.d2h_ms = elapsed(ctx, 6, 7);
+  const char* h = (const char*)ctx->stage_out.p;
+  const char* d = (const char*)ctx->sol_arena.p;
+  auto H = [&](const void* devp) { return h + ((const char*)devp - d); };
+  const SolView& v = ctx->sol;
+  if (out->state) memcpy(out->state, H(v.state), S);
+  if (out->acc) memcpy(out->acc, H(v.acc), S * 4);
+  if (out->num_replicas) memcpy(out->num_replicas, H(v.num_replicas), S * 4);
+  if (out->batch_size) memcpy(out->batch_size, H(v.batch_size), S * 4);
+  if (out->cost) memcpy(out->cost, H(v.cost), S * 4);
+  if (out->value) memcpy(out->value, H(v.value), S * 4);
+  if (out->itl) memcpy(out->itl, H(v.itl), S * 4);
+  if (out->ttft) memcpy(out->ttft, H(v.ttft), S * 4);
+  if (out->rho) memcpy(out->rho, H(v.rho), S * 4);
+  if (out->max_arrv_rate) memcpy(out->max_arrv_rate, H(v.max_arrv_rate), S * 4);
+  if (out->type_count) memcpy(out->type_count, H(ctx->d_type_count), T * 8);
+  if (out->type_cost) memcpy(out->type_cost, H(ctx->d_type_cost), T * 8);
+  return WVA_OK;
+}
+
+}  // extern "C"
+
+#include "capi_aux.inl"

@@ -1,0 +1,410 @@
+// capi_aux.inl — second half of the C-ABI implementation (included at the end of
+// capi.cu): replica grid, M/M/1/K leg, V1 saturation, limiter,
+// FP64 microbenchmarks.
+
+// ------------------------------------------------------------------ replica grid
+template <int WARPS>
+static cudaError_t launch_grid(wva_ctx* ctx, int blocks, size_t smem, int R, const GridOut& o, unsigned long long n_pairs,
+                               int nmax, GridCounters* ctr) {
+  auto k = grid_kernel<WARPS>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<blocks, WARPS * 32, smem, ctx->stream>>>(ctx->sys, R, o, n_pairs, nmax, ctr);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+// Runs the grid on the resident system and keeps the results in HBM.
+// full != 0 materialises ok/ttft/itl/rho/tput [S*A*R]; the frontier [S*A] is always produced.
+extern "C" int32_t wva_grid_run(wva_ctx* ctx, int32_t R, int32_t full) {
+  if (!ctx || R < 1) return WVA_ERR_ARG;
+  if (!ctx->loaded) { ctx->last_error = "wva_grid_run before wva_load_system"; return WVA_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  GridState& g = ctx->grid;
+  const size_t P = (size_t)ctx->S * ctx->A, n = P * (size_t)R;
+  Layout L;
+  size_t o_ctr = L.take(256), o_nmax = L.take(256), o_front = L.take(P * 4);
+  size_t o_ok = 0, o_ttft = 0, o_itl = 0, o_rho = 0, o_tput = 0;
+  if (full) { o_ok = L.take(n); o_ttft = L.take(n * 4); o_itl = L.take(n * 4); o_rho = L.take(n * 4); o_tput = L.take(n * 4); }
+  CK(g.buf.reserve(L.off + 256));
+  char* d = (char*)g.buf.p;
+  g.ctr = (GridCounters*)(d + o_ctr);
+  int* d_nmax = (int*)(d + o_nmax);
+  g.view.frontier = (int*)(d + o_front);
+  g.view.ok = full ? (unsigned char*)(d + o_ok) : nullptr;
+  g.view.ttft = full ? (float*)(d + o_ttft) : nullptr;
+  g.view.itl = full ? (float*)(d + o_itl) : nullptr;
+  g.view.rho = full ? (float*)(d + o_rho) : nullptr;
+  g.view.tput = full ? (float*)(d + o_tput) : nullptr;
+  g.R = R; g.full = full != 0; g.ran = false;
+  CK(cudaMemsetAsync(d, 0, 512, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (P > 0) {
+    int blocks = (int)((P + 255) / 256); if (blocks > 4096) blocks = 4096;
+    max_batch_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->sys, (unsigned long long)P, d_nmax);
+    ctx->launches++;
+    int nmax = 0;
+    CK(cudaMemcpyAsync(&nmax, d_nmax, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nmax < 1) nmax = 1;
+    if (nmax > 8192) { ctx->last_error = "grid: max batch size above 8192"; return WVA_ERR_LIMIT; }
+    // warps per CTA so that (a) the per-warp float32 tables fit and (b) >= 32 warps sit on an SM
+    const size_t per_warp = (size_t)nmax * 4;
+    cudaError_t e;
+    if (per_warp * 8 <= 48 * 1024) {
+      int per_sm = (int)((200 * 1024) / (per_warp * 8 + 1024)); if (per_sm > 8) per_sm = 8; if (per_sm < 1) per_sm = 1;
+      e = launch_grid<8>(ctx, ctx->sm_count * per_sm, per_warp * 8, R, g.view, P, nmax, g.ctr);
+    } else {
+      int per_sm = (int)((200 * 1024) / (per_warp * 4 + 1024)); if (per_sm > 8) per_sm = 8; if (per_sm < 1) per_sm = 1;
+      e = launch_grid<4>(ctx, ctx->sm_count * per_sm, per_warp * 4, R, g.view, P, nmax, g.ctr);
+    }
+    if (e != cudaSuccess) { ctx->last_error = std::string("grid launch: ") + cudaGetErrorString(e); return WVA_ERR_CUDA; }
+  }
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  GridCounters hc;
+  CK(cudaMemcpyAsync(&hc, g.ctr, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.grid_ms = elapsed(ctx, 2, 3);
+  ctx->timing.chain_solves = (int64_t)hc.solves;
+  ctx->timing.chain_states = (int64_t)hc.states;
+  ctx->timing.overflow_pairs = (int64_t)hc.overflow;
+  if (hc.limit_hit) { ctx->last_error = "grid: a pair needs a larger max batch size than the launch was built for"; return WVA_ERR_LIMIT; }
+  g.ran = true;
+  return WVA_OK;
+}
+
+extern "C" int32_t wva_grid_fetch(wva_ctx* ctx, uint8_t* ok, float* ttft, float* itl, float* rho, float* tput, int32_t* frontier) {
+  if (!ctx) return WVA_ERR_ARG;
+  GridState& g = ctx->grid;
+  if (!g.ran) { ctx->last_error = "wva_grid_fetch before wva_grid_run"; return WVA_ERR_STATE; }
+  if ((ok || ttft || itl || rho || tput) && !g.full) { ctx->last_error = "grid was run without full outputs"; return WVA_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  const size_t P = (size_t)ctx->S * ctx->A, n = P * (size_t)g.R;
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  if (ok && n) CK(cudaMemcpyAsync(ok, g.view.ok, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ttft && n) CK(cudaMemcpyAsync(ttft, g.view.ttft, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (itl && n) CK(cudaMemcpyAsync(itl, g.view.itl, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (rho && n) CK(cudaMemcpyAsync(rho, g.view.rho, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (tput && n) CK(cudaMemcpyAsync(tput, g.view.tput, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (frontier && P) CK(cudaMemcpyAsync(frontier, g.view.frontier, P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.d2h_ms = elapsed(ctx, 6, 7);
+  return WVA_OK;
+}
+
+extern "C" int32_t wva_analyze_grid(wva_ctx* ctx, int32_t R, uint8_t* ok, float* ttft, float* itl, float* rho, float* tput,
+                         int32_t* frontier) {
+  int32_t rc = wva_grid_run(ctx, R, (ok || ttft || itl || rho || tput) ? 1 : 0);
+  if (rc != WVA_OK) return rc;
+  return wva_grid_fetch(ctx, ok, ttft, itl, rho, tput, frontier);
+}
+
+// ------------------------------------------------------------------ M/M/1/K leg
+extern "C" int32_t wva_mm1k_eval(wva_ctx* ctx, int64_t n, const float* lambda, const float* mu, const int32_t* K, uint8_t* valid,
+                      float* avg_resp, float* avg_wait, float* avg_serv, float* avg_num, float* avg_queue,
+                      float* throughput, float* rho) {
+  if (!ctx || n < 0) return WVA_ERR_ARG;
+  if (n == 0) return WVA_OK;
+  if (!lambda || !mu || !K || !valid || !avg_resp || !avg_wait || !avg_serv || !avg_num || !avg_queue || !throughput || !rho)
+    return WVA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  Layout L;
+  size_t o_l = L.take(n * 4), o_m = L.take(n * 4), o_k = L.take(n * 4);
+  CK(ctx->io_in.reserve(L.off + 256));
+  Layout O;
+  size_t o_v = O.take(n), o_f[7];
+  for (int i = 0; i < 7; i++) o_f[i] = O.take(n * 4);
+  CK(ctx->io_out.reserve(O.off + 256));
+  char* di = (char*)ctx->io_in.p; char* dout = (char*)ctx->io_out.p;
+  CK(cudaMemcpyAsync(di + o_l, lambda, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(di + o_m, mu, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(di + o_k, K, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  mm1k_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+      n, (const float*)(di + o_l), (const float*)(di + o_m), (const int*)(di + o_k), (unsigned char*)(dout + o_v),
+      (float*)(dout + o_f[0]), (float*)(dout + o_f[1]), (float*)(dout + o_f[2]), (float*)(dout + o_f[3]),
+      (float*)(dout + o_f[4]), (float*)(dout + o_f[5]), (float*)(dout + o_f[6]));
+  ctx->launches++;
+  CK(cudaGetLastError());
+  float* dst[7] = {avg_resp, avg_wait, avg_serv, avg_num, avg_queue, throughput, rho};
+  CK(cudaMemcpyAsync(valid, dout + o_v, n, cudaMemcpyDeviceToHost, ctx->stream));
+  for (int i = 0; i < 7; i++) CK(cudaMemcpyAsync(dst[i], dout + o_f[i], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WVA_OK;
+}
+
+// ------------------------------------------------------------------ V1 saturation
+extern "C" int32_t wva_saturation_upload(wva_ctx* ctx, const wva_saturation_in* in) {
+  if (!ctx || !in) return WVA_ERR_ARG;
+  const long long M = in->n_models, V = in->n_variants, P = in->n_replicas;
+  if (M < 0 || V < 0 || P < 0 || P > 0x7fffffffLL || V > 0x7fffffffLL) return WVA_ERR_ARG;
+  if (!in->model_variant_off || !in->variant_replica_off) return WVA_ERR_ARG;
+  if (in->model_variant_off[0] != 0 || in->model_variant_off[M] != V || in->variant_replica_off[0] != 0 ||
+      in->variant_replica_off[V] != P)
+    return WVA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  SatState& st = ctx->sat;
+  Layout L;
+  size_t o_mvo = L.take((M + 1) * 4), o_vro = L.take((V + 1) * 4), o_kv = L.take(P * 8), o_q = L.take(P * 8),
+         o_cost = L.take(V * 8), o_cur = L.take(V * 4), o_des = L.take(V * 4), o_pen = L.take(V * 4), o_hs = L.take(V),
+         o_c0 = L.take(M * 8), o_c1 = L.take(M * 8), o_c2 = L.take(M * 8), o_c3 = L.take(M * 8);
+  CK(st.in.reserve(L.off + 256));
+  char* d = (char*)st.in.p;
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  struct { size_t off; const void* src; size_t b; } cp[] = {
+      {o_mvo, in->model_variant_off, (size_t)(M + 1) * 4}, {o_vro, in->variant_replica_off, (size_t)(V + 1) * 4},
+      {o_kv, in->rep_kv, (size_t)P * 8}, {o_q, in->rep_queue, (size_t)P * 8}, {o_cost, in->var_cost, (size_t)V * 8},
+      {o_cur, in->var_current, (size_t)V * 4}, {o_des, in->var_desired, (size_t)V * 4}, {o_pen, in->var_pending, (size_t)V * 4},
+      {o_hs, in->var_has_state, in->var_has_state ? (size_t)V : 0},
+      {o_c0, in->cfg_kv_threshold, (size_t)M * 8}, {o_c1, in->cfg_queue_threshold, (size_t)M * 8},
+      {o_c2, in->cfg_kv_trigger, (size_t)M * 8}, {o_c3, in->cfg_queue_trigger, (size_t)M * 8}};
+  for (auto& x : cp) {
+    if (x.b == 0) continue;
+    if (!x.src) return WVA_ERR_ARG;
+    CK(cudaMemcpyAsync(d + x.off, x.src, x.b, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  SatIn& v = st.vin;
+  v.n_models = M; v.n_variants = V; v.n_replicas = P;
+  v.model_variant_off = (const int*)(d + o_mvo); v.variant_replica_off = (const int*)(d + o_vro);
+  v.rep_kv = (const double*)(d + o_kv); v.rep_queue = (const long long*)(d + o_q);
+  v.var_cost = (const double*)(d + o_cost); v.var_current = (const int*)(d + o_cur);
+  v.var_desired = (const int*)(d + o_des); v.var_pending = (const int*)(d + o_pen);
+  v.var_has_state = in->var_has_state ? (const unsigned char*)(d + o_hs) : nullptr;
+  v.cfg_kv_threshold = (const double*)(d + o_c0); v.cfg_queue_threshold = (const double*)(d + o_c1);
+  v.cfg_kv_trigger = (const double*)(d + o_c2); v.cfg_queue_trigger = (const double*)(d + o_c3);
+  // output arena
+  Layout O;
+  size_t q_part = O.take(64), q_t = O.take(V * 4), q_rc = O.take(V * 4), q_ns = O.take(V * 4), q_mk = O.take(V * 8),
+         q_mq = O.take(V * 8), q_ak = O.take(V * 8), q_aq = O.take(V * 8), q_rs = O.take(P), q_mt = O.take(M * 4),
+         q_mn = O.take(M * 4), q_mak = O.take(M * 8), q_maq = O.take(M * 8), q_mf = O.take(M);
+  CK(st.out.reserve(O.off + 256));
+  st.out_bytes = O.off;
+  char* o = (char*)st.out.p;
+  SatOut& w = st.vout;
+  w.partials = (long long*)(o + q_part); w.var_target = (int*)(o + q_t); w.var_replica_count = (int*)(o + q_rc);
+  w.var_non_saturated = (int*)(o + q_ns); w.var_max_kv = (double*)(o + q_mk); w.var_max_queue = (long long*)(o + q_mq);
+  w.var_avg_spare_kv = (double*)(o + q_ak); w.var_avg_spare_queue = (double*)(o + q_aq);
+  w.rep_saturated = (unsigned char*)(o + q_rs); w.mod_total_replicas = (int*)(o + q_mt);
+  w.mod_non_saturated = (int*)(o + q_mn); w.mod_avg_spare_kv = (double*)(o + q_mak);
+  w.mod_avg_spare_queue = (double*)(o + q_maq); w.mod_flags = (unsigned char*)(o + q_mf);
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.h2d_ms = elapsed(ctx, 0, 1);
+  st.M = M; st.V = V; st.P = P; st.uploaded = true; st.ran = false;
+  return WVA_OK;
+}
+
+// detail != 0 also materialises the per-variant / per-replica / per-model analysis fields;
+// detail == 0 writes only targets, model flags and the shard partials.
+extern "C" int32_t wva_saturation_run(wva_ctx* ctx, int32_t detail) {
+  if (!ctx) return WVA_ERR_ARG;
+  SatState& st = ctx->sat;
+  if (!st.uploaded) { ctx->last_error = "wva_saturation_run before wva_saturation_upload"; return WVA_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  SatOut w = st.vout;
+  if (!detail) {
+    w.var_replica_count = nullptr; w.var_non_saturated = nullptr; w.var_max_kv = nullptr; w.var_max_queue = nullptr;
+    w.var_avg_spare_kv = nullptr; w.var_avg_spare_queue = nullptr; w.rep_saturated = nullptr;
+    w.mod_total_replicas = nullptr; w.mod_non_saturated = nullptr; w.mod_avg_spare_kv = nullptr;
+    w.mod_avg_spare_queue = nullptr;
+  }
+  CK(cudaMemsetAsync(w.partials, 0, 64, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (st.M > 0) {
+    long long warps = st.M;
+    long long blocks = (warps * 32 + 255) / 256;
+    long long cap = (long long)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    saturation_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(st.vin, w);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.saturation_ms = elapsed(ctx, 2, 3);
+  st.ran = true;
+  return WVA_OK;
+}
+
+extern "C" int32_t wva_saturation_fetch(wva_ctx* ctx, const wva_saturation_out* out) {
+  if (!ctx || !out) return WVA_ERR_ARG;
+  SatState& st = ctx->sat;
+  if (!st.ran) { ctx->last_error = "wva_saturation_fetch before wva_saturation_run"; return WVA_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  const size_t M = st.M, V = st.V, P = st.P;
+  const SatOut& w = st.vout;
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  struct { void* dst; const void* src; size_t b; } cp[] = {
+      {out->var_target, w.var_target, V * 4}, {out->var_replica_count, w.var_replica_count, V * 4},
+      {out->var_non_saturated, w.var_non_saturated, V * 4}, {out->var_max_kv, w.var_max_kv, V * 8},
+      {out->var_max_queue, w.var_max_queue, V * 8}, {out->var_avg_spare_kv, w.var_avg_spare_kv, V * 8},
+      {out->var_avg_spare_queue, w.var_avg_spare_queue, V * 8}, {out->rep_saturated, w.rep_saturated, P},
+      {out->mod_total_replicas, w.mod_total_replicas, M * 4}, {out->mod_non_saturated, w.mod_non_saturated, M * 4},
+      {out->mod_avg_spare_kv, w.mod_avg_spare_kv, M * 8}, {out->mod_avg_spare_queue, w.mod_avg_spare_queue, M * 8},
+      {out->mod_flags, w.mod_flags, M}, {out->partials, w.partials, 32}};
+  for (auto& x : cp)
+    if (x.dst && x.b) CK(cudaMemcpyAsync(x.dst, x.src, x.b, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.d2h_ms = elapsed(ctx, 6, 7);
+  return WVA_OK;
+}
+
+extern "C" int32_t wva_saturation_v1(wva_ctx* ctx, const wva_saturation_in* in, const wva_saturation_out* out) {
+  if (!out) return WVA_ERR_ARG;
+  int32_t rc = wva_saturation_upload(ctx, in);
+  if (rc != WVA_OK) return rc;
+  bool detail = out->var_replica_count || out->var_non_saturated || out->var_max_kv || out->var_max_queue ||
+                out->var_avg_spare_kv || out->var_avg_spare_queue || out->rep_saturated || out->mod_total_replicas ||
+                out->mod_non_saturated || out->mod_avg_spare_kv || out->mod_avg_spare_queue;
+  rc = wva_saturation_run(ctx, detail ? 1 : 0);
+  if (rc != WVA_OK) return rc;
+  return wva_saturation_fetch(ctx, out);
+}
+
+// ------------------------------------------------------------------ limiter
+extern "C" int32_t wva_limit(wva_ctx* ctx, int64_t D, int32_t T, const int32_t* acc_type, const int32_t* current,
+                  const int32_t* target, const int32_t* gpr, const double* spare, const double* cost,
+                  const int32_t* type_limit, int32_t* out_target, int32_t* out_gpus, uint8_t* out_limited) {
+  if (!ctx || D < 0 || T < 0 || D > 0x7fffffffLL) return WVA_ERR_ARG;
+  if (D == 0) return WVA_OK;   // default_limiter.go:43-45
+  if (!acc_type || !current || !target || !gpr || !spare || !cost || !out_target || !out_gpus || !out_limited ||
+      (T > 0 && !type_limit))
+    return WVA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)D;
+  Layout L;
+  size_t o_at = L.take(n * 4), o_cur = L.take(n * 4), o_tgt = L.take(n * 4), o_gpr = L.take(n * 4), o_sp = L.take(n * 8),
+         o_co = L.take(n * 8), o_lim = L.take((size_t)(T + 1) * 4);
+  CK(ctx->io_in.reserve(L.off + 256));
+  char* di = (char*)ctx->io_in.p;
+  Layout O;
+  size_t q_used = O.take((size_t)(T + 1) * 8), q_ncand = O.take(64), q_flag = O.take(n), q_ot = O.take(n * 4), q_og = O.take(n * 4),
+         q_ol = O.take(n), q_idxA = O.take(n * 4), q_idxB = O.take(n * 4), q_kA = O.take(n * 8), q_kB = O.take(n * 8),
+         q_tA = O.take(n * 4), q_tB = O.take(n * 4), q_req = O.take(n * 8), q_pre = O.take(n * 8);
+  size_t tmp_bytes = 0, tb;
+  {
+    cub::CountingInputIterator<int> cnt(0);
+    cub::DeviceSelect::Flagged(nullptr, tb, cnt, (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, (int)n, ctx->stream);
+    tmp_bytes = tb;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr,
+                                    (int*)nullptr, (int)n, 0, 64, ctx->stream);
+    if (tb > tmp_bytes) tmp_bytes = tb;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int)n, 0, 8,
+                                    ctx->stream);
+    if (tb > tmp_bytes) tmp_bytes = tb;
+    cub::DeviceScan::ExclusiveSumByKey(nullptr, tb, (int*)nullptr, (long long*)nullptr, (long long*)nullptr, (int)n,
+                                       cub::Equality(), ctx->stream);
+    if (tb > tmp_bytes) tmp_bytes = tb;
+  }
+  size_t q_tmp = O.take(tmp_bytes + 256);
+  CK(ctx->io_out.reserve(O.off + 256));
+  char* dd = (char*)ctx->io_out.p;
+  CK(cudaMemcpyAsync(di + o_at, acc_type, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(di + o_cur, current, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(di + o_tgt, target, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(di + o_gpr, gpr, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(di + o_sp, spare, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(di + o_co, cost, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (T > 0) CK(cudaMemcpyAsync(di + o_lim, type_limit, (size_t)T * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const int* d_at = (const int*)(di + o_at); const int* d_cur = (const int*)(di + o_cur); const int* d_tgt = (const int*)(di + o_tgt);
+  const int* d_gpr = (const int*)(di + o_gpr); const double* d_sp = (const double*)(di + o_sp); const double* d_co = (const double*)(di + o_co);
+  const int* d_lim = (const int*)(di + o_lim);
+  long long* d_used = (long long*)(dd + q_used); int* d_ncand = (int*)(dd + q_ncand);
+  unsigned char* d_flag = (unsigned char*)(dd + q_flag);
+  int* d_ot = (int*)(dd + q_ot); int* d_og = (int*)(dd + q_og); unsigned char* d_ol = (unsigned char*)(dd + q_ol);
+  int* idxA = (int*)(dd + q_idxA); int* idxB = (int*)(dd + q_idxB);
+  unsigned long long* kA = (unsigned long long*)(dd + q_kA); unsigned long long* kB = (unsigned long long*)(dd + q_kB);
+  int* tA = (int*)(dd + q_tA); int* tB = (int*)(dd + q_tB);
+  long long* d_req = (long long*)(dd + q_req); long long* d_pre = (long long*)(dd + q_pre);
+  void* d_tmp = dd + q_tmp;
+  CK(cudaMemsetAsync(d_used, 0, (size_t)(T + 1) * 8, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  limiter_prepare_kernel<<<nb, 256, 0, ctx->stream>>>((long long)n, T, d_at, d_cur, d_tgt, d_gpr, d_used, d_flag, d_ot, d_og, d_ol);
+  ctx->launches++;
+  {
+    cub::CountingInputIterator<int> cnt(0);
+    size_t tb2 = tmp_bytes;
+    CK(cub::DeviceSelect::Flagged(d_tmp, tb2, cnt, d_flag, idxA, d_ncand, (int)n, ctx->stream));
+    ctx->launches++;
+  }
+  int nc = 0;
+  CK(cudaMemcpyAsync(&nc, d_ncand, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (nc > 0) {
+    const unsigned cb = (unsigned)((nc + 255) / 256);
+    size_t tb2;
+    // pass 1: by cost (payload = ascending decision index -> stable tie-break)
+    limiter_keys_kernel<<<cb, 256, 0, ctx->stream>>>(nc, T, idxA, d_at, d_sp, d_co, kA, kB);
+    tb2 = tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp, tb2, kA, kB, idxA, idxB, nc, 0, 64, ctx->stream));
+    // pass 2: by spare capacity
+    limiter_gather_kernel<<<cb, 256, 0, ctx->stream>>>(nc, T, idxB, d_at, d_cur, d_tgt, d_gpr, d_sp, kA, nullptr, nullptr);
+    tb2 = tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp, tb2, kA, kB, idxB, idxA, nc, 0, 64, ctx->stream));
+    // pass 3: by accelerator type (segments)
+    limiter_gather_kernel<<<cb, 256, 0, ctx->stream>>>(nc, T, idxA, d_at, d_cur, d_tgt, d_gpr, d_sp, nullptr, tA, nullptr);
+    tb2 = tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp, tb2, tA, tB, idxA, idxB, nc, 0, 8, ctx->stream));
+    // requested GPUs in final order, segmented exclusive scan, apply
+    limiter_gather_kernel<<<cb, 256, 0, ctx->stream>>>(nc, T, idxB, d_at, d_cur, d_tgt, d_gpr, d_sp, nullptr, nullptr, d_req);
+    tb2 = tmp_bytes;
+    CK(cub::DeviceScan::ExclusiveSumByKey(d_tmp, tb2, tB, d_req, d_pre, nc, cub::Equality(), ctx->stream));
+    limiter_apply_kernel<<<cb, 256, 0, ctx->stream>>>(nc, T, idxB, tB, d_req, d_pre, d_used, d_lim, d_cur, d_tgt, d_gpr, d_ot, d_og, d_ol);
+    ctx->launches += 9;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CK(cudaMemcpyAsync(out_target, d_ot, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_gpus, d_og, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_limited, d_ol, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.limit_ms = elapsed(ctx, 2, 3);
+  return WVA_OK;
+}
+
+// ------------------------------------------------------------------ FP64 microbenchmarks
+__global__ void __launch_bounds__(256) mb_dfma_kernel(double* out, int iters) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+  double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+    a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void __launch_bounds__(256) mb_ddiv_kernel(double* out, int iters) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+  const double m = 1.000001;
+  for (int i = 0; i < iters; i++) {
+    a0 = __ddiv_rn(a0, m); a1 = __ddiv_rn(a1, m); a2 = __ddiv_rn(a2, m); a3 = __ddiv_rn(a3, m);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3;
+}
+
+// peak double-precision FMA and IEEE-divide instruction throughput (lane-ops per second)
+extern "C" int32_t wva_microbench_fp64(wva_ctx* ctx, double* dfma_per_s, double* ddiv_per_s) {
+  if (!ctx || !dfma_per_s || !ddiv_per_s) return WVA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  CK(ctx->io_out.reserve((size_t)blocks * threads * 8));
+  double* d = (double*)ctx->io_out.p;
+  const int it_fma = 20000, it_div = 4000;
+  float best_fma = 1e30f, best_div = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    mb_dfma_kernel<<<blocks, threads, 0, ctx->stream>>>(d, it_fma);
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    mb_ddiv_kernel<<<blocks, threads, 0, ctx->stream>>>(d, it_div);
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 2;
+    float a = elapsed(ctx, 2, 3), b = elapsed(ctx, 3, 4);
+    if (rep > 0) { if (a < best_fma) best_fma = a; if (b < best_div) best_div = b; }
+  }
+  *dfma_per_s = (double)blocks * threads * 8.0 * it_fma / (best_fma * 1e-3);
+  *ddiv_per_s = (double)blocks * threads * 4.0 * it_div / (best_div * 1e-3);
+  return WVA_OK;
+}

@@ -1,0 +1,164 @@
+// grid_kernel.cuh — replica-grid evaluator: for every (server, accelerator, r) one
+// QueueAnalyzer.Analyze(totalRate / r) (pkg/analyzer/queueanalyzer.go:127-167), the
+// call CreateAllocation makes at pkg/core/allocation.go:140-148 with numReplicas = r.
+//
+// Mapping: one warp per (server, accelerator) pair.  The pair's head table mu_n is
+// built once by the warp into shared memory; the 32 lanes then pull replica levels
+// r = 1, 2, ... from a warp-local counter (largest arrival rate first) and each runs
+// its own chain solve through the same flattened state machine as the sizer, so a
+// lane that finishes early immediately starts the next replica level.  The per-pair
+// frontier (smallest r meeting every SLO) is a warp-shuffle min.
+#pragma once
+#include "wva_core.cuh"
+
+namespace wva {
+
+struct GridOut {
+  unsigned char* ok;
+  float *ttft, *itl, *rho, *tput;
+  int* frontier;
+};
+
+struct GridCounters {
+  unsigned long long next_pair, solves, states, overflow;
+  int limit_hit;
+};
+
+// per-pair preparation shared by all lanes of the warp; false -> every level is "not ok"
+__device__ __forceinline__ bool grid_setup(PairModel& m, const SysView& s, int srv, int acc, int n_limit,
+                                           float* total_rate, float* slo_ttft, float* slo_itl, float* slo_tps,
+                                           int* limit_hit) {
+  float arrival = s.srv_arrival[srv];
+  int in_tok = s.srv_in_tokens[srv], out_tok = s.srv_out_tokens[srv];
+  int model = s.srv_model[srv];
+  if (arrival < 0.0f || in_tok < 0 || out_tok < 0 || model < 0 || model >= s.n_models) return false;
+  size_t pi = (size_t)model * s.n_acc + acc;
+  if (!s.perf_present[pi] || !s.srv_target_present[srv] || arrival == 0.0f || out_tok == 0) return false;
+  long long N;
+  if (s.srv_max_batch[srv] > 0) N = s.srv_max_batch[srv];
+  else { N = (long long)s.perf_max_batch[pi] * s.perf_at_tokens[pi] / out_tok; if (N < 1) N = 1; }
+  if (N > n_limit) { *limit_hit = 1; return false; }
+  model_init(m, s.perf_alpha[pi], s.perf_beta[pi], s.perf_gamma[pi], in_tok, out_tok, (int)N);
+  *slo_ttft = s.srv_slo_ttft[srv]; *slo_itl = s.srv_slo_itl[srv]; *slo_tps = s.srv_slo_tps[srv];
+  *total_rate = (*slo_tps == 0.0f) ? f_div(arrival, 60.0f) : f_div(*slo_tps, (float)out_tok);
+  return true;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax, GridCounters* ctr) {
+  extern __shared__ float smem_tab[];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tab = smem_tab + (size_t)warp * nmax;
+  unsigned long long my_solves = 0, my_states = 0;
+
+  while (true) {
+    unsigned long long pair = 0;
+    if (lane == 0) pair = atomicAdd(&ctr->next_pair, 1ull);
+    pair = __shfl_sync(full, pair, 0);
+    if (pair >= n_pairs) break;
+    const int srv = (int)(pair / (unsigned)s.n_acc), acc = (int)(pair % (unsigned)s.n_acc);
+    const size_t obase = (size_t)pair * (size_t)R;
+    PairModel m;
+    float total_rate = 0, slo_ttft = 0, slo_itl = 0, slo_tps = 0;
+    int lim = 0;
+    bool valid = grid_setup(m, s, srv, acc, nmax, &total_rate, &slo_ttft, &slo_itl, &slo_tps, &lim);
+    if (lim && lane == 0) ctr->limit_hit = 1;
+    if (!valid) {
+      for (int r = lane; r < R; r += 32) {
+        if (out.ok) out.ok[obase + r] = 0;
+        if (out.ttft) out.ttft[obase + r] = 0.0f;
+        if (out.itl) out.itl[obase + r] = 0.0f;
+        if (out.rho) out.rho[obase + r] = 0.0f;
+        if (out.tput) out.tput[obase + r] = 0.0f;
+      }
+      if (out.frontier && lane == 0) out.frontier[pair] = 0;
+      continue;
+    }
+    __syncwarp();
+    model_fill_table(m, tab, 1, lane, 32);
+    __syncwarp();
+    model_finish(m, tab, 1);
+    const float lambda_tps = f_mul(m.lambda_max, f_sub(1.0f, WVA_STABILITY_SAFETY));
+
+    Chain c;
+    SolveStats st;
+    bool live = false;
+    int my_r = 0, next_r = 1, front = 0x7fffffff;
+    float my_rate = 0.0f;
+    while (true) {
+      // hand out replica levels to idle lanes (warp-uniform counter)
+      unsigned want = __ballot_sync(full, !live);
+      if (want && next_r <= R) {
+        int rank = __popc(want & ((1u << lane) - 1u));
+        if (!live) {
+          int r = next_r + rank;
+          if (r <= R) {
+            my_r = r;
+            my_rate = f_div(total_rate, (float)r);
+            if (analyze_admits(m, my_rate)) {
+              chain_start(c, f_div(my_rate, 1000.0f));
+              c.tail_ok = d_bits(c.lamg) <= d_bits(m.mu_last);
+              live = true;
+              my_solves++;
+            } else {
+              size_t o = obase + (size_t)(r - 1);
+              if (out.ok) out.ok[o] = 0;
+              if (out.ttft) out.ttft[o] = 0.0f;
+              if (out.itl) out.itl[o] = 0.0f;
+              if (out.rho) out.rho[o] = 0.0f;
+              if (out.tput) out.tput[o] = 0.0f;
+            }
+          }
+        }
+        next_r += __popc(want);
+      }
+      if (!__any_sync(full, live)) { if (next_r > R) break; else continue; }
+      for (int it = 0; it < 64; it++) {
+        if (live) {
+          if (chain_step(c, m, st)) {
+            live = false;
+            my_states += c.states;
+            size_t o = obase + (size_t)(my_r - 1);
+            if (c.phase == CH_OVERFLOW) {
+              // recorded; the exact overflow-rescale path is only wired for the sizer
+              if (lane >= 0) atomicAdd(&ctr->overflow, 1ull);
+              if (out.ok) out.ok[o] = 0;
+              if (out.ttft) out.ttft[o] = 0.0f;
+              if (out.itl) out.itl[o] = 0.0f;
+              if (out.rho) out.rho[o] = 0.0f;
+              if (out.tput) out.tput[o] = 0.0f;
+            } else {
+              // Analyze: queueanalyzer.go:143-166
+              float pf = prefill_time(m, st.avgNumInServers);
+              float dec = f_div(f_sub(st.avgServTime, pf), m.out_tok);
+              float avg_ttft = f_add(f_add(st.avgWaitTime, pf), dec);
+              float rho = f_div(st.avgNumInServers, (float)m.N);
+              rho = fminf(fmaxf(rho, 0.0f), 1.0f);
+              if (out.ok) out.ok[o] = 1;
+              if (out.ttft) out.ttft[o] = f_add(st.avgWaitTime, pf);   // allocation.go:148
+              if (out.itl) out.itl[o] = dec;
+              if (out.rho) out.rho[o] = rho;
+              if (out.tput) out.tput[o] = f_mul(st.throughput, 1000.0f);
+              bool meets = (slo_ttft <= 0.0f || avg_ttft <= slo_ttft) && (slo_itl <= 0.0f || dec <= slo_itl) &&
+                           (slo_tps <= 0.0f || f_div(my_rate, 1000.0f) <= lambda_tps);
+              if (meets && my_r < front) front = my_r;
+            }
+          }
+        }
+        if ((it & 7) == 7 && (!__any_sync(full, live) || (next_r <= R && __any_sync(full, !live)))) break;
+      }
+    }
+    for (int o = 16; o; o >>= 1) front = min(front, __shfl_down_sync(full, front, o));
+    if (out.frontier && lane == 0) out.frontier[pair] = (front == 0x7fffffff) ? 0 : front;
+    __syncwarp();
+  }
+  for (int o = 16; o; o >>= 1) {
+    my_solves += __shfl_down_sync(full, my_solves, o);
+    my_states += __shfl_down_sync(full, my_states, o);
+  }
+  if (lane == 0) { atomicAdd(&ctr->solves, my_solves); atomicAdd(&ctr->states, my_states); }
+}
+
+}  // namespace wva

@@ -1,0 +1,236 @@
+"""Python binding of the C-ABI (include/wva_b200.h) — the call path tests/ and bench.py use.
+
+``Engine`` owns one ``wva_ctx`` (one GPU).  Method names mirror the reference
+entry points they replace:
+
+    load_system      System.SetFromSpec           pkg/core/system.go:82
+    calculate        System.Calculate             pkg/core/system.go:258
+    solve            Manager.Optimize             pkg/manager/manager.go:21
+    candidates       Server.AllAllocations        pkg/core/server.go:138
+    solution         System.GenerateSolution      pkg/core/system.go:303
+    analyze_grid     QueueAnalyzer.Analyze grid   pkg/analyzer/queueanalyzer.go:127
+    mm1k_eval        MM1KModel.Solve              pkg/analyzer/mm1kmodel.go:30
+    saturation_v1    AnalyzeModelSaturation + CalculateSaturationTargets
+                                                  internal/saturation/analyzer.go:31,290
+    limit            DefaultLimiter.Limit         internal/engines/pipeline/default_limiter.go:42
+
+There is no CPU fallback: a missing library or a missing GPU raises WvaError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class WvaError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "csrc", "libwva_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen csrc/libwva_b200.so (built in-tree by __graft_entry__.build()); raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise WvaError(f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(p)
+    ctxp = C.c_void_p
+    L.wva_create.argtypes = [C.c_int32, C.POINTER(ctxp)]
+    L.wva_destroy.argtypes = [ctxp]
+    L.wva_strerror.argtypes = [C.c_int32]
+    L.wva_strerror.restype = C.c_char_p
+    L.wva_last_error.argtypes = [ctxp]
+    L.wva_last_error.restype = C.c_char_p
+    L.wva_launch_count.argtypes = [ctxp]
+    L.wva_launch_count.restype = C.c_int64
+    L.wva_load_system.argtypes = [ctxp, C.POINTER(abi.System)]
+    L.wva_calculate.argtypes = [ctxp]
+    L.wva_solve.argtypes = [ctxp]
+    L.wva_get_candidates.argtypes = [ctxp, C.POINTER(abi.Candidates)]
+    L.wva_get_solution.argtypes = [ctxp, C.POINTER(abi.Solution)]
+    L.wva_analyze_grid.argtypes = [ctxp, C.c_int32] + [C.c_void_p] * 6
+    L.wva_grid_run.argtypes = [ctxp, C.c_int32, C.c_int32]
+    L.wva_grid_fetch.argtypes = [ctxp] + [C.c_void_p] * 6
+    L.wva_saturation_upload.argtypes = [ctxp, C.POINTER(abi.SaturationIn)]
+    L.wva_saturation_run.argtypes = [ctxp, C.c_int32]
+    L.wva_saturation_fetch.argtypes = [ctxp, C.POINTER(abi.SaturationOut)]
+    L.wva_mm1k_eval.argtypes = [ctxp, C.c_int64] + [C.c_void_p] * 11
+    L.wva_saturation_v1.argtypes = [ctxp, C.POINTER(abi.SaturationIn), C.POINTER(abi.SaturationOut)]
+    L.wva_limit.argtypes = [ctxp, C.c_int64, C.c_int32] + [C.c_void_p] * 10
+    L.wva_last_timing.argtypes = [ctxp, C.POINTER(abi.Timing)]
+    L.wva_microbench_fp64.argtypes = [ctxp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+EXPORTS = ["wva_create", "wva_destroy", "wva_strerror", "wva_last_error", "wva_launch_count",
+           "wva_load_system", "wva_calculate", "wva_solve", "wva_get_candidates", "wva_get_solution",
+           "wva_analyze_grid", "wva_grid_run", "wva_grid_fetch", "wva_mm1k_eval", "wva_saturation_v1",
+           "wva_saturation_upload", "wva_saturation_run", "wva_saturation_fetch", "wva_limit", "wva_last_timing",
+           "wva_microbench_fp64"]
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.wva_create(device, C.byref(self.ctx))
+        if rc != abi.WVA_OK:
+            self.ctx = None
+            raise WvaError(f"wva_create(device={device}) failed: {self.lib.wva_strerror(rc).decode()}")
+        self.S = self.A = self.T = 0
+
+    def _check(self, rc, what):
+        if rc != abi.WVA_OK:
+            detail = self.lib.wva_last_error(self.ctx).decode()
+            raise WvaError(f"{what}: {self.lib.wva_strerror(rc).decode()} {detail}")
+
+    def close(self):
+        if self.ctx:
+            self.lib.wva_destroy(self.ctx)
+            self.ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- queueing sizing + allocator ------------------------------------------------------
+    def load_system(self, sysd: dict):
+        st, keep = abi.make_system(sysd)
+        self._check(self.lib.wva_load_system(self.ctx, C.byref(st)), "wva_load_system")
+        self.S, self.A, self.T = st.n_servers, st.n_acc, st.n_types
+
+    def calculate(self):
+        self._check(self.lib.wva_calculate(self.ctx), "wva_calculate")
+
+    def solve(self):
+        self._check(self.lib.wva_solve(self.ctx), "wva_solve")
+
+    def candidates(self):
+        cst, cand = abi.alloc_candidates(self.S, self.A)
+        self._check(self.lib.wva_get_candidates(self.ctx, C.byref(cst)), "wva_get_candidates")
+        return cand
+
+    def solution(self):
+        sst, sol = abi.alloc_solution(self.S, self.T)
+        self._check(self.lib.wva_get_solution(self.ctx, C.byref(sst)), "wva_get_solution")
+        return sol
+
+    def optimize(self, sysd: dict):
+        """The whole reference path in one call: SetFromSpec -> Calculate -> Optimize -> solution."""
+        self.load_system(sysd)
+        self.calculate()
+        self.solve()
+        return self.solution()
+
+    def analyze_grid(self, R: int, full: bool = True, frontier: bool = True):
+        S, A = self.S, self.A
+        n = S * A * R
+        out = {}
+        if full:
+            out["ok"] = np.zeros(max(n, 1), dtype=np.uint8)
+            for k in ("ttft", "itl", "rho", "tput"):
+                out[k] = np.zeros(max(n, 1), dtype=np.float32)
+        if frontier:
+            out["frontier"] = np.zeros(max(S * A, 1), dtype=np.int32)
+        p = lambda k: out[k].ctypes.data if k in out else None
+        self._check(self.lib.wva_analyze_grid(self.ctx, R, p("ok"), p("ttft"), p("itl"), p("rho"), p("tput"),
+                                              p("frontier")), "wva_analyze_grid")
+        for k in list(out):
+            out[k] = out[k][: S * A].reshape(S, A) if k == "frontier" else out[k][:n].reshape(S, A, R)
+        return out
+
+    def grid_run(self, R: int, full: bool = False):
+        """Grid on the resident system, results stay in HBM (bench: device-resident timing)."""
+        self._check(self.lib.wva_grid_run(self.ctx, R, 1 if full else 0), "wva_grid_run")
+
+    def grid_fetch_frontier(self):
+        f = np.zeros(max(self.S * self.A, 1), dtype=np.int32)
+        self._check(self.lib.wva_grid_fetch(self.ctx, None, None, None, None, None, f.ctypes.data), "wva_grid_fetch")
+        return f[: self.S * self.A].reshape(self.S, self.A)
+
+    def mm1k_eval(self, lam, mu, K):
+        lam = np.ascontiguousarray(lam, np.float32); mu = np.ascontiguousarray(mu, np.float32)
+        K = np.ascontiguousarray(K, np.int32)
+        n = lam.size
+        names = ("avg_resp", "avg_wait", "avg_serv", "avg_num", "avg_queue", "throughput", "rho")
+        out = {"valid": np.zeros(max(n, 1), np.uint8)}
+        for k in names:
+            out[k] = np.zeros(max(n, 1), np.float32)
+        self._check(self.lib.wva_mm1k_eval(self.ctx, n, lam.ctypes.data, mu.ctypes.data, K.ctypes.data,
+                                           out["valid"].ctypes.data, *[out[k].ctypes.data for k in names]),
+                    "wva_mm1k_eval")
+        return {k: v[:n] for k, v in out.items()}
+
+    # ---- saturation + limiter ---------------------------------------------------------------
+    def saturation_v1(self, d: dict):
+        ist, keep = abi.make_saturation_in(d)
+        ost, out = abi.alloc_saturation_out(ist.n_models, ist.n_variants, ist.n_replicas)
+        self._check(self.lib.wva_saturation_v1(self.ctx, C.byref(ist), C.byref(ost)), "wva_saturation_v1")
+        return out
+
+    def saturation_upload(self, d: dict):
+        ist, keep = abi.make_saturation_in(d)
+        self._check(self.lib.wva_saturation_upload(self.ctx, C.byref(ist)), "wva_saturation_upload")
+        self._sat_dims = (ist.n_models, ist.n_variants, ist.n_replicas)
+
+    def saturation_run(self, detail: bool = False):
+        self._check(self.lib.wva_saturation_run(self.ctx, 1 if detail else 0), "wva_saturation_run")
+
+    def saturation_fetch(self, detail: bool = False):
+        M, V, P = self._sat_dims
+        ost, out = abi.alloc_saturation_out(M, V, P)
+        if not detail:
+            for k in ("var_replica_count", "var_non_saturated", "var_max_kv", "var_max_queue", "var_avg_spare_kv",
+                      "var_avg_spare_queue", "rep_saturated", "mod_total_replicas", "mod_non_saturated",
+                      "mod_avg_spare_kv", "mod_avg_spare_queue"):
+                setattr(ost, k, None)
+        self._check(self.lib.wva_saturation_fetch(self.ctx, C.byref(ost)), "wva_saturation_fetch")
+        return out
+
+    def limit(self, d: dict):
+        D = len(d["current"])
+        arr = {k: np.ascontiguousarray(d[k], dt) for k, dt in
+               (("acc_type", np.int32), ("current", np.int32), ("target", np.int32),
+                ("gpus_per_replica", np.int32), ("spare", np.float64), ("cost", np.float64),
+                ("type_limit", np.int32))}
+        out = {"target": np.zeros(max(D, 1), np.int32), "gpus_allocated": np.zeros(max(D, 1), np.int32),
+               "was_limited": np.zeros(max(D, 1), np.uint8)}
+        self._check(self.lib.wva_limit(self.ctx, D, int(d["n_types"]), arr["acc_type"].ctypes.data,
+                                       arr["current"].ctypes.data, arr["target"].ctypes.data,
+                                       arr["gpus_per_replica"].ctypes.data, arr["spare"].ctypes.data,
+                                       arr["cost"].ctypes.data, arr["type_limit"].ctypes.data,
+                                       out["target"].ctypes.data, out["gpus_allocated"].ctypes.data,
+                                       out["was_limited"].ctypes.data), "wva_limit")
+        return {k: v[:D] for k, v in out.items()}
+
+    # ---- observability ------------------------------------------------------------------------
+    def timing(self) -> dict:
+        t = abi.Timing()
+        self._check(self.lib.wva_last_timing(self.ctx, C.byref(t)), "wva_last_timing")
+        return {k: getattr(t, k) for k, _ in abi.Timing._fields_}
+
+    def launch_count(self) -> int:
+        return int(self.lib.wva_launch_count(self.ctx))
+
+    def microbench_fp64(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.wva_microbench_fp64(self.ctx, C.byref(a), C.byref(b)), "wva_microbench_fp64")
+        return a.value, b.value

@@ -1,0 +1,101 @@
+// TEST INFRASTRUCTURE ONLY — host build of the device core (csrc/wva_core.cuh) so
+// the lane state machines and the exact-division / early-exit logic can be checked
+// against the oracle on a machine without a GPU.  Never linked into the product.
+#include "../../include/wva_b200.h"
+#include "../../llm-d-workload-variant-autoscaler_b200/csrc/wva_core.cuh"
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+using namespace wva;
+
+static SysView make_view(const wva_system* s) {
+  SysView v;
+  v.n_acc = s->n_acc; v.n_types = s->n_types; v.n_models = s->n_models; v.n_servers = s->n_servers;
+  v.acc_cost = s->acc_cost; v.acc_multiplicity = s->acc_multiplicity; v.acc_type = s->acc_type; v.type_count = s->type_count;
+  v.perf_alpha = s->perf_alpha; v.perf_beta = s->perf_beta; v.perf_gamma = s->perf_gamma;
+  v.perf_max_batch = s->perf_max_batch; v.perf_at_tokens = s->perf_at_tokens; v.perf_acc_count = s->perf_acc_count;
+  v.perf_present = s->perf_present;
+  v.srv_model = s->srv_model; v.srv_priority = s->srv_priority; v.srv_min_replicas = s->srv_min_replicas;
+  v.srv_max_batch = s->srv_max_batch; v.srv_keep_acc = s->srv_keep_acc; v.srv_target_present = s->srv_target_present;
+  v.srv_slo_ttft = s->srv_slo_ttft; v.srv_slo_itl = s->srv_slo_itl; v.srv_slo_tps = s->srv_slo_tps;
+  v.srv_arrival = s->srv_arrival; v.srv_in_tokens = s->srv_in_tokens; v.srv_out_tokens = s->srv_out_tokens;
+  v.srv_cur_acc = s->srv_cur_acc; v.srv_cur_replicas = s->srv_cur_replicas; v.srv_cur_cost = s->srv_cur_cost;
+  return v;
+}
+
+extern "C" {
+
+// System.Calculate through the lane state machine, one lane at a time.
+int emul_calculate(const wva_system* sys, wva_candidates* out, int64_t* solves, int64_t* states, int64_t* overflow) {
+  SysView s = make_view(sys);
+  CandView o;
+  o.state = out->state; o.num_replicas = out->num_replicas; o.batch_size = out->batch_size; o.cost = out->cost;
+  o.value = out->value; o.itl = out->itl; o.ttft = out->ttft; o.rho = out->rho; o.max_arrv_rate = out->max_arrv_rate;
+  o.n_solves = out->n_solves;
+  int64_t ns = 0, nst = 0, nov = 0;
+  std::vector<float> tab;
+  for (int srv = 0; srv < s.n_servers; srv++)
+    for (int acc = 0; acc < s.n_acc; acc++) {
+      SizerLane z;
+      int lim = 0;
+      if (sizer_setup(z, s, o, srv, acc, 1 << 20, &lim) == SETUP_DONE) continue;
+      tab.assign((size_t)z.m.N, 0.0f);
+      model_fill_table(z.m, tab.data(), 1, 0, 1);
+      model_finish(z.m, tab.data(), 1);
+      bool live = sizer_begin(z, s, o);
+      SolveStats st;
+      while (live) {
+        if (chain_step(z.c, z.m, st)) {
+          if (z.c.phase == CH_OVERFLOW) { nov++; lane_fail(z, s, o); break; }
+          live = sizer_on_solve(z, s, o, st);
+        }
+      }
+      ns += z.solves; nst += z.states;
+    }
+  if (solves) *solves = ns;
+  if (states) *states = nst;
+  if (overflow) *overflow = nov;
+  return 0;
+}
+
+// exact-division self-checks against the IEEE operator; returns number of mismatches
+int64_t emul_check_div_f32den(int64_t n, uint64_t seed) {
+  std::mt19937_64 g(seed);
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    uint64_t a = g(), b = g();
+    // random double with exponent in a wide window, random float32 divisor
+    uint64_t xm = a & 0xFFFFFFFFFFFFFull; int xe = 1023 + (int)((a >> 52) % 600) - 300;
+    uint64_t xb = ((uint64_t)xe << 52) | xm; double x; memcpy(&x, &xb, 8);
+    uint32_t mm = (uint32_t)(b & 0x7FFFFF); int me = 127 + (int)((b >> 23) % 60) - 30;
+    uint32_t mb = ((uint32_t)me << 23) | mm; float m32; memcpy(&m32, &mb, 4);
+    if ((i & 7) == 0) mb |= 0x7FFFFFu, memcpy(&m32, &mb, 4);           // all-ones significand
+    if ((i & 7) == 1) { mb &= ~0x7FFFFFu; memcpy(&m32, &mb, 4); }       // power of two
+    double mu = (double)m32;
+    double r = rcp_f32den(m32, mu);
+    double q = div_f32den(x, mu, r);
+    if (q != x / mu) bad++;
+  }
+  return bad;
+}
+int64_t emul_check_div_markstein2(int64_t n, uint64_t seed) {
+  std::mt19937_64 g(seed);
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    uint64_t a = g(), b = g();
+    uint64_t xm = a & 0xFFFFFFFFFFFFFull; int xe = 1023 + (int)((a >> 52) % 400) - 200;
+    uint64_t xb = ((uint64_t)xe << 52) | xm; double x; memcpy(&x, &xb, 8);
+    uint64_t ym = b & 0xFFFFFFFFFFFFFull; int ye = 1023 + (int)((b >> 52) % 400) - 200;
+    if ((i & 15) == 0) ym = 0xFFFFFFFFFFFFFull;
+    if ((i & 15) == 1) ym = 0;
+    if ((i & 15) == 2) ym = 0xFFFFFFFFFFFFEull;
+    uint64_t yb = ((uint64_t)ye << 52) | ym; double y; memcpy(&y, &yb, 8);
+    double q = div_markstein2(x, y, 1.0 / y);
+    if (q != x / y) bad++;
+  }
+  return bad;
+}
+
+}  // extern "C"

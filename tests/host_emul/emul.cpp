@@ -48,7 +48,24 @@ int emul_calculate(const wva_system* sys, wva_candidates* out, int64_t* solves, 
       SolveStats st;
       while (live) {
         if (chain_step(z.c, z.m, st)) {
-          if (z.c.phase == CH_OVERFLOW) { nov++; lane_fail(z, s, o); break; }
+          if (z.c.phase == CH_OVERFLOW) {
+            // same redo as overflow_slow_kernel: literal stored-p[] algorithm from the start of the pair
+            nov++;
+            SizerLane y;
+            int lim2 = 0;
+            sizer_setup(y, s, o, srv, acc, 1 << 20, &lim2);
+            model_finish(y.m, tab.data(), 1);
+            std::vector<double> p((size_t)y.m.K + 1);
+            bool bad = false;
+            bool l2 = sizer_begin(y, s, o);
+            while (l2) {
+              literal_solve(y.m, y.cur_x, p.data(), st, &bad);
+              y.c.states = y.m.K + 1;
+              l2 = sizer_on_solve(y, s, o, st);
+            }
+            z = y;
+            break;
+          }
           live = sizer_on_solve(z, s, o, st);
         }
       }

@@ -1,0 +1,280 @@
+"""GPU parity tests proper: the CUDA path through the C-ABI vs the oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): integers bit-exact, float32 outputs within 1e-6 relative.
+In practice the float outputs are bit-identical too (asserted where it holds by construction).
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+INT_FIELDS = ("state", "num_replicas", "batch_size")
+F32_FIELDS = ("cost", "value", "itl", "ttft", "rho", "max_arrv_rate")
+RTOL = 1e-6  # predicted latencies / throughputs: 1e-6 relative (north_star)
+
+
+def _cmp_candidates(g, o):
+    for k in INT_FIELDS:
+        assert np.array_equal(g[k], o[k]), f"{k}: {np.argwhere(g[k] != o[k])[:5]}"
+    for k in F32_FIELDS:
+        np.testing.assert_allclose(g[k], o[k], rtol=RTOL, atol=0, err_msg=k)
+
+
+def _bit_equal(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+
+
+# ---- sizing: System.Calculate --------------------------------------------------------------------
+@pytest.mark.parametrize("S,A,N,stream", [(10, 4, 32, 1), (64, 8, 16, 7), (48, 16, 128, 2), (16, 8, 256, 3),
+                                          (33, 5, 1, 11), (20, 3, 7, 12)])
+def test_calculate_matches_oracle(pkg, engine, oracle, S, A, N, stream):
+    sysd = pkg.synth.queue_system(S, A, N, stream=stream)
+    engine.load_system(sysd)
+    engine.calculate()
+    g = engine.candidates()
+    o = oracle.calculate(sysd)
+    _cmp_candidates(g, o)
+    # by construction the float32 outputs are the same bits, not merely within 1e-6
+    for k in F32_FIELDS:
+        assert _bit_equal(g[k], o[k]), k
+    t = engine.timing()
+    assert t["chain_solves"] > 0 and t["overflow_pairs"] == 0
+
+
+def test_baseline_config1_full_path(pkg, engine, oracle):
+    """BASELINE config 1: 10 models x 4 variants x 32 levels, single class, unlimited."""
+    sysd = pkg.synth.baseline_config(1)
+    sol = engine.optimize(sysd)
+    oc = oracle.calculate(sysd)
+    osol = oracle.solve(sysd, oc)
+    for k in ("state", "acc", "num_replicas", "batch_size"):
+        assert np.array_equal(sol[k], osol[k]), k
+    for k in F32_FIELDS:
+        np.testing.assert_allclose(sol[k], osol[k], rtol=RTOL, atol=0, err_msg=k)
+    assert np.array_equal(sol["type_count"], osol["type_count"])
+    np.testing.assert_allclose(sol["type_cost"], osol["type_cost"], rtol=1e-12)
+    # the reference sums by-type cost in float32 in map order: only ~1e-5 accurate itself
+    np.testing.assert_allclose(sol["type_cost"], osol["type_cost_f32"], rtol=1e-4)
+
+
+def test_edge_cases_match_oracle(pkg, engine, oracle):
+    """zero load, min replicas 0, keepAccelerator, unknown model/target, missing perf, TPS targets,
+    server max-batch override, negative load, unknown current accelerator, current allocation penalties."""
+    sysd = pkg.synth.queue_system(40, 6, 24, stream=21)
+    s = sysd
+    s["srv_arrival"][0] = 0.0; s["srv_min_replicas"][0] = 0          # empty allocation
+    s["srv_arrival"][1] = 0.0; s["srv_min_replicas"][1] = 3          # zero-load with replicas
+    s["srv_out_tokens"][2] = 0                                        # zero-load via AvgOutTokens == 0
+    s["srv_keep_acc"][3] = 1; s["srv_cur_acc"][3] = 2; s["srv_cur_replicas"][3] = 4; s["srv_cur_cost"][3] = 321.5
+    s["srv_keep_acc"][4] = 1; s["srv_cur_acc"][4] = -2                # unknown current accelerator: no candidates
+    s["srv_keep_acc"][5] = 1; s["srv_cur_acc"][5] = -1                # keep but no current: all candidates
+    s["srv_model"][6] = -1                                            # unknown model
+    s["srv_target_present"][7] = 0                                    # no class / target
+    s["perf_present"][8 * 6 + 1] = 0; s["perf_present"][8 * 6 + 4] = 0
+    s["srv_slo_tps"][9] = 500.0                                       # TPS target drives totalRate
+    s["srv_slo_ttft"][10] = 0.0; s["srv_slo_itl"][10] = 0.0           # no latency targets at all
+    s["srv_max_batch"][11] = 9                                        # override N
+    s["srv_arrival"][12] = -1.0                                       # negative load -> nil
+    s["srv_cur_acc"][13] = 1; s["srv_cur_replicas"][13] = 2; s["srv_cur_cost"][13] = 100.0
+    s["perf_acc_count"][14 * 6:15 * 6] = 0                            # AccCount <= 0 -> 1
+    s["srv_slo_ttft"][15] = 1e-3                                      # unattainable TTFT
+    s["srv_min_replicas"][16] = 50                                    # min replicas binds
+    s["srv_in_tokens"][17] = 0                                        # PrefillTime == 0 branch
+    s["srv_arrival"][18] = 1e9                                        # enormous load
+    s["srv_slo_itl"][19] = 1e9; s["srv_slo_ttft"][19] = 1e9           # targets above the bounded region (ind = +1)
+    engine.load_system(sysd)
+    engine.calculate()
+    g = engine.candidates()
+    o = oracle.calculate(sysd)
+    _cmp_candidates(g, o)
+    assert (g["state"] == 2).any() and (g["state"] == 0).any() and (g["state"] == 1).any()
+    engine.solve()
+    sol = engine.solution()
+    osol = oracle.solve(sysd, o)
+    for k in ("state", "acc", "num_replicas"):
+        assert np.array_equal(sol[k], osol[k]), k
+    assert np.array_equal(sol["type_count"], osol["type_count"])
+
+
+def test_empty_and_ragged(pkg, engine, oracle):
+    sysd = pkg.synth.queue_system(1, 1, 4, stream=5)
+    sol = engine.optimize(sysd)
+    oc = oracle.calculate(sysd)
+    osol = oracle.solve(sysd, oc)
+    assert np.array_equal(sol["num_replicas"], osol["num_replicas"])
+    # zero servers
+    empty = pkg.synth.queue_system(1, 3, 4, stream=5)
+    for k in list(empty):
+        if k.startswith("srv_"):
+            empty[k] = empty[k][:0]
+    empty["n_servers"] = 0
+    sol = engine.optimize(empty)
+    assert sol["state"].size == 0 and (sol["type_count"] == 0).all()
+
+
+def test_float64_overflow_rescale_path(pkg, engine, oracle):
+    """alpha-dominated service (beta = gamma = 0, I = 0) with N = 1024 overflows float64."""
+    sysd = pkg.synth.queue_system(2, 2, 1024, stream=31)
+    sysd["perf_alpha"][:] = 4.0
+    sysd["perf_beta"][:] = 0.0
+    sysd["perf_gamma"][:] = 0.0
+    sysd["srv_in_tokens"][:] = 0
+    sysd["srv_out_tokens"][:] = 16
+    sysd["perf_at_tokens"][:] = 16
+    sysd["srv_arrival"][:] = 60.0 * 2000
+    sysd["srv_slo_ttft"][:] = 5000.0
+    sysd["srv_slo_itl"][:] = 0.0
+    engine.load_system(sysd)
+    engine.calculate()
+    g = engine.candidates()
+    o = oracle.calculate(sysd)
+    _cmp_candidates(g, o)
+    assert engine.timing()["overflow_pairs"] > 0
+
+
+# ---- replica grid ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,A,N,R,stream", [(10, 4, 32, 32, 1), (24, 8, 128, 128, 2), (6, 3, 256, 70, 3)])
+def test_grid_matches_oracle(pkg, engine, oracle, S, A, N, R, stream):
+    sysd = pkg.synth.queue_system(S, A, N, stream=stream, R=R)
+    engine.load_system(sysd)
+    g = engine.analyze_grid(R)
+    o = oracle.analyze_grid(sysd, R)
+    assert np.array_equal(g["ok"], o["ok"])
+    assert np.array_equal(g["frontier"], o["frontier"])
+    for k in ("ttft", "itl", "rho", "tput"):
+        np.testing.assert_allclose(g[k], o[k], rtol=RTOL, atol=0, err_msg=k)
+        assert _bit_equal(g[k], o[k]), k
+    # frontier-only run (no [S,A,R] materialisation) gives the same frontier
+    engine.grid_run(R, full=False)
+    assert np.array_equal(engine.grid_fetch_frontier(), o["frontier"])
+
+
+def test_grid_monotone_in_replicas(pkg, engine):
+    """Size-independent property at BASELINE config 2 shape: more replicas never raise ITL/TTFT/rho."""
+    sysd = pkg.synth.baseline_config(2, scale=0.05)
+    engine.load_system(sysd)
+    g = engine.analyze_grid(128)
+    ok = g["ok"].astype(bool)
+    for k in ("itl", "rho"):
+        v = np.where(ok, g[k], np.nan)
+        d = np.diff(v, axis=2)
+        assert np.nanmax(d) <= 1e-4 * np.nanmax(np.abs(v)), k
+
+
+# ---- M/M/1/K leg ---------------------------------------------------------------------------------------
+def test_mm1k_matches_oracle(engine, oracle):
+    rng = np.random.default_rng(7)
+    n = 5000
+    mu = rng.uniform(0.01, 5.0, n).astype(np.float32)
+    lam = (mu * rng.uniform(0.0, 1.4, n)).astype(np.float32)
+    K = rng.integers(1, 1500, n).astype(np.int32)
+    lam[:5] = [1, 0, -1, 1, 1]; mu[:5] = [2, 2, 2, 0, -1]; K[:5] = 10      # queuemodel_test.go:9-102
+    lam[5:8] = [9.9, 11, 3]; mu[5:8] = [1, 1, 3]; K[5:8] = [10, 10, 5]
+    g = engine.mm1k_eval(lam, mu, K)
+    o = oracle.mm1k_eval(lam, mu, K)
+    assert np.array_equal(g["valid"], o["valid"])
+    v = o["valid"].astype(bool) & (lam > 0)   # lambda == 0 gives T = NaN in the reference too
+    for k in ("avg_resp", "avg_wait", "avg_serv", "avg_num", "avg_queue", "throughput", "rho"):
+        np.testing.assert_allclose(g[k][v], o[k][v], rtol=2e-6, atol=1e-7, err_msg=k)
+
+
+# ---- V1 saturation ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,V,stream", [(200, 32, 4), (77, 5, 41), (50, 40, 42), (300, 1, 43)])
+def test_saturation_matches_oracle(pkg, engine, oracle, M, V, stream):
+    d = pkg.synth.saturation_batch(M, V, stream=stream)
+    g = engine.saturation_v1(d)
+    o = oracle.saturation_v1(d)
+    for k in ("var_target", "var_replica_count", "var_non_saturated", "var_max_queue", "rep_saturated",
+              "mod_total_replicas", "mod_non_saturated", "mod_flags", "partials"):
+        assert np.array_equal(g[k], o[k]), k
+    for k in ("var_max_kv", "var_avg_spare_kv", "var_avg_spare_queue", "mod_avg_spare_kv", "mod_avg_spare_queue"):
+        assert _bit_equal(g[k], o[k]), k   # float64 sums are taken in the same order -> same bits
+    assert (o["mod_flags"] & 1).any() and (o["mod_flags"] & 4).any()
+
+
+def test_saturation_ragged(pkg, engine, oracle):
+    """variants without replicas, variants without state, models without variants, empty batch."""
+    d = pkg.synth.saturation_batch(40, 6, stream=44)
+    off = d["variant_replica_off"].astype(np.int64)
+    cnt = np.diff(off)
+    cnt[::7] = 0                                  # some variants have no metrics
+    cnt[6:12] = 0                                 # a whole model without metrics -> nil-safety path
+    off2 = np.zeros_like(off); np.cumsum(cnt, out=off2[1:])
+    P = int(off2[-1])
+    d["variant_replica_off"] = off2.astype(np.int32)
+    d["rep_kv"] = d["rep_kv"][:P]; d["rep_queue"] = d["rep_queue"][:P]; d["n_replicas"] = P
+    hs = np.ones(d["n_variants"], np.uint8); hs[3::11] = 0
+    d["var_has_state"] = hs
+    mvo = d["model_variant_off"].copy()
+    mvo[20] = mvo[19]                             # model 19 has zero variants (model 20 gets its share)
+    d["model_variant_off"] = mvo
+    g = engine.saturation_v1(d)
+    o = oracle.saturation_v1(d)
+    for k in ("var_target", "mod_flags", "mod_total_replicas", "partials"):
+        assert np.array_equal(g[k], o[k]), k
+    empty = pkg.synth.saturation_batch(1, 1, stream=45)
+    empty.update(n_models=0, n_variants=0, n_replicas=0, model_variant_off=np.zeros(1, np.int32),
+                 variant_replica_off=np.zeros(1, np.int32))
+    for k in ("rep_kv", "rep_queue", "var_cost", "var_current", "var_desired", "var_pending", "cfg_kv_threshold",
+              "cfg_queue_threshold", "cfg_kv_trigger", "cfg_queue_trigger"):
+        empty[k] = empty[k][:0]
+    g = engine.saturation_v1(empty)
+    assert g["var_target"].size == 0 and (g["partials"] == 0).all()
+
+
+# ---- limiter -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D,T,stream,tight", [(5000, 8, 6, 0.6), (1, 1, 61, 0.5), (3000, 3, 62, 0.0),
+                                              (4000, 16, 63, 1.5)])
+def test_limiter_matches_oracle(pkg, engine, oracle, D, T, stream, tight):
+    d = pkg.synth.limiter_batch(D, T, stream=stream, tightness=tight)
+    g = engine.limit(d)
+    o = oracle.limit(d)
+    for k in ("target", "gpus_allocated", "was_limited"):
+        assert np.array_equal(g[k], o[k]), k
+
+
+def test_limiter_reference_vectors(engine):
+    """internal/engines/pipeline/greedy_saturation_algorithm_test.go:78-169,202-270."""
+    base = dict(n_types=1, acc_type=[0, 0, 0], current=[1, 1, 1], target=[2, 2, 2], gpus_per_replica=[2, 2, 2],
+                spare=[0.3, 0.05, 0.5], cost=[10.0, 10.0, 10.0], type_limit=[6 + 6])
+    g = engine.limit(base)
+    assert g["gpus_allocated"].tolist() == [2, 2, 2] and not g["was_limited"].any()
+    # pool 3 GPUs free, 1 -> 3 replicas at 2 GPUs each: one replica, the odd GPU is consumed but not counted
+    g = engine.limit(dict(n_types=1, acc_type=[0], current=[1], target=[3], gpus_per_replica=[2], spare=[0.1],
+                          cost=[5.0], type_limit=[2 + 3]))
+    assert g["gpus_allocated"].tolist() == [2] and g["target"].tolist() == [2] and g["was_limited"].tolist() == [1]
+    # equal spare -> cheaper first
+    g = engine.limit(dict(n_types=1, acc_type=[0, 0], current=[1, 1], target=[2, 2], gpus_per_replica=[2, 2],
+                          spare=[0.2, 0.2], cost=[20.0, 5.0], type_limit=[4 + 2]))
+    assert g["target"].tolist() == [1, 2]
+    # gpusPerReplica 0 -> 1
+    g = engine.limit(dict(n_types=1, acc_type=[0], current=[1], target=[3], gpus_per_replica=[0], spare=[0.1],
+                          cost=[5.0], type_limit=[10]))
+    assert g["target"].tolist() == [3] and g["gpus_allocated"].tolist() == [2]
+
+
+# ---- boundary behaviour ----------------------------------------------------------------------------------------
+def test_call_order_and_errors(pkg):
+    with pkg.Engine(0) as e:
+        with pytest.raises(pkg.WvaError):
+            e.calculate()                       # before load
+        e.load_system(pkg.synth.baseline_config(1))
+        with pytest.raises(pkg.WvaError):
+            e.solve()                           # before calculate
+        e.calculate()
+        with pytest.raises(pkg.WvaError):
+            e.solution()                        # before solve
+        bad = pkg.synth.baseline_config(1)
+        bad["acc_type"] = np.array([0, 1, 2, 99], np.int32)
+        with pytest.raises(pkg.WvaError):
+            e.load_system(bad)
+        assert e.launch_count() > 0
+    with pytest.raises(pkg.WvaError):
+        pkg.Engine(device=10_000)               # no such device: no fallback
+
+
+def test_fp64_microbench(engine):
+    dfma, ddiv = engine.microbench_fp64()
+    assert dfma > 1e11 and ddiv > 1e9

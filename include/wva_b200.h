@@ -172,6 +172,10 @@ const char* wva_last_error(const wva_ctx* ctx);
 /* number of kernel launches issued by this ctx since creation */
 int64_t wva_launch_count(const wva_ctx* ctx);
 
+/* options (wva_set_option): tuning / test hooks, never needed for correctness */
+#define WVA_OPT_FORCE_LANE_SIZER 1 /* 1: always use the lane-per-pair sizer kernel */
+int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value);
+
 /* ---- queueing sizing + allocator ---------------------------------------- */
 /* System.SetFromSpec (pkg/core/system.go:82-89): copies the SoA to HBM. */
 int32_t wva_load_system(wva_ctx* ctx, const wva_system* sys);

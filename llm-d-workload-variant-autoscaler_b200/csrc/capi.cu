@@ -5,6 +5,7 @@
 #include "../../include/wva_b200.h"
 #include "wva_core.cuh"
 #include "sizer_kernel.cuh"
+#include "sizer_warp_kernel.cuh"
 #include "solve_kernels.cuh"
 #include "grid_kernel.cuh"
 #include "saturation_kernel.cuh"
@@ -85,6 +86,7 @@ struct wva_ctx {
 
   // queueing system
   bool loaded = false, calculated = false, solved = false;
+  bool force_lane_sizer = false;
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
   int policy = 0;
@@ -275,7 +277,24 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
   ctx->launches++;
   return cudaGetLastError();
 }
+template <int WARPS>
+static cudaError_t launch_sizer_warp(wva_ctx* ctx, int blocks, size_t smem, unsigned long long n_pairs, int nmax,
+                                     int* ovf_list) {
+  auto k = sizer_warp_kernel<WARPS>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<blocks, WARPS * 32, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, ctx->d_ctr, ovf_list);
+  ctx->launches++;
+  return cudaGetLastError();
+}
 extern "C" {
+
+/* test / profiling hook: 1 forces the lane-per-pair sizer regardless of the system size */
+int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
+  if (!ctx) return WVA_ERR_ARG;
+  if (option == WVA_OPT_FORCE_LANE_SIZER) { ctx->force_lane_sizer = value != 0; return WVA_OK; }
+  return WVA_ERR_ARG;
+}
 
 int32_t wva_calculate(wva_ctx* ctx) {
   if (!ctx) return WVA_ERR_ARG;
@@ -315,7 +334,28 @@ int32_t wva_calculate(wva_ctx* ctx) {
       if (per_sm * sizes[i] > 1024) per_sm = 1024 / sizes[i];
       if (per_sm * sizes[i] > best_threads * best_per_sm) { best_threads = sizes[i]; best_per_sm = per_sm; }
     }
+    // small problems are latency bound: spread the pairs over every SM with as few lanes per SM
+    // as needed instead of filling the first SMs (lanes pull one pair each from the queue)
+    const unsigned long long lanes_needed = (n_pairs + ctx->sm_count - 1) / ctx->sm_count;
+    if (best_per_sm >= 1 && lanes_needed <= 256 && lanes_needed < (unsigned long long)best_threads * best_per_sm) {
+      int t = 64;
+      while ((unsigned long long)t < lanes_needed) t += 64;
+      if (per_lane * t + 1024 <= SMEM_PER_SM) { best_threads = t; best_per_sm = 1; }
+    }
     cudaError_t e;
+    // Small / medium systems are bound by the critical path of their slowest pair: use the
+    // warp-per-pair sizer (speculative bisection, sizer_warp_kernel.cuh) while the whole system
+    // fits in a few waves of warps and its per-warp tables (20 B x nmax) fit in shared memory.
+    const size_t warp_tab = (size_t)nmax * 20;
+    if (n_pairs <= (unsigned long long)ctx->sm_count * 512 && warp_tab * 4 + 1024 <= SMEM_PER_SM && !ctx->force_lane_sizer) {
+      if (warp_tab * 8 <= 48 * 1024) {
+        int per_sm = (int)(SMEM_PER_SM / (warp_tab * 8 + 1024)); if (per_sm > 6) per_sm = 6; if (per_sm < 1) per_sm = 1;
+        e = launch_sizer_warp<8>(ctx, ctx->sm_count * per_sm, warp_tab * 8, n_pairs, nmax, d_ovf);
+      } else {
+        int per_sm = (int)(SMEM_PER_SM / (warp_tab * 4 + 1024)); if (per_sm > 8) per_sm = 8; if (per_sm < 1) per_sm = 1;
+        e = launch_sizer_warp<4>(ctx, ctx->sm_count * per_sm, warp_tab * 4, n_pairs, nmax, d_ovf);
+      }
+    } else
     if (best_per_sm >= 1) {
       int blocks = ctx->sm_count * best_per_sm;
       size_t smem = per_lane * best_threads;

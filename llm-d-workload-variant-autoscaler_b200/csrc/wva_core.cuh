@@ -461,7 +461,7 @@ enum { SETUP_DONE = 0, SETUP_NEEDS_TABLE = 1 };
 // allocation.go:27-100: everything before the queue analyzer exists.  When the pair
 // is decided without any chain solve the candidate is written and SETUP_DONE returned.
 WVA_HD int sizer_setup(SizerLane& z, const SysView& s, const CandView& out, int srv, int acc, int n_limit,
-                       int* limit_hit) {
+                       int* limit_hit, bool write = true) {
   z.srv = srv; z.acc = acc; z.solves = 0; z.states = 0;
   size_t idx = (size_t)srv * s.n_acc + acc;
   Alloc a; a.state = ALLOC_NONE; a.num_replicas = 0; a.batch_size = 0;
@@ -477,7 +477,7 @@ WVA_HD int sizer_setup(SizerLane& z, const SysView& s, const CandView& out, int 
              model >= s.n_models || !s.srv_target_present[srv];
   size_t pi = nil ? 0 : (size_t)model * s.n_acc + acc;
   if (!nil && !s.perf_present[pi]) nil = true;
-  if (nil) { store_candidate(out, idx, a, 0); return SETUP_DONE; }
+  if (nil) { if (write) store_candidate(out, idx, a, 0); return SETUP_DONE; }
   z.min_replicas = s.srv_min_replicas[srv];
   z.n_inst = num_instances(s, model, acc);
   z.acc_cost = s.acc_cost[acc];
@@ -502,7 +502,7 @@ WVA_HD int sizer_setup(SizerLane& z, const SysView& s, const CandView& out, int 
       a.max_arrv = f_div((float)mb, max_serv);
     }
     a.value = transition_penalty(cur_acc, s.srv_cur_replicas[srv], s.srv_cur_cost[srv], a, acc);
-    store_candidate(out, idx, a, 0);
+    if (write) store_candidate(out, idx, a, 0);
     return SETUP_DONE;
   }
   // allocation.go:79-88
@@ -514,7 +514,7 @@ WVA_HD int sizer_setup(SizerLane& z, const SysView& s, const CandView& out, int 
   }
   if (Nll > n_limit) {  // larger than the kernels are built for: reported, never silently clipped
     if (limit_hit) *limit_hit = 1;
-    store_candidate(out, idx, a, 0);
+    if (write) store_candidate(out, idx, a, 0);
     return SETUP_DONE;
   }
   // Configuration.check / RequestSize.check (utils.go:95-118): N>0 holds; AvgOutputTokens >= 1 holds
@@ -523,7 +523,7 @@ WVA_HD int sizer_setup(SizerLane& z, const SysView& s, const CandView& out, int 
   z.slo_tps = s.srv_slo_tps[srv];
   z.sT.target = ttft; z.sI.target = itl;
   // TargetPerf.check (utils.go:121-128)
-  if (itl < 0.0f || ttft < 0.0f || z.slo_tps < 0.0f) { store_candidate(out, idx, a, 0); return SETUP_DONE; }
+  if (itl < 0.0f || ttft < 0.0f || z.slo_tps < 0.0f) { if (write) store_candidate(out, idx, a, 0); return SETUP_DONE; }
   // allocation.go:127-132
   z.total_rate = (z.slo_tps == 0.0f) ? f_div(arrival, 60.0f) : f_div(z.slo_tps, (float)out_tok);
   return SETUP_NEEDS_TABLE;
@@ -583,6 +583,49 @@ WVA_HD void search_consume(Search& q, float x, float y) {
   q.iter++;
   if (q.iter >= WVA_MAX_ITER) { q.result = x; q.active = false; return; }
   q.x = f_mul(0.5f, f_add(q.lo, q.hi));
+  // (E6) fixpoint: once the next midpoint equals the point just evaluated, eval() returns
+  // the same y, the same branch is taken and (lo, hi) no longer change, so every remaining
+  // iteration up to maxIterations repeats this one and BinarySearch returns x.  (The 1e-6
+  // relative tolerance sits at float32 resolution, so ~1 in 5 searches ends this way.)
+  if (q.x == x) { q.result = x; q.active = false; }
+}
+
+// ---- speculative bisection (used by the warp-per-pair sizer; see sizer_warp_kernel.cuh) ----
+// x of heap node `node` (1-based; children 2j, 2j+1) of the bisection tree rooted at (lo, hi):
+// left child = the branch that sets hi = x, right child = the branch that sets lo = x.
+WVA_HD float spec_node_x(float lo, float hi, int node, int depth_of_node) {
+  float x = f_mul(0.5f, f_add(lo, hi));
+  for (int b = depth_of_node - 2; b >= 0; b--) {
+    if ((node >> b) & 1) lo = x; else hi = x;
+    x = f_mul(0.5f, f_add(lo, hi));
+  }
+  return x;
+}
+WVA_HD int spec_depth_of(int node) {  // 1 for the root
+  int d = 0;
+  while (node) { d++; node >>= 1; }
+  return d;
+}
+
+// Walk one search through an evaluated tree of `depth` levels.  get_y(node) returns f(x_node).
+// On return either the search finished (q.active == false, q.result set) or (q.lo, q.hi, q.iter,
+// q.x) describe the interval for the next round.
+template <typename GetY>
+WVA_HD void spec_walk(Search& q, int depth, GetY get_y) {
+  int node = 1;
+  for (int lvl = 0; lvl < depth && q.active; lvl++) {
+    float x = q.x;
+    float y = get_y(node);
+    bool right;
+    if (within_tolerance(y, q.target, WVA_BS_EPSILON)) { q.result = x; q.active = false; break; }
+    if ((q.increasing && q.target < y) || (!q.increasing && q.target > y)) { q.hi = x; right = false; }
+    else { q.lo = x; right = true; }
+    q.iter++;
+    if (q.iter >= WVA_MAX_ITER) { q.result = x; q.active = false; break; }
+    q.x = f_mul(0.5f, f_add(q.lo, q.hi));
+    if (q.x == x) { q.result = x; q.active = false; break; }   // (E6) fixpoint
+    node = 2 * node + (right ? 1 : 0);
+  }
 }
 
 // The solve at z.cur_x completed with stats st.  Returns false when the pair is finished.

@@ -58,6 +58,7 @@ def load_library():
     L.wva_last_error.restype = C.c_char_p
     L.wva_launch_count.argtypes = [ctxp]
     L.wva_launch_count.restype = C.c_int64
+    L.wva_set_option.argtypes = [ctxp, C.c_int32, C.c_int32]
     L.wva_load_system.argtypes = [ctxp, C.POINTER(abi.System)]
     L.wva_calculate.argtypes = [ctxp]
     L.wva_solve.argtypes = [ctxp]
@@ -78,7 +79,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["wva_create", "wva_destroy", "wva_strerror", "wva_last_error", "wva_launch_count",
+EXPORTS = ["wva_set_option", "wva_create", "wva_destroy", "wva_strerror", "wva_last_error", "wva_launch_count",
            "wva_load_system", "wva_calculate", "wva_solve", "wva_get_candidates", "wva_get_solution",
            "wva_analyze_grid", "wva_grid_run", "wva_grid_fetch", "wva_mm1k_eval", "wva_saturation_v1",
            "wva_saturation_upload", "wva_saturation_run", "wva_saturation_fetch", "wva_limit", "wva_last_timing",
@@ -110,6 +111,9 @@ class Engine:
 
     def __exit__(self, *a):
         self.close()
+
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.wva_set_option(self.ctx, option, value), "wva_set_option")
 
     # ---- queueing sizing + allocator ------------------------------------------------------
     def load_system(self, sysd: dict):

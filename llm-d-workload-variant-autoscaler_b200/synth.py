@@ -126,7 +126,10 @@ def saturation_batch(M: int, V_per_model: int = 32, stream: int = 4, max_replica
     np.cumsum(nrep, out=off[1:])
     P = int(off[-1])
     assert P < 2**31
-    kv = g.beta(2.0, 3.0, P)
+    # per-model load level so that every branch occurs: idle models (scale-down safe), busy models
+    # (no action) and hot models (scale-up)
+    level = np.repeat(g.choice([0.45, 1.0, 1.75], M, p=[0.35, 0.35, 0.30]), V_per_model)
+    kv = np.minimum(g.beta(2.0, 3.0, P) * np.repeat(level, nrep), 0.999)
     hot = g.random(P) < 0.10
     kv[hot] = g.uniform(0.8, 1.0, int(hot.sum()))
     queue = g.poisson(1.5, P).astype(np.int64)

@@ -43,6 +43,25 @@ def test_calculate_matches_oracle(pkg, engine, oracle, S, A, N, stream):
     assert t["chain_solves"] > 0 and t["overflow_pairs"] == 0
 
 
+@pytest.mark.parametrize("S,A,N,stream", [(10, 4, 32, 1), (64, 8, 16, 7), (48, 16, 128, 2), (16, 8, 256, 3),
+                                          (33, 5, 1, 11)])
+def test_calculate_lane_kernel_matches_oracle(pkg, engine, oracle, S, A, N, stream):
+    """Small systems default to the warp-per-pair sizer; force the lane-per-pair kernel (the one large
+    systems use) and hold it to the same bar."""
+    sysd = pkg.synth.queue_system(S, A, N, stream=stream)
+    engine.set_option(1, 1)
+    try:
+        engine.load_system(sysd)
+        engine.calculate()
+        g = engine.candidates()
+    finally:
+        engine.set_option(1, 0)
+    o = oracle.calculate(sysd)
+    _cmp_candidates(g, o)
+    for k in F32_FIELDS:
+        assert _bit_equal(g[k], o[k]), k
+
+
 def test_baseline_config1_full_path(pkg, engine, oracle):
     """BASELINE config 1: 10 models x 4 variants x 32 levels, single class, unlimited."""
     sysd = pkg.synth.baseline_config(1)
@@ -72,13 +91,13 @@ def test_edge_cases_match_oracle(pkg, engine, oracle):
     s["srv_keep_acc"][5] = 1; s["srv_cur_acc"][5] = -1                # keep but no current: all candidates
     s["srv_model"][6] = -1                                            # unknown model
     s["srv_target_present"][7] = 0                                    # no class / target
-    s["perf_present"][8 * 6 + 1] = 0; s["perf_present"][8 * 6 + 4] = 0
+    s["perf_present"][8, 1] = 0; s["perf_present"][8, 4] = 0
     s["srv_slo_tps"][9] = 500.0                                       # TPS target drives totalRate
     s["srv_slo_ttft"][10] = 0.0; s["srv_slo_itl"][10] = 0.0           # no latency targets at all
     s["srv_max_batch"][11] = 9                                        # override N
     s["srv_arrival"][12] = -1.0                                       # negative load -> nil
     s["srv_cur_acc"][13] = 1; s["srv_cur_replicas"][13] = 2; s["srv_cur_cost"][13] = 100.0
-    s["perf_acc_count"][14 * 6:15 * 6] = 0                            # AccCount <= 0 -> 1
+    s["perf_acc_count"][14, :] = 0                            # AccCount <= 0 -> 1
     s["srv_slo_ttft"][15] = 1e-3                                      # unattainable TTFT
     s["srv_min_replicas"][16] = 50                                    # min replicas binds
     s["srv_in_tokens"][17] = 0                                        # PrefillTime == 0 branch

@@ -33,7 +33,16 @@ def emul(pkg):
         cand["_solves"], cand["_states"], cand["_overflow"] = a.value, b.value, c.value
         return cand
 
+    lib.emul_calculate_spec.argtypes = [C.POINTER(abi.System), C.POINTER(abi.Candidates)]
+
+    def calculate_spec(sysd):
+        st, keep = abi.make_system(sysd)
+        cst, cand = abi.alloc_candidates(st.n_servers, st.n_acc)
+        lib.emul_calculate_spec(C.byref(st), C.byref(cst))
+        return cand
+
     lib.calculate = calculate
+    lib.calculate_spec = calculate_spec
     return lib
 
 
@@ -60,6 +69,18 @@ def test_lane_state_machine_matches_oracle(pkg, oracle, emul, S, A, N, stream):
     for k in F32_FIELDS:
         assert _bit_equal(e[k], o[k]), k
     assert e["_overflow"] == 0 and e["_solves"] <= o["_solves"]
+
+
+@pytest.mark.parametrize("S,A,N,stream", [(10, 4, 32, 1), (40, 8, 16, 7), (10, 6, 128, 2), (20, 3, 1, 11)])
+def test_speculative_bisection_matches_oracle(pkg, oracle, emul, S, A, N, stream):
+    """The tree-speculative search of the warp-per-pair sizer takes exactly BinarySearch's branches."""
+    sysd = pkg.synth.queue_system(S, A, N, stream=stream)
+    e = emul.calculate_spec(sysd)
+    o = oracle.calculate(sysd)
+    for k in ("state", "num_replicas", "batch_size"):
+        assert np.array_equal(e[k], o[k]), k
+    for k in F32_FIELDS:
+        assert _bit_equal(e[k], o[k]), k
 
 
 def test_overflow_rescale_path_matches_oracle(pkg, oracle, emul):

@@ -17,100 +17,11 @@
 #pragma once
 #include "wva_core.cuh"
 #include "sizer_kernel.cuh"
+#include "lockstep_solve.cuh"
 
 namespace wva {
 
 #if defined(__CUDACC__)
-
-// One MM1ModelStateDependent.Solve per lane, all lanes in lock step over the state index.
-// tab[n] = (mu_n, ~1/mu_n) for n in [0, N-1).  Inactive lanes only keep the loops uniform.
-__device__ __forceinline__ void warp_solve(const PairModel& m, const double2* __restrict__ tab, float lambda,
-                                           bool active, SolveStats& st, long long& states, bool& overflow) {
-  const unsigned full = 0xffffffffu;
-  const int K = m.K, N = m.N;
-  const double lam = (double)lambda, lamg = d_mul(lam, 1.000001);
-  const bool tail_ok = d_bits(lamg) <= d_bits(m.mu_last);
-  double p = 1.0, sum = 1.0;
-  bool done = !active;
-  overflow = false;
-  int n = 0;
-  // ---- pass 1: sum of the unnormalised probabilities -----------------------------------------------
-  while (__any_sync(full, !done)) {
-    double mu, r;
-    bool exit_ok;
-    if (n < N - 1) {
-      double2 t = tab[n];
-      mu = t.x; r = t.y;
-      exit_ok = (n >= m.mono) && (d_bits(lamg) <= d_bits(mu));
-    } else { mu = m.mu_last; r = m.r_last; exit_ok = tail_ok; }
-    if (!done) {
-      double x = d_mul(p, lam);
-      double pn1 = in_window(x) ? div_f32den(x, mu, r) : d_div(x, mu);
-      states++;
-      if (!(pn1 >= 0.0) || pn1 > DBL_MAX) { overflow = true; done = true; }
-      else {
-        double s2 = d_add(sum, pn1);
-        if (s2 > DBL_MAX) { overflow = true; done = true; }
-        else {
-          bool fin = (n + 1 == K) || (d_bits(pn1) == 0) || (exit_ok && d_bits(s2) == d_bits(sum));
-          sum = s2; p = pn1;
-          if (fin) done = true;
-        }
-      }
-    }
-    n++;
-  }
-  // ---- pass 2: normalise, accumulate (mm1modelstatedependent.go:108-112, 47-55) ----------------------
-  const bool sum_ok = in_window(sum);
-  const double rsum = d_rcp(sum);
-  double sumP = d_div(1.0, sum), L = 0.0, Lserv = 0.0, pK = 0.0;
-  p = 1.0;
-  done = !active || overflow;
-  bool lserv_set = false;
-  n = 0;
-  while (__any_sync(full, !done)) {
-    double mu, r;
-    bool exit_ok;
-    if (n < N - 1) {
-      double2 t = tab[n];
-      mu = t.x; r = t.y;
-      exit_ok = (n >= m.mono) && (d_bits(lamg) <= d_bits(mu));
-    } else { mu = m.mu_last; r = m.r_last; exit_ok = tail_ok; }
-    if (!done) {
-      const int i = n + 1;
-      double x = d_mul(p, lam);
-      double pn1 = in_window(x) ? div_f32den(x, mu, r) : d_div(x, mu);
-      double pi = (sum_ok && in_window(pn1)) ? div_markstein2(pn1, sum, rsum) : d_div(pn1, sum);
-      states++;
-      double L2 = d_add(L, d_mul((double)i, pi));
-      double sP2 = d_add(sumP, pi);
-      if (i == N) { Lserv = d_add(L2, d_mul(d_sub(1.0, sP2), (double)N)); lserv_set = true; }
-      bool fin = (i == K) || (d_bits(pn1) == 0);
-      if (!fin && exit_ok) {
-        double tmax = d_mul((double)K, pi);
-        fin = (d_bits(d_add(L2, tmax)) == d_bits(L2)) && (d_bits(d_add(sP2, pi)) == d_bits(sP2));
-      }
-      L = L2; sumP = sP2; p = pn1;
-      if (fin) { pK = (i == K) ? pi : 0.0; done = true; }
-    }
-    n++;
-  }
-  if (!lserv_set) Lserv = d_add(L, d_mul(d_sub(1.0, sumP), (double)N));
-  st.avgNumInServers = (float)Lserv;
-  st.avgNumInSystem = (float)L;
-  st.throughput = f_mul(lambda, f_sub(1.0f, (float)pK));
-  st.avgRespTime = f_div(st.avgNumInSystem, st.throughput);
-  st.avgServTime = f_div(st.avgNumInServers, st.throughput);
-  float w = f_sub(st.avgRespTime, st.avgServTime);
-  st.avgWaitTime = (w < 0.0f) ? 0.0f : w;
-}
-
-// evaluation values of a finished solve (EvalTTFT / EvalITL, queueanalyzer.go:283-308)
-__device__ __forceinline__ void eval_values(const PairModel& m, const SolveStats& st, float* ttft, float* itl, float* pf) {
-  *pf = prefill_time(m, st.avgNumInServers);
-  *itl = f_div(f_sub(st.avgServTime, *pf), m.out_tok);
-  *ttft = f_add(f_add(st.avgWaitTime, *pf), *itl);
-}
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -121,6 +32,7 @@ sizer_warp_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
   double2* tab = smem_tab2 + (size_t)warp * nmax;
   float* tabf = (float*)(smem_tab2 + (size_t)WARPS * nmax) + (size_t)warp * nmax;  // float32 copy for model_finish
   long long my_states = 0;
+  int sv_states = 0;
   unsigned long long my_solves = 0;
 
   while (true) {
@@ -173,7 +85,7 @@ sizer_warp_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
         if (lane == 0) { x = m.lambda_min; act = true; }
         else if (lane == 1) { x = m.lambda_max; act = true; }
         else if (lane < 2 + 15) { int node = lane - 1; x = spec_node_x(m.lambda_min, m.lambda_max, node, spec_depth_of(node)); act = true; }
-        warp_solve(m, tab, x, act, st, my_states, ovf);
+        lockstep_solve(m, WarpTable{tab}, x, act, st, sv_states, ovf); my_states += sv_states;
         solves += 17;
         if (__any_sync(full, act && ovf)) ovf_any = true;
         eval_values(m, st, &y_t, &y_i, &pf);
@@ -205,7 +117,7 @@ sizer_warp_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
           else { node = lane + 1; mine_is_I = sI.active; act = lane < 31; }
           const Search& mq = mine_is_I ? sI : sT;
           x = act ? spec_node_x(mq.lo, mq.hi, node, spec_depth_of(node)) : 0.0f;
-          warp_solve(m, tab, x, act, st, my_states, ovf);
+          lockstep_solve(m, WarpTable{tab}, x, act, st, sv_states, ovf); my_states += sv_states;
           solves += both ? 30 : 31;
           if (__any_sync(full, act && ovf)) { ovf_any = true; break; }
           eval_values(m, st, &y_t, &y_i, &pf);
@@ -229,7 +141,7 @@ sizer_warp_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
       float request_rate = f_mul(lambda, 1000.0f);
       if (!analyze_admits(m, request_rate)) failed = true;
       else {
-        warp_solve(m, tab, f_div(request_rate, 1000.0f), lane == 0, st, my_states, ovf);
+        lockstep_solve(m, WarpTable{tab}, f_div(request_rate, 1000.0f), lane == 0, st, sv_states, ovf); my_states += sv_states;
         solves++;
         if (__shfl_sync(full, (int)ovf, 0)) ovf_any = true;
         else {
@@ -241,7 +153,7 @@ sizer_warp_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
           float rate = f_div(z.total_rate, (float)nr);
           if (!analyze_admits(m, rate)) failed = true;
           else {
-            warp_solve(m, tab, f_div(rate, 1000.0f), lane == 0, st, my_states, ovf);
+            lockstep_solve(m, WarpTable{tab}, f_div(rate, 1000.0f), lane == 0, st, sv_states, ovf); my_states += sv_states;
             solves++;
             if (__shfl_sync(full, (int)ovf, 0)) ovf_any = true;
             else if (lane == 0) {

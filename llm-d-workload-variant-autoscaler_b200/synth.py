@@ -128,8 +128,11 @@ def saturation_batch(M: int, V_per_model: int = 32, stream: int = 4, max_replica
     assert P < 2**31
     # per-model load level so that every branch occurs: idle models (scale-down safe), busy models
     # (no action) and hot models (scale-up)
-    level = np.repeat(g.choice([0.45, 1.0, 1.75], M, p=[0.35, 0.35, 0.30]), V_per_model)
-    kv = np.minimum(g.beta(2.0, 3.0, P) * np.repeat(level, nrep), 0.999)
+    level = np.repeat(np.repeat(g.choice([0, 1, 2], M, p=[0.35, 0.35, 0.30]), V_per_model), nrep)
+    kv = g.beta(2.0, 3.0, P)
+    kv[level == 0] *= 0.45                                                # idle: spare KV ~0.6
+    hot_m = level == 2                                                    # hot: spare KV ~0.06 < trigger 0.1
+    kv[hot_m] = g.uniform(0.68, 0.795, int(hot_m.sum()))
     hot = g.random(P) < 0.10
     kv[hot] = g.uniform(0.8, 1.0, int(hot.sum()))
     queue = g.poisson(1.5, P).astype(np.int64)

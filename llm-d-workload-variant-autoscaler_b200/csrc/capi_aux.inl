@@ -47,16 +47,18 @@ extern "C" int32_t wva_grid_run(wva_ctx* ctx, int32_t R, int32_t full) {
     CK(cudaMemcpyAsync(&nmax, d_nmax, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (nmax < 1) nmax = 1;
-    if (nmax > 8192) { ctx->last_error = "grid: max batch size above 8192"; return WVA_ERR_LIMIT; }
-    // warps per CTA so that (a) the per-warp float32 tables fit and (b) >= 32 warps sit on an SM
-    const size_t per_warp = (size_t)nmax * 4;
+    // per-warp head table: (mu, 1/mu) float64 pairs + the float32 copy = 20 B per state
+    const size_t per_warp = (size_t)nmax * 20;
+    if (per_warp + 1024 > 200 * 1024) { ctx->last_error = "grid: max batch size above 10188"; return WVA_ERR_LIMIT; }
     cudaError_t e;
-    if (per_warp * 8 <= 48 * 1024) {
-      int per_sm = (int)((200 * 1024) / (per_warp * 8 + 1024)); if (per_sm > 8) per_sm = 8; if (per_sm < 1) per_sm = 1;
+    if (per_warp * 8 <= 64 * 1024) {
+      int per_sm = (int)((200 * 1024) / (per_warp * 8 + 1024)); if (per_sm > 6) per_sm = 6; if (per_sm < 1) per_sm = 1;
       e = launch_grid<8>(ctx, ctx->sm_count * per_sm, per_warp * 8, R, g.view, P, nmax, g.ctr);
-    } else {
+    } else if (per_warp * 4 + 1024 <= 200 * 1024) {
       int per_sm = (int)((200 * 1024) / (per_warp * 4 + 1024)); if (per_sm > 8) per_sm = 8; if (per_sm < 1) per_sm = 1;
       e = launch_grid<4>(ctx, ctx->sm_count * per_sm, per_warp * 4, R, g.view, P, nmax, g.ctr);
+    } else {
+      e = launch_grid<1>(ctx, ctx->sm_count * 4, per_warp, R, g.view, P, nmax, g.ctr);
     }
     if (e != cudaSuccess) { ctx->last_error = std::string("grid launch: ") + cudaGetErrorString(e); return WVA_ERR_CUDA; }
   }

@@ -2,14 +2,16 @@
 // QueueAnalyzer.Analyze(totalRate / r) (pkg/analyzer/queueanalyzer.go:127-167), the
 // call CreateAllocation makes at pkg/core/allocation.go:140-148 with numReplicas = r.
 //
-// Mapping: one warp per (server, accelerator) pair.  The pair's head table mu_n is
-// built once by the warp into shared memory; the 32 lanes then pull replica levels
-// r = 1, 2, ... from a warp-local counter (largest arrival rate first) and each runs
-// its own chain solve through the same flattened state machine as the sizer, so a
-// lane that finishes early immediately starts the next replica level.  The per-pair
-// frontier (smallest r meeting every SLO) is a warp-shuffle min.
+// Mapping: one warp per (server, accelerator) pair ("one block per model sweeps its
+// variant x replica grid" at warp granularity).  The pair's head table (mu_n, 1/mu_n)
+// is built once by the warp into shared memory; the 32 lanes then take 32 consecutive
+// replica levels per round and solve their chains in lock step (lockstep_solve.cuh):
+// broadcast table reads, no per-state control flow, a lane whose terms became no-ops
+// idles until the round's longest chain ends.  The per-pair frontier (smallest r meeting
+// every SLO) is a warp-shuffle min.
 #pragma once
 #include "wva_core.cuh"
+#include "lockstep_solve.cuh"
 
 namespace wva {
 
@@ -47,10 +49,11 @@ __device__ __forceinline__ bool grid_setup(PairModel& m, const SysView& s, int s
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax, GridCounters* ctr) {
-  extern __shared__ float smem_tab[];
+  extern __shared__ double2 smem_grid[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* tab = smem_tab + (size_t)warp * nmax;
+  double2* tab = smem_grid + (size_t)warp * nmax;
+  float* tabf = (float*)(smem_grid + (size_t)WARPS * nmax) + (size_t)warp * nmax;
   unsigned long long my_solves = 0, my_states = 0;
 
   while (true) {
@@ -77,77 +80,72 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
       continue;
     }
     __syncwarp();
-    model_fill_table(m, tab, 1, lane, 32);
+    for (int n = lane; n < m.N; n += 32) {
+      float mu32 = serv_rate(m, n + 1);
+      double mu = (double)mu32;
+      tabf[n] = mu32;
+      tab[n] = make_double2(mu, rcp_f32den(mu32, mu));
+    }
     __syncwarp();
-    model_finish(m, tab, 1);
+    model_finish(m, tabf, 1);
     const float lambda_tps = f_mul(m.lambda_max, f_sub(1.0f, WVA_STABILITY_SAFETY));
+    int front = 0x7fffffff;
 
-    Chain c;
-    SolveStats st;
-    bool live = false;
-    int my_r = 0, next_r = 1, front = 0x7fffffff;
-    float my_rate = 0.0f;
-    while (true) {
-      // hand out replica levels to idle lanes (warp-uniform counter)
-      unsigned want = __ballot_sync(full, !live);
-      if (want && next_r <= R) {
-        int rank = __popc(want & ((1u << lane) - 1u));
-        if (!live) {
-          int r = next_r + rank;
-          if (r <= R) {
-            my_r = r;
-            my_rate = f_div(total_rate, (float)r);
-            if (analyze_admits(m, my_rate)) {
-              chain_start(c, f_div(my_rate, 1000.0f));
-              c.tail_ok = d_bits(c.lamg) <= d_bits(m.mu_last);
-              live = true;
-              my_solves++;
-            } else {
-              size_t o = obase + (size_t)(r - 1);
-              if (out.ok) out.ok[o] = 0;
-              if (out.ttft) out.ttft[o] = 0.0f;
-              if (out.itl) out.itl[o] = 0.0f;
-              if (out.rho) out.rho[o] = 0.0f;
-              if (out.tput) out.tput[o] = 0.0f;
-            }
-          }
+    for (int r0 = 0; r0 < R; r0 += 32) {
+      const int r = r0 + lane + 1;
+      const bool in_range = r <= R;
+      const float rate = f_div(total_rate, (float)r);
+      const bool admitted = in_range && analyze_admits(m, rate);      // queueanalyzer.go:128-136
+      if (!__any_sync(full, admitted)) {
+        if (in_range) {
+          const size_t o = obase + (size_t)(r - 1);
+          if (out.ok) out.ok[o] = 0;
+          if (out.ttft) out.ttft[o] = 0.0f;
+          if (out.itl) out.itl[o] = 0.0f;
+          if (out.rho) out.rho[o] = 0.0f;
+          if (out.tput) out.tput[o] = 0.0f;
         }
-        next_r += __popc(want);
+        continue;
       }
-      if (!__any_sync(full, live)) { if (next_r > R) break; else continue; }
-      for (int it = 0; it < 64; it++) {
-        if (live) {
-          if (chain_step(c, m, st)) {
-            live = false;
-            my_states += c.states;
-            size_t o = obase + (size_t)(my_r - 1);
-            if (c.phase == CH_OVERFLOW) {
-              // recorded; the exact overflow-rescale path is only wired for the sizer
-              if (lane >= 0) atomicAdd(&ctr->overflow, 1ull);
-              if (out.ok) out.ok[o] = 0;
-              if (out.ttft) out.ttft[o] = 0.0f;
-              if (out.itl) out.itl[o] = 0.0f;
-              if (out.rho) out.rho[o] = 0.0f;
-              if (out.tput) out.tput[o] = 0.0f;
-            } else {
-              // Analyze: queueanalyzer.go:143-166
-              float pf = prefill_time(m, st.avgNumInServers);
-              float dec = f_div(f_sub(st.avgServTime, pf), m.out_tok);
-              float avg_ttft = f_add(f_add(st.avgWaitTime, pf), dec);
-              float rho = f_div(st.avgNumInServers, (float)m.N);
-              rho = fminf(fmaxf(rho, 0.0f), 1.0f);
-              if (out.ok) out.ok[o] = 1;
-              if (out.ttft) out.ttft[o] = f_add(st.avgWaitTime, pf);   // allocation.go:148
-              if (out.itl) out.itl[o] = dec;
-              if (out.rho) out.rho[o] = rho;
-              if (out.tput) out.tput[o] = f_mul(st.throughput, 1000.0f);
-              bool meets = (slo_ttft <= 0.0f || avg_ttft <= slo_ttft) && (slo_itl <= 0.0f || dec <= slo_itl) &&
-                           (slo_tps <= 0.0f || f_div(my_rate, 1000.0f) <= lambda_tps);
-              if (meets && my_r < front) front = my_r;
-            }
-          }
+      const float lambda = f_div(rate, 1000.0f);
+      SolveStats st;
+      int sv = 0;
+      bool bad = false, ovf = false;
+      lockstep_solve(m, WarpTable{tab}, lambda, admitted, st, sv, bad);
+      if (admitted) { my_solves++; my_states += (unsigned long long)sv; }
+      if (admitted && bad) {
+        // outside the exponent window: redo this level alone through the per-lane state machine
+        // (IEEE divisions); a true float64 overflow stays flagged (only the sizer has the rescale path)
+        Chain c;
+        chain_start(c, lambda);
+        c.tail_ok = d_bits(c.lamg) <= d_bits(m.mu_last);
+        while (!chain_step(c, m, st)) {}
+        ovf = c.phase == CH_OVERFLOW;
+        if (ovf) atomicAdd(&ctr->overflow, 1ull);
+      }
+      if (in_range) {
+        const size_t o = obase + (size_t)(r - 1);
+        if (!admitted || ovf) {
+          if (out.ok) out.ok[o] = 0;
+          if (out.ttft) out.ttft[o] = 0.0f;
+          if (out.itl) out.itl[o] = 0.0f;
+          if (out.rho) out.rho[o] = 0.0f;
+          if (out.tput) out.tput[o] = 0.0f;
+        } else {
+          // Analyze: queueanalyzer.go:143-166
+          float pf, dec, avg_ttft;
+          eval_values(m, st, &avg_ttft, &dec, &pf);
+          float rho = f_div(st.avgNumInServers, (float)m.N);
+          rho = fminf(fmaxf(rho, 0.0f), 1.0f);
+          if (out.ok) out.ok[o] = 1;
+          if (out.ttft) out.ttft[o] = f_add(st.avgWaitTime, pf);   // allocation.go:148
+          if (out.itl) out.itl[o] = dec;
+          if (out.rho) out.rho[o] = rho;
+          if (out.tput) out.tput[o] = f_mul(st.throughput, 1000.0f);
+          bool meets = (slo_ttft <= 0.0f || avg_ttft <= slo_ttft) && (slo_itl <= 0.0f || dec <= slo_itl) &&
+                       (slo_tps <= 0.0f || lambda <= lambda_tps);
+          if (meets && r < front) front = r;
         }
-        if ((it & 7) == 7 && (!__any_sync(full, live) || (next_r <= R && __any_sync(full, !live)))) break;
       }
     }
     for (int o = 16; o; o >>= 1) front = min(front, __shfl_down_sync(full, front, o));

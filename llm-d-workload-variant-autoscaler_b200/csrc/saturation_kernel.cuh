@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(256) saturation_kernel(SatIn in, SatOut out) {
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   long long n_up = 0, n_down = 0, n_trans = 0, sum_targets = 0;
+  const double* __restrict__ in_kv = in.rep_kv;
+  const long long* __restrict__ in_q = in.rep_queue;
+  __shared__ double2 terms[8][32];
+  double2* my_terms = terms[threadIdx.x >> 5];
 
   for (long long m = warp0; m < in.n_models; m += nwarps) {
     const int v0 = in.model_variant_off[m], v1 = in.model_variant_off[m + 1];
@@ -68,18 +72,32 @@ __global__ void __launch_bounds__(256) saturation_kernel(SatIn in, SatOut out) {
       if (act) {
         const int lo = in.variant_replica_off[v], hi = in.variant_replica_off[v + 1];
         cnt = hi - lo;
-        for (int i = lo; i < hi; i++) {
-          const double kv = in.rep_kv[i];
-          const long long q = in.rep_queue[i];
-          const bool sat = kv >= kvThr || (double)q >= qThr;               // analyzer.go:160-161
-          if (out.rep_saturated) out.rep_saturated[i] = sat ? 1 : 0;
-          if (!sat) {
-            sumKv = d_add(sumKv, d_sub(kvThr, kv));                        // :167-171
-            sumQ = d_add(sumQ, d_sub(qThr, (double)q));
-            ns++;
+        // replicas are streamed 4 at a time: the 8 loads of a batch are independent (one memory
+        // round trip), the accumulation below stays in slice order (float64 sums are order dependent)
+        for (int base = lo; base < hi; base += 4) {
+          double kvv[4]; long long qq[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const bool in = base + j < hi;
+            kvv[j] = in ? __ldg(in_kv + base + j) : 0.0;
+            qq[j] = in ? __ldg(in_q + base + j) : 0;
           }
-          if (kv > maxKv) maxKv = kv;                                      // :177-182
-          if (q > maxQ) maxQ = q;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (base + j < hi) {
+              const double kv = kvv[j];
+              const long long q = qq[j];
+              const bool sat = kv >= kvThr || (double)q >= qThr;               // analyzer.go:160-161
+              if (out.rep_saturated) out.rep_saturated[base + j] = sat ? 1 : 0;
+              if (!sat) {
+                sumKv = d_add(sumKv, d_sub(kvThr, kv));                        // :167-171
+                sumQ = d_add(sumQ, d_sub(qThr, (double)q));
+                ns++;
+              }
+              if (kv > maxKv) maxKv = kv;                                      // :177-182
+              if (q > maxQ) maxQ = q;
+            }
+          }
         }
         if (ns > 0) { avgKv = d_div(sumKv, (double)ns); avgQ = d_div(sumQ, (double)ns); }  // :188-191
         if (out.var_replica_count) out.var_replica_count[v] = cnt;
@@ -93,10 +111,14 @@ __global__ void __launch_bounds__(256) saturation_kernel(SatIn in, SatOut out) {
       // ordered accumulation over the chunk (analyzer.go:86-94)
       const double termKv = d_mul(avgKv, (double)ns), termQ = d_mul(avgQ, (double)ns);
       const unsigned amask = __ballot_sync(full, analysed);
-      const int chunk_n = min(32, v1 - c0);
-      for (int l = 0; l < chunk_n; l++) {
-        const double tk = shfl_d(full, termKv, l), tq = shfl_d(full, termQ, l);
-        if ((amask >> l) & 1u) { totalSpareKv = d_add(totalSpareKv, tk); totalSpareQueue = d_add(totalSpareQueue, tq); }
+      // in ascending variant order, through shared memory (broadcast reads; exact sequential sum)
+      __syncwarp();
+      my_terms[lane] = make_double2(termKv, termQ);
+      __syncwarp();
+      for (unsigned rest = amask; rest; rest &= rest - 1) {
+        const double2 t2 = my_terms[__ffs(rest) - 1];
+        totalSpareKv = d_add(totalSpareKv, t2.x);
+        totalSpareQueue = d_add(totalSpareQueue, t2.y);
       }
       int t;
       t = analysed ? ns : 0;  for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(full, t, o);  nonSaturated += t;

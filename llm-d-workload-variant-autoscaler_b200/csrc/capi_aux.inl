@@ -217,7 +217,8 @@ extern "C" int32_t wva_saturation_run(wva_ctx* ctx, int32_t detail) {
     long long blocks = (warps * 32 + 255) / 256;
     long long cap = (long long)ctx->sm_count * 32;
     if (blocks > cap) blocks = cap;
-    saturation_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(st.vin, w);
+    if (detail) saturation_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(st.vin, w);
+    else saturation_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(st.vin, w);
     ctx->launches++;
     CK(cudaGetLastError());
   }

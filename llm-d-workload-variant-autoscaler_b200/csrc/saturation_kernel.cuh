@@ -4,10 +4,12 @@
 // CalculateSaturationTargets (analyzer.go:290-439).
 //
 // One warp per model, one lane per variant (chunks of 32).  A lane streams its
-// variant's replicas in slice order (the per-variant float64 sums are order
-// dependent); the variant -> model accumulation runs in ascending variant index on
-// every lane redundantly (canonical order, see oracle/saturation.hpp).  HBM-bound:
-// 16 B per replica (kv float64 + queue int64) is the only large stream.
+// variant's replicas in slice order, 4 independent loads at a time (the per-variant
+// float64 sums are order dependent); the variant -> model accumulation runs in
+// ascending variant index through shared memory (broadcast reads, fixed 32-step
+// unrolled chain; lanes without metrics contribute an exact +0.0).  The cheapest /
+// most-expensive variant search runs only for the models that scale.  HBM-bound by
+// design: 16 B per replica (kv float64 + queue int64) is the only large stream.
 #pragma once
 #include "wva_core.cuh"
 
@@ -36,12 +38,13 @@ struct SatOut {
 #define SAT_FLAG_KV 8
 #define SAT_FLAG_Q 16
 
-__device__ __forceinline__ double shfl_d(unsigned mask, double v, int src) {
-  int lo = __shfl_sync(mask, __double2loint(v), src), hi = __shfl_sync(mask, __double2hiint(v), src);
+__device__ __forceinline__ double shfl_xor_d(unsigned mask, double v, int lanemask) {
+  int lo = __shfl_xor_sync(mask, __double2loint(v), lanemask), hi = __shfl_xor_sync(mask, __double2hiint(v), lanemask);
   return __hiloint2double(hi, lo);
 }
 
-__global__ void __launch_bounds__(256) saturation_kernel(SatIn in, SatOut out) {
+template <bool DETAIL>
+__global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -49,6 +52,7 @@ __global__ void __launch_bounds__(256) saturation_kernel(SatIn in, SatOut out) {
   long long n_up = 0, n_down = 0, n_trans = 0, sum_targets = 0;
   const double* __restrict__ in_kv = in.rep_kv;
   const long long* __restrict__ in_q = in.rep_queue;
+  const int* __restrict__ vro = in.variant_replica_off;
   __shared__ double2 terms[8][32];
   double2* my_terms = terms[threadIdx.x >> 5];
 
@@ -59,8 +63,6 @@ __global__ void __launch_bounds__(256) saturation_kernel(SatIn in, SatOut out) {
     double totalSpareKv = 0.0, totalSpareQueue = 0.0;
     int nonSaturated = 0, totalReplicas = 0, nAnalysed = 0;
     bool inTransition = false;
-    int cheap_v = -1, exp_v = -1;
-    double cheap_c = 0.0, exp_c = 0.0;
 
     // ---- phase A: analyzeVariant per lane, ordered combine ---------------------------------
     for (int c0 = v0; c0 < v1; c0 += 32) {
@@ -70,87 +72,67 @@ __global__ void __launch_bounds__(256) saturation_kernel(SatIn in, SatOut out) {
       double sumKv = 0.0, sumQ = 0.0, maxKv = 0.0, avgKv = 0.0, avgQ = 0.0;
       long long maxQ = 0;
       if (act) {
-        const int lo = in.variant_replica_off[v], hi = in.variant_replica_off[v + 1];
+        const int lo = vro[v], hi = vro[v + 1];
         cnt = hi - lo;
-        // replicas are streamed 4 at a time: the 8 loads of a batch are independent (one memory
-        // round trip), the accumulation below stays in slice order (float64 sums are order dependent)
         for (int base = lo; base < hi; base += 4) {
           double kvv[4]; long long qq[4];
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            const bool in = base + j < hi;
-            kvv[j] = in ? __ldg(in_kv + base + j) : 0.0;
-            qq[j] = in ? __ldg(in_q + base + j) : 0;
+            const bool inb = base + j < hi;
+            kvv[j] = inb ? __ldg(in_kv + base + j) : 0.0;
+            qq[j] = inb ? __ldg(in_q + base + j) : 0;
           }
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             if (base + j < hi) {
               const double kv = kvv[j];
               const long long q = qq[j];
-              const bool sat = kv >= kvThr || (double)q >= qThr;               // analyzer.go:160-161
-              if (out.rep_saturated) out.rep_saturated[base + j] = sat ? 1 : 0;
+              const double qd = (double)q;
+              const bool sat = kv >= kvThr || qd >= qThr;                       // analyzer.go:160-161
+              if (DETAIL) { if (out.rep_saturated) out.rep_saturated[base + j] = sat ? 1 : 0; }
               if (!sat) {
                 sumKv = d_add(sumKv, d_sub(kvThr, kv));                        // :167-171
-                sumQ = d_add(sumQ, d_sub(qThr, (double)q));
+                sumQ = d_add(sumQ, d_sub(qThr, qd));
                 ns++;
               }
-              if (kv > maxKv) maxKv = kv;                                      // :177-182
-              if (q > maxQ) maxQ = q;
+              if (DETAIL) {
+                if (kv > maxKv) maxKv = kv;                                    // :177-182
+                if (q > maxQ) maxQ = q;
+              }
             }
           }
         }
         if (ns > 0) { avgKv = d_div(sumKv, (double)ns); avgQ = d_div(sumQ, (double)ns); }  // :188-191
-        if (out.var_replica_count) out.var_replica_count[v] = cnt;
-        if (out.var_non_saturated) out.var_non_saturated[v] = ns;
-        if (out.var_max_kv) out.var_max_kv[v] = maxKv;
-        if (out.var_max_queue) out.var_max_queue[v] = maxQ;
-        if (out.var_avg_spare_kv) out.var_avg_spare_kv[v] = avgKv;
-        if (out.var_avg_spare_queue) out.var_avg_spare_queue[v] = avgQ;
+        if (DETAIL) {
+          if (out.var_replica_count) out.var_replica_count[v] = cnt;
+          if (out.var_non_saturated) out.var_non_saturated[v] = ns;
+          if (out.var_max_kv) out.var_max_kv[v] = maxKv;
+          if (out.var_max_queue) out.var_max_queue[v] = maxQ;
+          if (out.var_avg_spare_kv) out.var_avg_spare_kv[v] = avgKv;
+          if (out.var_avg_spare_queue) out.var_avg_spare_queue[v] = avgQ;
+        }
       }
       const bool analysed = act && cnt > 0;   // only variants with metrics enter VariantAnalyses
-      // ordered accumulation over the chunk (analyzer.go:86-94)
-      const double termKv = d_mul(avgKv, (double)ns), termQ = d_mul(avgQ, (double)ns);
-      const unsigned amask = __ballot_sync(full, analysed);
-      // in ascending variant order, through shared memory (broadcast reads; exact sequential sum)
+      // ordered accumulation over the chunk (analyzer.go:86-94).  A variant without metrics has
+      // ns == 0 -> term +0.0, and x + 0.0 == x exactly, so all 32 slots are added unconditionally.
+      const double termKv = analysed ? d_mul(avgKv, (double)ns) : 0.0, termQ = analysed ? d_mul(avgQ, (double)ns) : 0.0;
       __syncwarp();
       my_terms[lane] = make_double2(termKv, termQ);
       __syncwarp();
-      for (unsigned rest = amask; rest; rest &= rest - 1) {
-        const double2 t2 = my_terms[__ffs(rest) - 1];
+#pragma unroll
+      for (int l = 0; l < 32; l++) {
+        const double2 t2 = my_terms[l];
         totalSpareKv = d_add(totalSpareKv, t2.x);
         totalSpareQueue = d_add(totalSpareQueue, t2.y);
       }
-      int t;
-      t = analysed ? ns : 0;  for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(full, t, o);  nonSaturated += t;
-      t = act ? cnt : 0;      for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(full, t, o);  totalReplicas += t;
-      nAnalysed += __popc(amask);
+      nonSaturated += __reduce_add_sync(full, analysed ? ns : 0);
+      totalReplicas += __reduce_add_sync(full, act ? cnt : 0);
+      nAnalysed += __popc(__ballot_sync(full, analysed));
       // transition checks (analyzer.go:322-341); a variant without state reads the zero value
       const bool hs = act && (!in.var_has_state || in.var_has_state[v]);
-      const int cur = hs ? in.var_current[v] : 0, des = hs ? in.var_desired[v] : 0, pen = hs ? in.var_pending[v] : 0;
+      const int cur = hs ? in.var_current[v] : 0, des = hs ? in.var_desired[v] : 0;
       const bool trans = analysed && ((des != 0 && des != cur) || (cnt != cur));
       if (__any_sync(full, trans)) inTransition = true;
-      // scale-up candidate: cheapest without pending, tie -> lower index (:378-395)
-      {
-        double c = (analysed && pen <= 0) ? in.var_cost[v] : 0.0;
-        int idx = (analysed && pen <= 0) ? v : -1;
-        for (int o = 16; o; o >>= 1) {
-          double oc = shfl_d(full, c, lane ^ o); int oi = __shfl_xor_sync(full, idx, o);
-          bool take = oi >= 0 && (idx < 0 || oc < c || (oc == c && oi < idx));
-          if (take) { c = oc; idx = oi; }
-        }
-        if (idx >= 0 && (cheap_v < 0 || c < cheap_c)) { cheap_v = idx; cheap_c = c; }
-      }
-      // scale-down candidate: most expensive with base target > 1, tie -> higher index (:407-425)
-      {
-        double c = (analysed && cnt > 1) ? in.var_cost[v] : 0.0;
-        int idx = (analysed && cnt > 1) ? v : -1;
-        for (int o = 16; o; o >>= 1) {
-          double oc = shfl_d(full, c, lane ^ o); int oi = __shfl_xor_sync(full, idx, o);
-          bool take = oi >= 0 && (idx < 0 || oc > c || (oc == c && oi > idx));
-          if (take) { c = oc; idx = oi; }
-        }
-        if (idx >= 0 && (exp_v < 0 || c >= exp_c)) { exp_v = idx; exp_c = c; }
-      }
     }
 
     // ---- model level (analyzer.go:96-121, 199-280) ---------------------------------------------
@@ -172,36 +154,64 @@ __global__ void __launch_bounds__(256) saturation_kernel(SatIn in, SatOut out) {
       }
     }
     if (lane == 0) {
-      if (out.mod_total_replicas) out.mod_total_replicas[m] = totalReplicas;
-      if (out.mod_non_saturated) out.mod_non_saturated[m] = nonSaturated;
-      if (out.mod_avg_spare_kv) out.mod_avg_spare_kv[m] = avgSpareKv;
-      if (out.mod_avg_spare_queue) out.mod_avg_spare_queue[m] = avgSpareQueue;
+      if (DETAIL) {
+        if (out.mod_total_replicas) out.mod_total_replicas[m] = totalReplicas;
+        if (out.mod_non_saturated) out.mod_non_saturated[m] = nonSaturated;
+        if (out.mod_avg_spare_kv) out.mod_avg_spare_kv[m] = avgSpareKv;
+        if (out.mod_avg_spare_queue) out.mod_avg_spare_queue[m] = avgSpareQueue;
+      }
       if (out.mod_flags)
         out.mod_flags[m] = (up ? SAT_FLAG_UP : 0) | (downSafe ? SAT_FLAG_DOWN : 0) | (inTransition ? SAT_FLAG_TRANS : 0) |
                            (kvT ? SAT_FLAG_KV : 0) | (qT ? SAT_FLAG_Q : 0);
     }
-    // ---- targets (analyzer.go:303-436) ------------------------------------------------------------
+    // ---- scaling candidate, only for the models that scale (analyzer.go:376-433) -------------------
     int plus_v = -1, minus_v = -1;
-    if (nAnalysed > 0 && !inTransition) {
-      if (up) plus_v = cheap_v;
-      else if (downSafe) minus_v = exp_v;
+    const bool stable = nAnalysed > 0 && !inTransition;
+    if (stable && (up || downSafe)) {
+      const bool want_min = up;    // cheapest without pending, tie -> lower index (:378-395)
+                                   // else most expensive with base target > 1, tie -> higher index (:407-425)
+      int best_v = -1;
+      double best_c = 0.0;
+      for (int c0 = v0; c0 < v1; c0 += 32) {
+        const int v = c0 + lane;
+        bool cand = false;
+        if (v < v1) {
+          const int cnt = vro[v + 1] - vro[v];
+          const bool hs = !in.var_has_state || in.var_has_state[v];
+          const int pen = hs ? in.var_pending[v] : 0;
+          cand = cnt > 0 && (want_min ? (pen <= 0) : (cnt > 1));
+        }
+        double c = cand ? in.var_cost[v] : 0.0;
+        int idx = cand ? v : -1;
+        for (int o = 16; o; o >>= 1) {
+          const double oc = shfl_xor_d(full, c, o);
+          const int oi = __shfl_xor_sync(full, idx, o);
+          const bool take = oi >= 0 && (idx < 0 || (want_min ? (oc < c || (oc == c && oi < idx))
+                                                              : (oc > c || (oc == c && oi > idx))));
+          if (take) { c = oc; idx = oi; }
+        }
+        if (idx >= 0 && (best_v < 0 || (want_min ? (c < best_c) : (c >= best_c)))) { best_v = idx; best_c = c; }
+      }
+      if (want_min) plus_v = best_v; else minus_v = best_v;
     }
     if (lane == 0) {
       if (nAnalysed > 0 && inTransition) n_trans++;
       if (plus_v >= 0) n_up++;
       if (minus_v >= 0) n_down++;
     }
+    // ---- targets (analyzer.go:303-436) ------------------------------------------------------------
     for (int c0 = v0; c0 < v1; c0 += 32) {
       const int v = c0 + lane;
       if (v >= v1) continue;
-      const int cnt = in.variant_replica_off[v + 1] - in.variant_replica_off[v];
+      const int cnt = vro[v + 1] - vro[v];
       const bool hs = !in.var_has_state || in.var_has_state[v];
-      const int cur = hs ? in.var_current[v] : 0, des = hs ? in.var_desired[v] : 0;
       int tgt;
-      if (nAnalysed == 0) tgt = hs ? in.var_current[v] : -1;          // nil safety :303-309
+      if (nAnalysed == 0) tgt = hs ? in.var_current[v] : -1;            // nil safety :303-309
       else if (cnt == 0) tgt = -1;                                      // not in VariantAnalyses
-      else if (inTransition) tgt = (des != 0 && des != cur) ? des : cur;  // :350-359
-      else tgt = cnt + (v == plus_v ? 1 : 0) - (v == minus_v ? 1 : 0);   // :362, :399, :428
+      else if (inTransition) {                                          // :350-359
+        const int cur = hs ? in.var_current[v] : 0, des = hs ? in.var_desired[v] : 0;
+        tgt = (des != 0 && des != cur) ? des : cur;
+      } else tgt = cnt + (v == plus_v ? 1 : 0) - (v == minus_v ? 1 : 0);   // :362, :399, :428
       if (out.var_target) out.var_target[v] = tgt;
       if (tgt >= 0) sum_targets += tgt;
     }

@@ -11,6 +11,7 @@
 #include "saturation_kernel.cuh"
 #include "limiter_kernel.cuh"
 #include "greedy_kernel.cuh"
+#include "greedy_solve.cuh"
 #include "mm1k_kernel.cuh"
 
 #include <cuda_runtime.h>

@@ -1,7 +1,7 @@
 // greedy_kernel.cuh — device side of the slow exact paths:
 //   (1) overflow_slow_kernel: CreateAllocation for the rare pairs whose chain overflows
 //       float64 (literal stored-p[] algorithm, one thread per pair);
-//   (2) run_solve_greedy: Solver.SolveGreedy (pkg/solver/greedy.go:35-341).
+//   (2) Solver.SolveGreedy lives in greedy_solve.cuh.
 #pragma once
 #include "wva_core.cuh"
 #include "solve_kernels.cuh"
@@ -65,13 +65,6 @@ static inline int32_t run_overflow_slow_path(const SysView& s, const CandView& o
   }
   cudaFree(pbuf); cudaFree(tabbuf); cudaFree(d_nmax);
   return rc;
-}
-
-// Solver.SolveGreedy (pkg/solver/greedy.go:35-341).  NOT BUILT YET: limited-capacity mode
-// fails loudly (there is no CPU fallback).
-static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, const SolView& o, int delayed, int policy,
-                                       void** ws, size_t* ws_cap, cudaStream_t stream, long long* launches) {
-  return 4;  // WVA_ERR_STATE
 }
 
 }  // namespace wva

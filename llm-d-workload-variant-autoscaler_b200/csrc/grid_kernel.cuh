@@ -47,7 +47,7 @@ __device__ __forceinline__ bool grid_setup(PairModel& m, const SysView& s, int s
 }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 3 : 1)
+__global__ void __launch_bounds__(WARPS * 32)
 grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax, GridCounters* ctr) {
   extern __shared__ double2 smem_grid[];
   const unsigned full = 0xffffffffu;

@@ -60,8 +60,9 @@ __device__ __forceinline__ void p2_step(P2& s, double lam, double mu, double r, 
 
 // `active` lanes solve at `lambda`; inactive lanes ride along (lambda 0).  On return `bad` is set
 // for a lane whose solve left the exponent window (caller: redo the pair on the slow path).
+// __noinline__: the sizer calls this from four places; one copy keeps the unrolled loops in the I-cache
 template <class Tab>
-__device__ __forceinline__ void lockstep_solve(const PairModel& m, const Tab& tab, float lambda, bool active,
+__device__ __noinline__ void lockstep_solve(const PairModel& m, const Tab& tab, float lambda, bool active,
                                                SolveStats& st, int& states, bool& bad) {
   const unsigned full = 0xffffffffu;
   const int K = m.K, N = m.N, NH = N - 1;

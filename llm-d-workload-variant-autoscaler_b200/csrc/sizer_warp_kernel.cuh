@@ -24,7 +24,7 @@ namespace wva {
 #if defined(__CUDACC__)
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 3 : 1)
+__global__ void __launch_bounds__(WARPS * 32)
 sizer_warp_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax, SizerCounters* ctr, int* overflow_list) {
   extern __shared__ double2 smem_tab2[];
   const unsigned full = 0xffffffffu;

@@ -153,6 +153,73 @@ def test_float64_overflow_rescale_path(pkg, engine, oracle):
     assert engine.timing()["overflow_pairs"] > 0
 
 
+# ---- limited capacity: Solver.SolveGreedy --------------------------------------------------------------
+SOL_INT = ("state", "acc", "num_replicas", "batch_size")
+
+
+def _greedy_case(pkg, engine, oracle, sysd, frac, policy, delayed):
+    engine.load_system(sysd)          # unlimited first: demand defines the capacity
+    engine.calculate()
+    cand = engine.candidates()
+    engine.solve()
+    un = engine.solution()
+    lim = pkg.synth.limit_capacity(sysd, un["type_count"], frac)
+    lim["saturation_policy"] = policy
+    lim["delayed_best_effort"] = delayed
+    engine.load_system(lim)
+    engine.calculate()
+    engine.solve()
+    g = engine.solution()
+    o = oracle.solve(lim, cand)
+    for k in SOL_INT:
+        assert np.array_equal(g[k], o[k]), (k, policy, delayed, np.argwhere(g[k] != o[k])[:5])
+    for k in F32_FIELDS:
+        assert _bit_equal(g[k], o[k]), (k, policy, delayed)
+    assert np.array_equal(g["type_count"], o["type_count"])
+    assert (g["type_count"] <= lim["type_count"]).all()
+    return g, un
+
+
+@pytest.mark.parametrize("policy", ["None", "PriorityExhaustive", "PriorityRoundRobin", "RoundRobin"])
+@pytest.mark.parametrize("delayed", [False, True])
+def test_greedy_matches_oracle(pkg, engine, oracle, policy, delayed):
+    sysd = pkg.synth.queue_system(300, 8, 16, stream=71)
+    g, un = _greedy_case(pkg, engine, oracle, sysd, 0.6, policy, delayed)
+    assert (g["state"] == 0).sum() >= (un["state"] == 0).sum()
+
+
+def test_greedy_ties_and_duplicates(pkg, engine, oracle):
+    """Identical servers give exactly equal (priority, delta, value) keys: the re-insertion rule
+    (before equal elements, latest first) and the canonical initial order must both match."""
+    sysd = pkg.synth.queue_system(96, 6, 16, stream=72)
+    for k, v in list(sysd.items()):
+        if isinstance(v, np.ndarray) and v.shape[:1] == (96,):
+            v[:] = np.concatenate([v[:8]] * 12)       # 12 copies of 8 distinct servers (and their models)
+    for frac in (0.3, 0.6, 0.9):
+        _greedy_case(pkg, engine, oracle, sysd, frac, "None", False)
+        _greedy_case(pkg, engine, oracle, sysd, frac, "PriorityRoundRobin", True)
+
+
+def test_greedy_ample_capacity_equals_unlimited(pkg, engine, oracle):
+    sysd = pkg.synth.queue_system(120, 6, 16, stream=73)
+    g, un = _greedy_case(pkg, engine, oracle, sysd, 10.0, "None", False)
+    assert np.array_equal(g["acc"], un["acc"]) and np.array_equal(g["num_replicas"], un["num_replicas"])
+
+
+def test_greedy_zero_capacity(pkg, engine, oracle):
+    sysd = pkg.synth.queue_system(50, 4, 16, stream=74)
+    engine.load_system(sysd); engine.calculate()
+    cand = engine.candidates()
+    lim = dict(sysd); lim["unlimited"] = False; lim["type_count"] = np.zeros(sysd["n_types"], np.int32)
+    lim["saturation_policy"] = "PriorityExhaustive"
+    engine.load_system(lim); engine.calculate(); engine.solve()
+    g = engine.solution()
+    o = oracle.solve(lim, cand)
+    for k in SOL_INT:
+        assert np.array_equal(g[k], o[k]), k
+    assert ((g["state"] == 1) & (g["num_replicas"] > 0)).sum() == 0
+
+
 # ---- replica grid ------------------------------------------------------------------------------------
 @pytest.mark.parametrize("S,A,N,R,stream", [(10, 4, 32, 32, 1), (24, 8, 128, 128, 2), (6, 3, 256, 70, 3)])
 def test_grid_matches_oracle(pkg, engine, oracle, S, A, N, R, stream):

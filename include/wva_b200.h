@@ -173,7 +173,8 @@ const char* wva_last_error(const wva_ctx* ctx);
 int64_t wva_launch_count(const wva_ctx* ctx);
 
 /* options (wva_set_option): tuning / test hooks, never needed for correctness */
-#define WVA_OPT_FORCE_LANE_SIZER 1 /* 1: always use the lane-per-pair sizer kernel */
+#define WVA_OPT_FORCE_LANE_SIZER 1 /* 0: pick by system size; 1: lane-per-pair, flattened state machine;
+                                      2: lane-per-pair, lock-step rounds (what large systems use) */
 int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value);
 
 /* ---- queueing sizing + allocator ---------------------------------------- */

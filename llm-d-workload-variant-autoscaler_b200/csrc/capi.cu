@@ -6,6 +6,7 @@
 #include "wva_core.cuh"
 #include "sizer_kernel.cuh"
 #include "sizer_warp_kernel.cuh"
+#include "sizer_lane_kernel.cuh"
 #include "solve_kernels.cuh"
 #include "grid_kernel.cuh"
 #include "saturation_kernel.cuh"
@@ -88,6 +89,7 @@ struct wva_ctx {
   // queueing system
   bool loaded = false, calculated = false, solved = false;
   bool force_lane_sizer = false;
+  int lane_sizer_mode = 2;   // 1 flattened, 2 lock-step
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
   int policy = 0;
@@ -271,7 +273,8 @@ int32_t wva_load_system(wva_ctx* ctx, const wva_system* s) {
 template <int THREADS, bool SMEM>
 static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned long long n_pairs, int nmax, float* gtab,
                                 int* ovf_list) {
-  auto k = sizer_kernel<THREADS, SMEM>;
+  // lane_sizer_mode 1 = flattened state machine (sizer_kernel.cuh); otherwise lock-step rounds
+  auto k = (ctx->lane_sizer_mode == 1) ? sizer_kernel<THREADS, SMEM> : sizer_lane_kernel<THREADS, SMEM>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list);
@@ -293,7 +296,11 @@ extern "C" {
 /* test / profiling hook: 1 forces the lane-per-pair sizer regardless of the system size */
 int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
   if (!ctx) return WVA_ERR_ARG;
-  if (option == WVA_OPT_FORCE_LANE_SIZER) { ctx->force_lane_sizer = value != 0; return WVA_OK; }
+  if (option == WVA_OPT_FORCE_LANE_SIZER) {
+    ctx->force_lane_sizer = value != 0;
+    if (value == 1 || value == 2) ctx->lane_sizer_mode = value;
+    return WVA_OK;
+  }
   return WVA_ERR_ARG;
 }
 

@@ -1,0 +1,111 @@
+// sizer_lane_kernel.cuh — System.Calculate for LARGE systems: one lane per (server,
+// accelerator) candidate, persistent CTAs pulling pairs from a global counter, and the
+// chain solves of the 32 pairs of a warp run in lock step (lockstep_solve.cuh) — each lane
+// with its own head table (float32 column in shared memory, bank = lane) and its own
+// arrival rate.  Between solves every lane advances its own bisection / Size / Analyze
+// state machine (wva_core.cuh sizer_on_solve), idle lanes refill from the queue.
+//
+// Compared with sizer_kernel.cuh (one state per loop iteration, lanes in arbitrary
+// phases) the lock-step rounds waste lanes whose chain ends early, but run ~10 instead
+// of ~70 instructions per state.  Lanes of a warp must share N for the lock-step loops
+// to be uniform; a round with mixed N falls back to the per-lane state machine.
+#pragma once
+#include "wva_core.cuh"
+#include "sizer_kernel.cuh"
+#include "lockstep_solve.cuh"
+
+namespace wva {
+
+template <int THREADS, bool SMEM_TABLE>
+__global__ void __launch_bounds__(THREADS)
+sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax, float* gtab,
+                  SizerCounters* ctr, int* overflow_list) {
+  extern __shared__ float smem_tab[];
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  float* tab;
+  int stride;
+  if (SMEM_TABLE) { tab = smem_tab + threadIdx.x; stride = THREADS; }
+  else { tab = gtab + ((size_t)blockIdx.x * THREADS + threadIdx.x); stride = gridDim.x * THREADS; }
+
+  SizerLane z;
+  z.m.N = 1; z.m.K = 11; z.m.mono = 0; z.m.mu_last = 1.0; z.m.r_last = 1.0;
+  SolveStats st;
+  bool live = false, exhausted = false;
+  unsigned long long my_solves = 0, my_states = 0;
+
+  while (true) {
+    // ---- refill ------------------------------------------------------------------------------
+    bool need_table = false;
+    if (!live && !exhausted) {
+      while (true) {
+        unsigned long long pair = atomicAdd(&ctr->next_pair, 1ull);
+        if (pair >= n_pairs) { exhausted = true; break; }
+        int srv = (int)(pair / (unsigned)s.n_acc), acc = (int)(pair % (unsigned)s.n_acc);
+        int lim = 0;
+        int rc = sizer_setup(z, s, out, srv, acc, nmax, &lim);
+        if (lim) ctr->limit_hit = 1;
+        if (rc == SETUP_NEEDS_TABLE) { need_table = true; break; }
+      }
+    }
+    unsigned need = __ballot_sync(full, need_table);
+    while (need) {   // BuildModel, cooperatively (see sizer_kernel.cuh)
+      int src = __ffs(need) - 1;
+      need &= need - 1;
+      PairModel b;
+      b.alpha = __shfl_sync(full, z.m.alpha, src);
+      b.beta = __shfl_sync(full, z.m.beta, src);
+      b.in_tok = __shfl_sync(full, z.m.in_tok, src);
+      b.out_tok = __shfl_sync(full, z.m.out_tok, src);
+      b.slope = __shfl_sync(full, z.m.slope, src);
+      b.pre_c = __shfl_sync(full, z.m.pre_c, src);
+      b.dec_c = __shfl_sync(full, z.m.dec_c, src);
+      b.N = __shfl_sync(full, z.m.N, src);
+      model_fill_table(b, tab + (src - lane), stride, lane, 32);
+    }
+    __syncwarp();
+    if (need_table) {
+      model_finish(z.m, tab, stride);
+      live = sizer_begin(z, s, out);
+      if (!live) my_solves += z.solves;
+    }
+    const unsigned live_mask = __ballot_sync(full, live);
+    if (!live_mask) {
+      if (!__any_sync(full, !exhausted)) break;
+      continue;
+    }
+    // ---- one round: every live lane solves its chain at z.cur_x -------------------------------
+    const int nref = __shfl_sync(full, z.m.N, __ffs(live_mask) - 1);
+    const bool uniform = __all_sync(full, !live || z.m.N == nref);
+    bool bad = false;
+    int sv = 0;
+    if (uniform) {
+      if (!live) { z.m.N = nref; z.m.K = nref + nref * WVA_QUEUE_TO_BATCH; }   // idle lanes only keep the loops uniform
+      LaneTable lt; lt.t = tab; lt.stride = stride;
+      lockstep_solve(z.m, lt, z.cur_x, live, st, sv, bad);
+      z.c.states = sv;
+    } else if (live) {
+      while (!chain_step(z.c, z.m, st)) {}
+      bad = z.c.phase == CH_OVERFLOW;
+    }
+    if (live) {
+      if (bad) {
+        unsigned long long k = atomicAdd(&ctr->overflow_pairs, 1ull);
+        if (overflow_list) overflow_list[k] = z.srv * s.n_acc + z.acc;
+        z.states += z.c.states;
+        lane_fail(z, s, out);
+        live = false;
+      } else {
+        live = sizer_on_solve(z, s, out, st);
+      }
+      if (!live) { my_solves += z.solves; my_states += z.states; }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    my_solves += __shfl_down_sync(full, my_solves, o);
+    my_states += __shfl_down_sync(full, my_states, o);
+  }
+  if (lane == 0) { atomicAdd(&ctr->solves, my_solves); atomicAdd(&ctr->states, my_states); }
+}
+
+}  // namespace wva

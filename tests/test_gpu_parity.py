@@ -45,11 +45,14 @@ def test_calculate_matches_oracle(pkg, engine, oracle, S, A, N, stream):
 
 @pytest.mark.parametrize("S,A,N,stream", [(10, 4, 32, 1), (64, 8, 16, 7), (48, 16, 128, 2), (16, 8, 256, 3),
                                           (33, 5, 1, 11)])
-def test_calculate_lane_kernel_matches_oracle(pkg, engine, oracle, S, A, N, stream):
-    """Small systems default to the warp-per-pair sizer; force the lane-per-pair kernel (the one large
-    systems use) and hold it to the same bar."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_calculate_lane_kernel_matches_oracle(pkg, engine, oracle, S, A, N, stream, mode):
+    """Small systems default to the warp-per-pair sizer; force the lane-per-pair kernels (mode 2 = lock-step
+    rounds, what large systems use; mode 1 = flattened state machine) and hold them to the same bar."""
     sysd = pkg.synth.queue_system(S, A, N, stream=stream)
-    engine.set_option(1, 1)
+    if mode == 2 and N == 128:
+        sysd["srv_max_batch"][::3] = 96          # mixed N inside a warp -> per-lane fallback rounds
+    engine.set_option(1, mode)
     try:
         engine.load_system(sysd)
         engine.calculate()

@@ -6,5 +6,6 @@ bench.py; the Go binding a maintainer would add is shown in INTEGRATION.md.
 There is no CPU fallback: constructing an Engine without the built CUDA library
 or without a GPU raises.
 """
-from . import _abi, synth  # noqa: F401
+from . import _abi, sharding, synth  # noqa: F401
+from . import engine  # noqa: F401
 from .engine import Engine, WvaError, lib_path, load_library  # noqa: F401

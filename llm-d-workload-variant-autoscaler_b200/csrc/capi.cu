@@ -89,7 +89,7 @@ struct wva_ctx {
   // queueing system
   bool loaded = false, calculated = false, solved = false;
   bool force_lane_sizer = false;
-  int lane_sizer_mode = 2;   // 1 flattened, 2 lock-step
+  int lane_sizer_mode = 3;   // 1 flattened, 2 lock-step, 3 lock-step with two chains per lane
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
   int policy = 0;
@@ -274,7 +274,8 @@ template <int THREADS, bool SMEM>
 static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned long long n_pairs, int nmax, float* gtab,
                                 int* ovf_list) {
   // lane_sizer_mode 1 = flattened state machine (sizer_kernel.cuh); otherwise lock-step rounds
-  auto k = (ctx->lane_sizer_mode == 1) ? sizer_kernel<THREADS, SMEM> : sizer_lane_kernel<THREADS, SMEM>;
+  auto k = (ctx->lane_sizer_mode == 1) ? sizer_kernel<THREADS, SMEM>
+           : (ctx->lane_sizer_mode == 2) ? sizer_lane_kernel<THREADS, SMEM, false> : sizer_lane_kernel<THREADS, SMEM, true>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list);
@@ -298,7 +299,7 @@ int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
   if (!ctx) return WVA_ERR_ARG;
   if (option == WVA_OPT_FORCE_LANE_SIZER) {
     ctx->force_lane_sizer = value != 0;
-    if (value == 1 || value == 2) ctx->lane_sizer_mode = value;
+    if (value >= 1 && value <= 3) ctx->lane_sizer_mode = value;
     return WVA_OK;
   }
   return WVA_ERR_ARG;

@@ -1,17 +1,18 @@
-// lockstep_solve.cuh — one MM1ModelStateDependent.Solve per lane
-// (pkg/analyzer/mm1modelstatedependent.go:28-116), all 32 lanes of a warp advancing the
-// state index together: pass 1 (sum of p~) for every lane, then pass 2 (normalise +
-// accumulate).  The loops are unrolled in chunks of 8 states and carry NO per-state
-// control flow:
-//   - the early exit (E4) is decided once per chunk: a lane is `done` when its current
-//     term is below 2^-54 of every accumulator (compared on the high words — conservative)
-//     and the remaining terms are non-increasing; a done lane keeps executing the same
-//     instructions, which by that very criterion are exact no-ops on its accumulators;
-//   - the exponent window (E3) is tracked with one integer min and one max per state and
-//     checked per chunk; a violation (float64 overflow / underflow regime, never seen on
-//     sane inputs) marks the solve `bad` and the pair is redone by the literal slow path;
-//   - the warp leaves a loop when every lane is done.
-// Per state: pass 1 = 5 FP64-pipe ops, pass 2 = 13 FP64-pipe ops.
+// lockstep_solve.cuh — MM1ModelStateDependent.Solve (pkg/analyzer/mm1modelstatedependent.go:28-116)
+// for NC independent arrival rates per lane, all 32 lanes of a warp advancing the state index
+// together: pass 1 (sum of p~) for every lane and chain, then pass 2 (normalise + accumulate).
+// The loops are unrolled in chunks of 8/NC states and carry NO per-state control flow:
+//   - the early exit (E4) is decided once per chunk: a chain is `done` when its current term is
+//     below 2^-54 of every accumulator (compared on the high words — conservative) and the
+//     remaining terms are non-increasing; a done chain keeps executing the same instructions,
+//     which by that very criterion are exact no-ops on its accumulators;
+//   - the exponent window (E3) is tracked with one integer min and one max per state and checked
+//     per chunk; a violation (float64 overflow / underflow regime, never seen on sane inputs)
+//     marks the solve `bad` and the pair is redone by the literal slow path;
+//   - the warp leaves a loop when every chain of every lane is done.
+// With NC = 2 the two chains of a lane share the table load (and, for per-lane float32 tables,
+// the reciprocal refinement) and give the FP64 pipe two independent dependency chains per lane.
+// Per state and chain: pass 1 = 5 FP64-pipe ops, pass 2 = 13 FP64-pipe ops.
 #pragma once
 #include "wva_core.cuh"
 
@@ -38,7 +39,7 @@ struct LaneTable {   // one float32 column per lane ([n][thread], bank = lane); 
 };
 
 struct P1 { double p, sum; int mn, mx; };
-struct P2 { double p, L, sumP, di, pi; int mn, mx; };
+struct P2 { double p, L, sumP, pi; int mn, mx; };
 
 __device__ __forceinline__ void p1_step(P1& s, double lam, double mu, double r) {
   double x = d_mul(s.p, lam);
@@ -47,150 +48,241 @@ __device__ __forceinline__ void p1_step(P1& s, double lam, double mu, double r) 
   s.p = div_f32den(x, mu, r);
   s.sum = d_add(s.sum, s.p);
 }
-__device__ __forceinline__ void p2_step(P2& s, double lam, double mu, double r, double sum, double rsum) {
+__device__ __forceinline__ void p2_step(P2& s, double lam, double mu, double r, double sum, double rsum, double di) {
   double x = d_mul(s.p, lam);
   int h = d_hi(x);
   s.mn = min(s.mn, h); s.mx = max(s.mx, h);
   s.p = div_f32den(x, mu, r);
   s.pi = div_markstein2(s.p, sum, rsum);
-  s.di = d_add(s.di, 1.0);
-  s.L = d_add(s.L, d_mul(s.di, s.pi));
+  s.L = d_add(s.L, d_mul(di, s.pi));
   s.sumP = d_add(s.sumP, s.pi);
 }
 
-// `active` lanes solve at `lambda`; inactive lanes ride along (lambda 0).  On return `bad` is set
-// for a lane whose solve left the exponent window (caller: redo the pair on the slow path).
-// __noinline__: the sizer calls this from four places; one copy keeps the unrolled loops in the I-cache
-template <class Tab>
-__device__ __noinline__ void lockstep_solve(const PairModel& m, const Tab& tab, float lambda, bool active,
-                                               SolveStats& st, int& states, bool& bad) {
+// Chains c with active[c] solve at lambda[c]; the others ride along (lambda 0).  On return `bad`
+// is set for a lane when one of its solves left the exponent window (caller: redo the pair on the
+// slow path).  __noinline__: callers invoke this from several places; one copy keeps the unrolled
+// loops in the instruction cache.
+template <int NC, class Tab>
+__device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab, const float* lambda,
+                                              const bool* active, SolveStats* st, int& states, bool& bad) {
+  constexpr int CH = 8 / NC;                           // states per unrolled chunk
   const unsigned full = 0xffffffffu;
   const int K = m.K, N = m.N, NH = N - 1;
-  const double lam = active ? (double)lambda : 0.0;
-  const double lamg = d_mul((double)lambda, 1.000001);
-  const bool tail_ok = d_bits(lamg) <= d_bits(m.mu_last);
   const double mu_l = m.mu_last, r_l = m.r_last;
+  double lam[NC], lamg[NC];
+  bool tail_ok[NC], done[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    lam[c] = active[c] ? (double)lambda[c] : 0.0;
+    lamg[c] = d_mul((double)lambda[c], 1.000001);
+    tail_ok[c] = d_bits(lamg[c]) <= d_bits(mu_l);
+    done[c] = !active[c];
+  }
   bad = false;
   states = 0;
   // ------------------------------------------------------------------ pass 1
-  P1 a; a.p = 1.0; a.sum = 1.0;
-  bool done = !active;
+  P1 a[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) { a[c].p = 1.0; a[c].sum = 1.0; }
   int n = 0;
   bool all_done = false;
-  while (n < NH && !all_done) {                       // head: table entries n .. n+c-1
-    const int c = min(8, NH - n);
-    const bool eok = (n >= m.mono) && (d_bits(lamg) <= d_bits(tab.mu_at(n)));
-    a.mn = 0x7fffffff; a.mx = 0;
-    if (c == 8) {
+  while (n < NH && !all_done) {                       // head: table entries n .. n+cnt-1
+    const int cnt = min(CH, NH - n);
+    const double mu0 = tab.mu_at(n);
 #pragma unroll
-      for (int j = 0; j < 8; j++) { double mu, r; tab.load(n + j, mu, r); p1_step(a, lam, mu, r); }
+    for (int c = 0; c < NC; c++) { a[c].mn = 0x7fffffff; a[c].mx = 0; }
+    if (cnt == CH) {
+#pragma unroll
+      for (int j = 0; j < CH; j++) {
+        double mu, r; tab.load(n + j, mu, r);
+#pragma unroll
+        for (int c = 0; c < NC; c++) p1_step(a[c], lam[c], mu, r);
+      }
     } else {
-      for (int j = 0; j < c; j++) { double mu, r; tab.load(n + j, mu, r); p1_step(a, lam, mu, r); }
+      for (int j = 0; j < cnt; j++) {
+        double mu, r; tab.load(n + j, mu, r);
+#pragma unroll
+        for (int c = 0; c < NC; c++) p1_step(a[c], lam[c], mu, r);
+      }
     }
-    n += c;
-    if (!done) {
-      states += c;
-      if (a.mn < WVA_HI_LO || a.mx >= WVA_HI_HI) { bad = true; done = true; }
-      else if (eok && d_hi(a.p) < d_hi(d_mul(a.sum, 0x1p-54))) done = true;
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      if (!done[c]) {
+        states += cnt;
+        const bool eok = (n >= m.mono) && (d_bits(lamg[c]) <= d_bits(mu0));
+        if (a[c].mn < WVA_HI_LO || a[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; }
+        else if (eok && d_hi(a[c].p) < d_hi(d_mul(a[c].sum, 0x1p-54))) done[c] = true;
+      }
+      any = any || !done[c];
     }
-    all_done = !__any_sync(full, !done);
+    n += cnt;
+    all_done = !__any_sync(full, any);
   }
   while (n < K && !all_done) {                        // tail: constant service rate
-    const int c = min(8, K - n);
-    a.mn = 0x7fffffff; a.mx = 0;
-    if (c == 8) {
+    const int cnt = min(CH, K - n);
 #pragma unroll
-      for (int j = 0; j < 8; j++) p1_step(a, lam, mu_l, r_l);
+    for (int c = 0; c < NC; c++) { a[c].mn = 0x7fffffff; a[c].mx = 0; }
+    if (cnt == CH) {
+#pragma unroll
+      for (int j = 0; j < CH; j++) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) p1_step(a[c], lam[c], mu_l, r_l);
+      }
     } else {
-      for (int j = 0; j < c; j++) p1_step(a, lam, mu_l, r_l);
+      for (int j = 0; j < cnt; j++) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) p1_step(a[c], lam[c], mu_l, r_l);
+      }
     }
-    n += c;
-    if (!done) {
-      states += c;
-      if (a.mn < WVA_HI_LO || a.mx >= WVA_HI_HI) { bad = true; done = true; }
-      else if (tail_ok && d_hi(a.p) < d_hi(d_mul(a.sum, 0x1p-54))) done = true;
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      if (!done[c]) {
+        states += cnt;
+        if (a[c].mn < WVA_HI_LO || a[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; }
+        else if (tail_ok[c] && d_hi(a[c].p) < d_hi(d_mul(a[c].sum, 0x1p-54))) done[c] = true;
+      }
+      any = any || !done[c];
     }
-    all_done = !__any_sync(full, !done);
+    n += cnt;
+    all_done = !__any_sync(full, any);
   }
   // ------------------------------------------------------------------ pass 2
-  const double sum = a.sum;
-  if (active && !bad && !in_window(sum)) bad = true;
-  const double rsum = d_rcp(sum);
   const double cK = 0x1p-55 / (double)K;              // 2x margin covers the rounding of cK itself
-  P2 b; b.p = 1.0; b.L = 0.0; b.di = 0.0; b.pi = 0.0;
-  b.sumP = d_div(1.0, sum);                           // p[0] = 1/sum
-  done = !active || bad;
-  all_done = !__any_sync(full, !done);
+  double sum[NC], rsum[NC], Lserv[NC];
+  bool reached_K[NC];
+  P2 b[NC];
+  bool any0 = false;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    sum[c] = a[c].sum;
+    if (active[c] && !in_window(sum[c])) bad = true;
+    rsum[c] = d_rcp(sum[c]);
+    b[c].p = 1.0; b[c].L = 0.0; b[c].pi = 0.0;
+    b[c].sumP = d_div(1.0, sum[c]);                   // p[0] = 1/sum
+    reached_K[c] = false;
+    Lserv[c] = 0.0;
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) { done[c] = !active[c] || bad; any0 = any0 || !done[c]; }
+  all_done = !__any_sync(full, any0);
+  double di = 0.0;                                    // float64(i), shared by the chains
   n = 0;
   while (n < NH && !all_done) {                       // head (i = n+1 <= N-1)
-    const int c = min(8, NH - n);
-    const bool eok = (n >= m.mono) && (d_bits(lamg) <= d_bits(tab.mu_at(n)));
-    b.mn = 0x7fffffff; b.mx = 0;
-    if (c == 8) {
+    const int cnt = min(CH, NH - n);
+    const double mu0 = tab.mu_at(n);
 #pragma unroll
-      for (int j = 0; j < 8; j++) { double mu, r; tab.load(n + j, mu, r); p2_step(b, lam, mu, r, sum, rsum); }
+    for (int c = 0; c < NC; c++) { b[c].mn = 0x7fffffff; b[c].mx = 0; }
+    if (cnt == CH) {
+#pragma unroll
+      for (int j = 0; j < CH; j++) {
+        double mu, r; tab.load(n + j, mu, r);
+        di = d_add(di, 1.0);
+#pragma unroll
+        for (int c = 0; c < NC; c++) p2_step(b[c], lam[c], mu, r, sum[c], rsum[c], di);
+      }
     } else {
-      for (int j = 0; j < c; j++) { double mu, r; tab.load(n + j, mu, r); p2_step(b, lam, mu, r, sum, rsum); }
-    }
-    n += c;
-    if (!done) {
-      states += c;
-      if (b.mn < WVA_HI_LO || b.mx >= WVA_HI_HI) { bad = true; done = true; }
-      else if (eok) {
-        int thr = min(d_hi(d_mul(b.L, cK)), d_hi(d_mul(b.sumP, 0x1p-54)));
-        if (d_hi(b.pi) < thr) done = true;
+      for (int j = 0; j < cnt; j++) {
+        double mu, r; tab.load(n + j, mu, r);
+        di = d_add(di, 1.0);
+#pragma unroll
+        for (int c = 0; c < NC; c++) p2_step(b[c], lam[c], mu, r, sum[c], rsum[c], di);
       }
     }
-    all_done = !__any_sync(full, !done);
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      if (!done[c]) {
+        states += cnt;
+        const bool eok = (n >= m.mono) && (d_bits(lamg[c]) <= d_bits(mu0));
+        if (b[c].mn < WVA_HI_LO || b[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; }
+        else if (eok) {
+          int thr = min(d_hi(d_mul(b[c].L, cK)), d_hi(d_mul(b[c].sumP, 0x1p-54)));
+          if (d_hi(b[c].pi) < thr) done[c] = true;
+        }
+      }
+      any = any || !done[c];
+    }
+    n += cnt;
+    all_done = !__any_sync(full, any);
   }
-  double Lserv;
   if (all_done) {
-    // every lane left before state N: the accumulators no longer change, so the value the
+    // every chain left before state N: the accumulators no longer change, so the value the
     // reference computes at i == N (mm1modelstatedependent.go:52-54) is the current one
-    Lserv = d_add(b.L, d_mul(d_sub(1.0, b.sumP), (double)N));
-  } else {
-    // state i == N uses servRate[N-1]
-    b.mn = 0x7fffffff; b.mx = 0;
-    p2_step(b, lam, mu_l, r_l, sum, rsum);
-    n = N;
-    if (!done) { states += 1; if (b.mn < WVA_HI_LO || b.mx >= WVA_HI_HI) { bad = true; done = true; } }
-    Lserv = d_add(b.L, d_mul(d_sub(1.0, b.sumP), (double)N));
-    if (!done && tail_ok) {
-      int thr = min(d_hi(d_mul(b.L, cK)), d_hi(d_mul(b.sumP, 0x1p-54)));
-      if (d_hi(b.pi) < thr) done = true;
-    }
-    all_done = !__any_sync(full, !done);
-  }
-  bool reached_K = false;
-  while (n < K && !all_done) {                        // tail (i = n+1 in N+1 .. K)
-    const int c = min(8, K - n);
-    b.mn = 0x7fffffff; b.mx = 0;
-    if (c == 8) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) p2_step(b, lam, mu_l, r_l, sum, rsum);
-    } else {
-      for (int j = 0; j < c; j++) p2_step(b, lam, mu_l, r_l, sum, rsum);
+    for (int c = 0; c < NC; c++) Lserv[c] = d_add(b[c].L, d_mul(d_sub(1.0, b[c].sumP), (double)N));
+  } else {
+    di = d_add(di, 1.0);                              // state i == N uses servRate[N-1]
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      b[c].mn = 0x7fffffff; b[c].mx = 0;
+      p2_step(b[c], lam[c], mu_l, r_l, sum[c], rsum[c], di);
+      if (!done[c]) { states += 1; if (b[c].mn < WVA_HI_LO || b[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; } }
+      Lserv[c] = d_add(b[c].L, d_mul(d_sub(1.0, b[c].sumP), (double)N));
+      if (!done[c] && tail_ok[c]) {
+        int thr = min(d_hi(d_mul(b[c].L, cK)), d_hi(d_mul(b[c].sumP, 0x1p-54)));
+        if (d_hi(b[c].pi) < thr) done[c] = true;
+      }
+      any = any || !done[c];
     }
-    n += c;
-    if (!done) {
-      states += c;
-      if (b.mn < WVA_HI_LO || b.mx >= WVA_HI_HI) { bad = true; done = true; }
-      else if (n == K) { reached_K = true; done = true; }
-      else if (tail_ok) {
-        int thr = min(d_hi(d_mul(b.L, cK)), d_hi(d_mul(b.sumP, 0x1p-54)));
-        if (d_hi(b.pi) < thr) done = true;
+    n = N;
+    all_done = !__any_sync(full, any);
+  }
+  while (n < K && !all_done) {                        // tail (i = n+1 in N+1 .. K)
+    const int cnt = min(CH, K - n);
+#pragma unroll
+    for (int c = 0; c < NC; c++) { b[c].mn = 0x7fffffff; b[c].mx = 0; }
+    if (cnt == CH) {
+#pragma unroll
+      for (int j = 0; j < CH; j++) {
+        di = d_add(di, 1.0);
+#pragma unroll
+        for (int c = 0; c < NC; c++) p2_step(b[c], lam[c], mu_l, r_l, sum[c], rsum[c], di);
+      }
+    } else {
+      for (int j = 0; j < cnt; j++) {
+        di = d_add(di, 1.0);
+#pragma unroll
+        for (int c = 0; c < NC; c++) p2_step(b[c], lam[c], mu_l, r_l, sum[c], rsum[c], di);
       }
     }
-    all_done = !__any_sync(full, !done);
+    n += cnt;
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      if (!done[c]) {
+        states += cnt;
+        if (b[c].mn < WVA_HI_LO || b[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; }
+        else if (n == K) { reached_K[c] = true; done[c] = true; }
+        else if (tail_ok[c]) {
+          int thr = min(d_hi(d_mul(b[c].L, cK)), d_hi(d_mul(b[c].sumP, 0x1p-54)));
+          if (d_hi(b[c].pi) < thr) done[c] = true;
+        }
+      }
+      any = any || !done[c];
+    }
+    all_done = !__any_sync(full, any);
   }
-  const double pK = reached_K ? b.pi : 0.0;            // (E4): an early exit implies p[K] < 2^-53
-  st.avgNumInServers = (float)Lserv;
-  st.avgNumInSystem = (float)b.L;
-  st.throughput = f_mul(lambda, f_sub(1.0f, (float)pK));
-  st.avgRespTime = f_div(st.avgNumInSystem, st.throughput);
-  st.avgServTime = f_div(st.avgNumInServers, st.throughput);
-  float w = f_sub(st.avgRespTime, st.avgServTime);
-  st.avgWaitTime = (w < 0.0f) ? 0.0f : w;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    const double pK = reached_K[c] ? b[c].pi : 0.0;   // (E4): an early exit implies p[K] < 2^-53
+    SolveStats& s = st[c];
+    s.avgNumInServers = (float)Lserv[c];
+    s.avgNumInSystem = (float)b[c].L;
+    s.throughput = f_mul(lambda[c], f_sub(1.0f, (float)pK));
+    s.avgRespTime = f_div(s.avgNumInSystem, s.throughput);
+    s.avgServTime = f_div(s.avgNumInServers, s.throughput);
+    float w = f_sub(s.avgRespTime, s.avgServTime);
+    s.avgWaitTime = (w < 0.0f) ? 0.0f : w;
+  }
+}
+
+template <class Tab>
+__device__ __forceinline__ void lockstep_solve(const PairModel& m, const Tab& tab, float lambda, bool active,
+                                               SolveStats& st, int& states, bool& bad) {
+  lockstep_solve_n<1, Tab>(m, tab, &lambda, &active, &st, states, bad);
 }
 
 // evaluation values of a finished solve (EvalTTFT / EvalITL, queueanalyzer.go:283-308)

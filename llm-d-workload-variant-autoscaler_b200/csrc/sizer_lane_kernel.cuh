@@ -16,7 +16,7 @@
 
 namespace wva {
 
-template <int THREADS, bool SMEM_TABLE>
+template <int THREADS, bool SMEM_TABLE, bool DUAL>
 __global__ void __launch_bounds__(THREADS)
 sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax, float* gtab,
                   SizerCounters* ctr, int* overflow_list) {
@@ -66,7 +66,7 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
     __syncwarp();
     if (need_table) {
       model_finish(z.m, tab, stride);
-      live = sizer_begin(z, s, out);
+      live = DUAL ? dual_begin(z, s, out) : sizer_begin(z, s, out);
       if (!live) my_solves += z.solves;
     }
     const unsigned live_mask = __ballot_sync(full, live);
@@ -79,26 +79,57 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
     const bool uniform = __all_sync(full, !live || z.m.N == nref);
     bool bad = false;
     int sv = 0;
-    if (uniform) {
-      if (!live) { z.m.N = nref; z.m.K = nref + nref * WVA_QUEUE_TO_BATCH; }   // idle lanes only keep the loops uniform
-      LaneTable lt; lt.t = tab; lt.stride = stride;
-      lockstep_solve(z.m, lt, z.cur_x, live, st, sv, bad);
-      z.c.states = sv;
-    } else if (live) {
-      while (!chain_step(z.c, z.m, st)) {}
-      bad = z.c.phase == CH_OVERFLOW;
-    }
-    if (live) {
-      if (bad) {
-        unsigned long long k = atomicAdd(&ctr->overflow_pairs, 1ull);
-        if (overflow_list) overflow_list[k] = z.srv * s.n_acc + z.acc;
-        z.states += z.c.states;
-        lane_fail(z, s, out);
-        live = false;
-      } else {
-        live = sizer_on_solve(z, s, out, st);
+    if (uniform && !live) { z.m.N = nref; z.m.K = nref + nref * WVA_QUEUE_TO_BATCH; }   // idle lanes only keep the loops uniform
+    LaneTable lt; lt.t = tab; lt.stride = stride;
+    if (DUAL) {
+      // TTFT and ITL searches advance together: two chains per lane share every table load
+      SolveStats st2[2];
+      float xs[2] = {z.x2[0], z.x2[1]};
+      bool act[2] = {live && z.act2[0], live && z.act2[1]};
+      if (uniform) {
+        lockstep_solve_n<2, LaneTable>(z.m, lt, xs, act, st2, sv, bad);
+      } else if (live) {
+        for (int c = 0; c < 2; c++) {
+          if (!act[c]) continue;
+          chain_start(z.c, xs[c]);
+          z.c.tail_ok = d_bits(z.c.lamg) <= d_bits(z.m.mu_last);
+          while (!chain_step(z.c, z.m, st2[c])) {}
+          bad = bad || z.c.phase == CH_OVERFLOW;
+          sv += z.c.states;
+        }
       }
-      if (!live) { my_solves += z.solves; my_states += z.states; }
+      if (live) {
+        if (bad) {
+          unsigned long long k = atomicAdd(&ctr->overflow_pairs, 1ull);
+          if (overflow_list) overflow_list[k] = z.srv * s.n_acc + z.acc;
+          z.states += sv;
+          lane_fail(z, s, out);
+          live = false;
+        } else {
+          live = dual_on_solve(z, s, out, st2, sv);
+        }
+        if (!live) { my_solves += z.solves; my_states += z.states; }
+      }
+    } else {
+      if (uniform) {
+        lockstep_solve(z.m, lt, z.cur_x, live, st, sv, bad);
+        z.c.states = sv;
+      } else if (live) {
+        while (!chain_step(z.c, z.m, st)) {}
+        bad = z.c.phase == CH_OVERFLOW;
+      }
+      if (live) {
+        if (bad) {
+          unsigned long long k = atomicAdd(&ctr->overflow_pairs, 1ull);
+          if (overflow_list) overflow_list[k] = z.srv * s.n_acc + z.acc;
+          z.states += z.c.states;
+          lane_fail(z, s, out);
+          live = false;
+        } else {
+          live = sizer_on_solve(z, s, out, st);
+        }
+        if (!live) { my_solves += z.solves; my_states += z.states; }
+      }
     }
   }
   for (int o = 16; o; o >>= 1) {

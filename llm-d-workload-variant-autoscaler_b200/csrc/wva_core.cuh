@@ -446,6 +446,9 @@ struct SizerLane {
   Search sT, sI;          // TTFT and ITL searches
   float slo_tps, total_rate, rate_star, acc_cost;
   float cur_x;
+  float x2[2];           // dual driver: the (up to) two arrival rates of the coming round
+  bool act2[2];
+  int i_chain;           // dual driver: chain that carries the ITL search's point
   int stage;
   int srv, acc, model;
   int min_replicas, n_inst;
@@ -588,6 +591,115 @@ WVA_HD void search_consume(Search& q, float x, float y) {
   // iteration up to maxIterations repeats this one and BinarySearch returns x.  (The 1e-6
   // relative tolerance sits at float32 resolution, so ~1 in 5 searches ends this way.)
   if (q.x == x) { q.result = x; q.active = false; }
+}
+
+// ---- dual-chain driver: TTFT and ITL searches advance in the SAME round (two chains per lane) -----
+// Used by the lock-step lane sizer.  Same decisions as sizer_on_solve (which runs the two searches one
+// after the other): both end points in round 0, then one bisection step of each search per round,
+// then the two Analyze solves.  ~30 rounds per pair instead of ~58 solves in sequence.
+enum { D2_ENDS = 0, D2_SEARCH = 1, D2_FINAL1 = 2, D2_FINAL2 = 3 };
+
+WVA_HD bool dual_after_search(SizerLane& z, const SysView& s, const CandView& out) {
+  float l_tps = z.m.lambda_max;
+  if (z.slo_tps > 0.0f) l_tps = f_mul(z.m.lambda_max, f_sub(1.0f, WVA_STABILITY_SAFETY));   // queueanalyzer.go:232-235
+  float lambda = fminf(fminf(z.sT.result, z.sI.result), l_tps);                              // :238
+  float request_rate = f_mul(lambda, 1000.0f);                                                // :239
+  if (!analyze_admits(z.m, request_rate)) { lane_fail(z, s, out); return false; }
+  z.stage = D2_FINAL1;
+  z.x2[0] = f_div(request_rate, 1000.0f); z.act2[0] = true; z.act2[1] = false;
+  z.solves++;
+  return true;
+}
+
+WVA_HD bool dual_schedule(SizerLane& z, const SysView& s, const CandView& out) {
+  if (!z.sT.active && !z.sI.active) return dual_after_search(z, s, out);
+  z.stage = D2_SEARCH;
+  z.act2[0] = true; z.act2[1] = false; z.i_chain = 0;
+  if (z.sT.active) {
+    z.x2[0] = z.sT.x;
+    if (z.sI.active && z.sI.x != z.sT.x) { z.x2[1] = z.sI.x; z.act2[1] = true; z.i_chain = 1; }
+  } else {
+    z.x2[0] = z.sI.x;
+  }
+  z.solves += z.act2[1] ? 2 : 1;
+  return true;
+}
+
+WVA_HD bool dual_begin(SizerLane& z, const SysView& s, const CandView& out) {
+  z.sT.enabled = z.sT.target > 0.0f; z.sI.enabled = z.sI.target > 0.0f;
+  z.sT.active = z.sT.enabled; z.sI.active = z.sI.enabled;
+  z.sT.result = z.m.lambda_max; z.sI.result = z.m.lambda_max;
+  z.sT.iter = z.sI.iter = 0;
+  if (z.sT.enabled || z.sI.enabled) {
+    if (z.m.lambda_min > z.m.lambda_max) { lane_fail(z, s, out); return false; }   // utils.go:29-31
+    z.stage = D2_ENDS;
+    z.x2[0] = z.m.lambda_min; z.x2[1] = z.m.lambda_max; z.act2[0] = z.act2[1] = true;
+    z.solves += 2;
+    return true;
+  }
+  return dual_after_search(z, s, out);
+}
+
+// st[c] = statistics of the solve at z.x2[c] (valid where z.act2[c]); n_states = states visited by the round
+WVA_HD bool dual_on_solve(SizerLane& z, const SysView& s, const CandView& out, const SolveStats* st, int n_states) {
+  z.states += n_states;
+  const PairModel& m = z.m;
+  float pf[2], dec[2], ttft[2];
+  for (int c = 0; c < 2; c++) {
+    pf[c] = prefill_time(m, st[c].avgNumInServers);
+    dec[c] = f_div(f_sub(st[c].avgServTime, pf[c]), m.out_tok);
+    ttft[c] = f_add(f_add(st[c].avgWaitTime, pf[c]), dec[c]);
+  }
+  if (z.stage == D2_ENDS) {
+    bool infeasible = false;
+    for (int k = 0; k < 2; k++) {
+      Search& q = k ? z.sI : z.sT;
+      if (!q.active) continue;
+      const float y_lo = k ? dec[0] : ttft[0], y_hi = k ? dec[1] : ttft[1];
+      if (within_tolerance(y_lo, q.target, WVA_BS_EPSILON)) { q.result = m.lambda_min; q.active = false; continue; }
+      if (within_tolerance(y_hi, q.target, WVA_BS_EPSILON)) { q.result = m.lambda_max; q.active = false; continue; }
+      q.increasing = y_lo < y_hi;
+      if ((q.increasing && q.target < y_lo) || (!q.increasing && q.target > y_lo)) { infeasible = true; q.active = false; continue; }
+      if ((q.increasing && q.target > y_hi) || (!q.increasing && q.target < y_hi)) { q.result = m.lambda_max; q.active = false; continue; }
+      q.lo = m.lambda_min; q.hi = m.lambda_max; q.iter = 0;
+      q.x = f_mul(0.5f, f_add(q.lo, q.hi));
+    }
+    if (infeasible) { lane_fail(z, s, out); return false; }
+    return dual_schedule(z, s, out);
+  }
+  if (z.stage == D2_SEARCH) {
+    const bool t_was = z.sT.active, i_was = z.sI.active;
+    if (t_was) search_consume(z.sT, z.x2[0], ttft[0]);
+    if (i_was) search_consume(z.sI, z.x2[z.i_chain], dec[z.i_chain]);
+    return dual_schedule(z, s, out);
+  }
+  if (z.stage == D2_FINAL1) {
+    z.rate_star = f_mul(st[0].throughput, 1000.0f);                                     // allocation.go:124
+    long long nr = go_int_ceil(d_div((double)z.total_rate, (double)z.rate_star));       // :133
+    if (nr < (long long)z.min_replicas) nr = z.min_replicas;
+    z.num_replicas = nr;
+    long long tot = (long long)((unsigned long long)z.n_inst * (unsigned long long)nr);
+    z.cost = f_mul(z.acc_cost, (float)tot);
+    float rate = f_div(z.total_rate, (float)nr);
+    if (!analyze_admits(m, rate)) { lane_fail(z, s, out); return false; }
+    z.stage = D2_FINAL2;
+    z.x2[0] = f_div(rate, 1000.0f); z.act2[0] = true; z.act2[1] = false;
+    z.solves++;
+    return true;
+  }
+  Alloc a;                                                                              // allocation.go:147-154
+  a.state = ALLOC_ACC;
+  a.num_replicas = z.num_replicas;
+  a.batch_size = m.N;
+  a.cost = z.cost;
+  a.itl = dec[0];
+  a.ttft = f_add(st[0].avgWaitTime, pf[0]);
+  float rho = f_div(st[0].avgNumInServers, (float)m.N);
+  a.rho = fminf(fmaxf(rho, 0.0f), 1.0f);
+  a.max_arrv = f_div(z.rate_star, 1000.0f);
+  a.value = transition_penalty(s.srv_cur_acc[z.srv], s.srv_cur_replicas[z.srv], s.srv_cur_cost[z.srv], a, z.acc);
+  store_candidate(out, (size_t)z.srv * s.n_acc + z.acc, a, z.solves);
+  return false;
 }
 
 // ---- speculative bisection (used by the warp-per-pair sizer; see sizer_warp_kernel.cuh) ----

@@ -139,6 +139,33 @@ extern "C" int emul_calculate_spec(const wva_system* sys, wva_candidates* out) {
   return 0;
 }
 
+// System.Calculate through the DUAL-chain driver (dual_begin / dual_on_solve) of the lock-step lane sizer.
+extern "C" int emul_calculate_dual(const wva_system* sys, wva_candidates* out) {
+  SysView s = make_view(sys);
+  CandView o;
+  o.state = out->state; o.num_replicas = out->num_replicas; o.batch_size = out->batch_size; o.cost = out->cost;
+  o.value = out->value; o.itl = out->itl; o.ttft = out->ttft; o.rho = out->rho; o.max_arrv_rate = out->max_arrv_rate;
+  o.n_solves = out->n_solves;
+  std::vector<float> tab;
+  for (int srv = 0; srv < s.n_servers; srv++)
+    for (int acc = 0; acc < s.n_acc; acc++) {
+      SizerLane z; int lim = 0;
+      if (sizer_setup(z, s, o, srv, acc, 1 << 20, &lim) == SETUP_DONE) continue;
+      tab.assign((size_t)z.m.N, 0.0f);
+      model_fill_table(z.m, tab.data(), 1, 0, 1);
+      model_finish(z.m, tab.data(), 1);
+      bool live = dual_begin(z, s, o);
+      while (live) {
+        SolveStats st2[2] = {};
+        bool ovf = false;
+        for (int c = 0; c < 2; c++)
+          if (z.act2[c]) st2[c] = host_solve(z.m, z.x2[c], &ovf);
+        live = dual_on_solve(z, s, o, st2, 0);
+      }
+    }
+  return 0;
+}
+
 extern "C" {
 
 // System.Calculate through the lane state machine, one lane at a time.

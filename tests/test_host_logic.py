@@ -41,7 +41,16 @@ def emul(pkg):
         lib.emul_calculate_spec(C.byref(st), C.byref(cst))
         return cand
 
+    lib.emul_calculate_dual.argtypes = [C.POINTER(abi.System), C.POINTER(abi.Candidates)]
+
+    def calculate_dual(sysd):
+        st, keep = abi.make_system(sysd)
+        cst, cand = abi.alloc_candidates(st.n_servers, st.n_acc)
+        lib.emul_calculate_dual(C.byref(st), C.byref(cst))
+        return cand
+
     lib.calculate = calculate
+    lib.calculate_dual = calculate_dual
     lib.calculate_spec = calculate_spec
     return lib
 
@@ -76,6 +85,20 @@ def test_speculative_bisection_matches_oracle(pkg, oracle, emul, S, A, N, stream
     """The tree-speculative search of the warp-per-pair sizer takes exactly BinarySearch's branches."""
     sysd = pkg.synth.queue_system(S, A, N, stream=stream)
     e = emul.calculate_spec(sysd)
+    o = oracle.calculate(sysd)
+    for k in ("state", "num_replicas", "batch_size"):
+        assert np.array_equal(e[k], o[k]), k
+    for k in F32_FIELDS:
+        assert _bit_equal(e[k], o[k]), k
+
+
+@pytest.mark.parametrize("S,A,N,stream", [(10, 4, 32, 1), (40, 8, 16, 7), (10, 6, 128, 2), (20, 3, 1, 11)])
+def test_dual_chain_driver_matches_oracle(pkg, oracle, emul, S, A, N, stream):
+    """TTFT and ITL searches advanced in the same round (lock-step lane sizer) = the sequential searches."""
+    sysd = pkg.synth.queue_system(S, A, N, stream=stream)
+    sysd["srv_slo_itl"][::5] = 0.0       # TTFT-only servers
+    sysd["srv_slo_ttft"][1::5] = 0.0     # ITL-only servers
+    e = emul.calculate_dual(sysd)
     o = oracle.calculate(sysd)
     for k in ("state", "num_replicas", "batch_size"):
         assert np.array_equal(e[k], o[k]), k

@@ -5,8 +5,10 @@ Metric (BASELINE.json): (model,variant,replica) evals/sec + solver wall-ms, next
 algorithm on the box's host cores.  One "step" = one pass of the hot path over one batch of synthetic
 input: System.Calculate (sizing of every (server, accelerator) candidate) -> Manager.Optimize
 (per-server cheapest feasible candidate + by-type totals) -> the (server, accelerator, replica) grid
-of QueueAnalyzer.Analyze evaluations.  An "evaluation" = one chain solve; a step's
-evaluations = S*A*R grid evaluations + the sizing solves counted on the device.
+of QueueAnalyzer.Analyze evaluations.  An "evaluation" = one (model, variant, replica) grid point = one
+QueueAnalyzer.Analyze chain solve.  `value` counts ONLY the S*A*R grid evaluations of a step
+and divides by the time of the WHOLE step (sizing + allocator + grid), so the bisection solves of the sizer
+(reported separately, `evals_per_step.sizing_solves`) make the number smaller, never larger.
 
 Workload at 1 GPU = BASELINE.json configs[1]: 1k models x 16 variants x 128 replica levels, N = 128
 (K = 1408 states), 3 service classes, unlimited.  With --gpus N the model set is sharded (weak scaling:
@@ -52,7 +54,8 @@ def config_dict(world):
             "models_per_gpu": S_PER_GPU, "variants": A, "replica_levels": R, "max_batch": NB,
             "chain_states": 11 * NB + 1, "parallelism": f"model-sharded x{world}",
             "l2": "flushed between steps (256 MiB write inside the timed region)",
-            "evaluation": "one chain solve: S*A*R grid Analyze calls + sizing solves counted on device"}
+            "evaluation": "value = S*A*R grid Analyze evaluations / time of the whole step (sizing + allocator + grid); "
+                          "the sizer's own chain solves are not counted"}
 
 
 class ClockSampler(threading.Thread):
@@ -107,7 +110,7 @@ def cpu_reference_leg(sample_servers: int):
     t2 = time.perf_counter()
     orc.analyze_grid(d, R, nthreads=cores, full=True)
     t3 = time.perf_counter()
-    evals = sample_servers * A * R + cand["_solves"]
+    evals = sample_servers * A * R          # same definition as the GPU arm: grid evaluations / whole-step time
     return {"value": evals / (t3 - t0), "unit": "evals/s", "cores": cores, "kind": "port",
             "sample": f"{sample_servers} of {S_PER_GPU} models x {A} variants x {R} levels (N={NB}), "
                       f"oracle C++ restatement of the reference, OpenMP over servers, every bisection step",
@@ -140,7 +143,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-sample", type=int, default=100, help="servers per step in the bounded CPU sample")
+    ap.add_argument("--ref-sample", type=int, default=400, help="servers per step in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -217,7 +220,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
 
-    evals_local = sum(S * A * R + i["size_solves"] for i in infos)
+    evals_local = S * A * R * len(infos)
     ev = torch.tensor([float(evals_local)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ev)
@@ -253,7 +256,7 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        sizer_name = "sizer_warp_kernel" if S * A <= 148 * 512 else "sizer_lane_kernel"
+        sizer_name = "sizer_warp_kernel" if S * A <= 148 * 80 else "sizer_lane_kernel"
         if grid_ms >= calc_ms:
             dominant, dom_ms, alg_bytes, dom_states = "grid_kernel", grid_ms, S * A * R * ALG_BYTES_PER_EVAL, last["grid_states"]
         else:

@@ -89,7 +89,7 @@ struct wva_ctx {
   // queueing system
   bool loaded = false, calculated = false, solved = false;
   bool force_lane_sizer = false;
-  int lane_sizer_mode = 3;   // 1 flattened, 2 lock-step, 3 lock-step with two chains per lane
+  int lane_sizer_mode = 2;   // 1 flattened, 2 lock-step (default), 3 lock-step with two chains per lane (slower: measured)
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
   int policy = 0;
@@ -353,10 +353,11 @@ int32_t wva_calculate(wva_ctx* ctx) {
     }
     cudaError_t e;
     // Small / medium systems are bound by the critical path of their slowest pair: use the
-    // warp-per-pair sizer (speculative bisection, sizer_warp_kernel.cuh) while the whole system
-    // fits in a few waves of warps and its per-warp tables (20 B x nmax) fit in shared memory.
+    // warp-per-pair sizer (speculative bisection, sizer_warp_kernel.cuh) while the system is small
+    // (measured crossover against the lock-step lane sizer: ~80 pairs per SM) and its per-warp
+    // tables (20 B x nmax) fit in shared memory.
     const size_t warp_tab = (size_t)nmax * 20;
-    if (n_pairs <= (unsigned long long)ctx->sm_count * 512 && warp_tab * 4 + 1024 <= SMEM_PER_SM && !ctx->force_lane_sizer) {
+    if (n_pairs <= (unsigned long long)ctx->sm_count * 80 && warp_tab * 4 + 1024 <= SMEM_PER_SM && !ctx->force_lane_sizer) {
       if (warp_tab * 8 <= 48 * 1024) {
         int per_sm = (int)(SMEM_PER_SM / (warp_tab * 8 + 1024)); if (per_sm > 6) per_sm = 6; if (per_sm < 1) per_sm = 1;
         e = launch_sizer_warp<8>(ctx, ctx->sm_count * per_sm, warp_tab * 8, n_pairs, nmax, d_ovf);

@@ -1,0 +1,128 @@
+"""Measure the BASELINE.json configs on one GPU (fills BASELINE.md §4).  Usage: run_configs.py [cfgs] [scale3] [scale4]
+
+Every queueing config is checked against the oracle on a small seeded subsample (full-size oracle runs take minutes to
+hours on the host); the full-size runs are checked through size-independent properties (capacity never exceeded, greedy
+with ample capacity == unlimited, targets differ from the metric count by at most one replica per model, ...).
+"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("llm-d-workload-variant-autoscaler_b200")
+from tests import oracle_lib  # noqa: E402  (checker only)
+
+cfgs = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1,2,3,4,5").split(",")]
+scale3 = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+scale4 = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+orc = oracle_lib.load()
+out = {}
+
+
+def best(f, n=5):
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter(); f(); ts.append((time.perf_counter() - t0) * 1e3)
+    return min(ts), float(np.median(ts))
+
+
+with pkg.Engine(0) as e:
+    dfma, ddiv = e.microbench_fp64()
+    out["fp64_peaks"] = {"dfma_per_s": dfma, "ddiv_per_s": ddiv}
+    for cfg in cfgs:
+        if cfg in (1, 2, 3):
+            d = pkg.synth.baseline_config(cfg, scale=scale3 if cfg == 3 else 1.0)
+            S, A = d["n_servers"], d["n_acc"]
+            N = int(d["perf_max_batch"].flat[0]); R = N
+            unl = dict(d); unl["unlimited"] = True
+            e.load_system(unl)
+            e.calculate(); e.calculate()
+            tc = e.timing()
+            e.solve(); ts = e.timing()
+            sol_un = e.solution()
+            e.grid_run(R, full=(cfg != 3)); e.grid_run(R, full=(cfg != 3))
+            tg = e.timing()
+            wall_min, wall_med = best(lambda: e.optimize(unl), 3)
+            row = {"S": S, "A": A, "N": N, "K": 11 * N, "R": R, "pairs": S * A,
+                   "calculate_ms": tc["calculate_ms"], "solve_unlimited_ms": ts["solve_ms"], "grid_ms": tg["grid_ms"],
+                   "sizing_solves": tc["chain_solves"], "sizing_states": tc["chain_states"],
+                   "grid_evals": S * A * R, "grid_states": tg["chain_states"],
+                   "grid_evals_per_s": S * A * R / (tg["grid_ms"] * 1e-3),
+                   "pairs_per_s": S * A / (tc["calculate_ms"] * 1e-3),
+                   "optimize_wall_ms_min": wall_min, "optimize_wall_ms_median": wall_med,
+                   "fp64_frac_sizer": 9.0 * tc["chain_states"] / (tc["calculate_ms"] * 1e-3) / dfma,
+                   "fp64_frac_grid": 9.0 * tg["chain_states"] / (tg["grid_ms"] * 1e-3) / dfma,
+                   "alg_gbs_grid": S * A * R * 17.9 / (tg["grid_ms"] * 1e-3) / 1e9,
+                   "alg_gbs_sizer": S * A * (24 + 36.0 / A + 37) / (tc["calculate_ms"] * 1e-3) / 1e9}
+            if cfg == 3:   # limited capacity: greedy at 60 % of the unconstrained demand
+                for pol in ("None", "PriorityRoundRobin"):
+                    lim = pkg.synth.limit_capacity(d, sol_un["type_count"], 0.6)
+                    lim["saturation_policy"] = pol
+                    e.load_system(lim); e.calculate(); e.solve()
+                    row[f"solve_greedy_ms_{pol}"] = e.timing()["solve_ms"]
+                    g = e.solution()
+                    assert (g["type_count"] <= lim["type_count"]).all()
+                    row[f"greedy_allocated_{pol}"] = int((g["state"] == 1).sum())
+                ample = pkg.synth.limit_capacity(d, sol_un["type_count"] * 4, 1.0)
+                e.load_system(ample); e.calculate(); e.solve()
+                g = e.solution()
+                row["greedy_ample_equals_unlimited"] = bool(np.array_equal(g["acc"], sol_un["acc"]) and
+                                                            np.array_equal(g["num_replicas"], sol_un["num_replicas"]))
+            # parity on a seeded subsample of the same generator
+            sub = pkg.synth.baseline_config(cfg, scale=min(1.0, 24.0 / max(S, 1)))
+            sub["unlimited"] = True
+            e.load_system(sub); e.calculate()
+            gc = e.candidates(); oc = orc.calculate(sub)
+            row["parity_subsample_pairs"] = int(sub["n_servers"] * A)
+            row["parity_ints_exact"] = bool(all(np.array_equal(gc[k], oc[k]) for k in ("state", "num_replicas", "batch_size")))
+            row["parity_floats_bit_equal"] = bool(all(np.array_equal(gc[k].view(np.uint32), oc[k].view(np.uint32))
+                                                      for k in ("cost", "value", "itl", "ttft", "rho", "max_arrv_rate")))
+            out[f"cfg{cfg}"] = row
+        if cfg == 4:
+            M = max(1, int(1_000_000 * scale4))
+            t0 = time.perf_counter()
+            d = pkg.synth.saturation_batch(M, 32, stream=4)
+            gen_s = time.perf_counter() - t0
+            t0 = time.perf_counter(); e.saturation_upload(d); up_ms = (time.perf_counter() - t0) * 1e3
+            ks = []
+            for _ in range(5):
+                e.saturation_run(False); ks.append(e.timing()["saturation_ms"])
+            res = e.saturation_fetch(False)
+            P, V = d["n_replicas"], d["n_variants"]
+            alg = P * 16 + V * 32 + M * 40
+            cnt = np.diff(d["variant_replica_off"].astype(np.int64))
+            ok = np.abs(res["var_target"].astype(np.int64) - cnt).max() <= max(1, int(np.abs(d["var_desired"] - d["var_current"]).max()))
+            sub = pkg.synth.saturation_batch(2000, 32, stream=4)
+            gs = e.saturation_v1(sub); os_ = orc.saturation_v1(sub)
+            out["cfg4"] = {"models": M, "variants": V, "replicas": P, "gen_s": gen_s, "upload_ms": up_ms,
+                           "kernel_ms_min": min(ks), "kernel_ms_median": float(np.median(ks)), "alg_bytes": alg,
+                           "alg_gbs": alg / (min(ks) * 1e-3) / 1e9, "replicas_per_s": P / (min(ks) * 1e-3),
+                           "partials": res["partials"].tolist(), "targets_within_one": bool(ok),
+                           "parity_subsample_exact": bool(np.array_equal(gs["var_target"], os_["var_target"]) and
+                                                          np.array_equal(gs["mod_flags"], os_["mod_flags"]))}
+        if cfg == 5:
+            lat = []
+            for b in range(60):
+                d = pkg.synth.saturation_batch(10_000, 32, stream=500 + b)
+                t0 = time.perf_counter()
+                r = e.saturation_v1(d)                       # upload + analysis + targets + fetch of everything
+                lim_in = {"n_types": 8, "acc_type": (np.arange(d["n_variants"]) % 8).astype(np.int32),
+                          "current": d["var_current"], "target": np.maximum(r["var_target"], 0).astype(np.int32),
+                          "gpus_per_replica": np.ones(d["n_variants"], np.int32),
+                          "spare": np.repeat(r["mod_avg_spare_kv"], 32), "cost": d["var_cost"],
+                          "type_limit": np.full(8, int(d["var_current"].sum() // 8 + 500), np.int32)}
+                e.limit(lim_in)
+                lat.append((time.perf_counter() - t0) * 1e3)
+            lat = np.array(lat[5:])
+            out["cfg5"] = {"models_per_batch": 10_000, "variants": 320_000, "replicas": int(d["n_replicas"]),
+                           "decision_latency_ms_p50": float(np.percentile(lat, 50)),
+                           "decision_latency_ms_p99": float(np.percentile(lat, 99)),
+                           "note": "host SoA batch -> upload -> saturation analysis + targets -> limiter -> host decisions"}
+print(json.dumps(out, indent=1))
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_r1.json"), "w"), indent=1)

@@ -11,13 +11,13 @@
 //                              (slices.BinarySearchFunc + slices.Insert, greedy.go:161-162).  That is
 //                              the order (key asc; among equal keys re-inserted entries first, latest
 //                              first; then the untouched entries in their sorted order), realised
-//                              here as: the sorted array consumed from its head + a binary heap of
+//                              here as: the sorted array consumed from its head + a 32-ary heap of
 //                              re-inserted entries keyed (key, insertion stamp desc); the next entry
 //                              is the heap top when top <= head, else the head.
 //
-// K2 is inherently sequential (every fit test depends on all earlier takes of the type) and runs on
-// ONE thread in this round — exact, on device, O((S + bumps) log S).  Widening it (warp-cooperative
-// 32-ary heap, chunked fast-forward over runs of fitting entries) is next-round work.
+// K2 is inherently sequential (every fit test depends on all earlier takes of the type): one warp runs
+// the sweep, the heap is 32-ary and its pops are warp-cooperative.  Chunked fast-forward over runs of
+// fitting entries is next-round work.
 #pragma once
 #include "wva_core.cuh"
 #include "solve_kernels.cuh"
@@ -111,36 +111,59 @@ __device__ __forceinline__ bool g_before(const GEntry& a, const GEntry& b) {
   return o < 0 || (o == 0 && a.tau > b.tau);
 }
 
+// 32-ary min-heap of re-inserted entries, operated by the whole warp: every lane runs the same control
+// flow on the same values (the sweep itself is sequential), and a pop inspects the 32 children of a node
+// with one coalesced load per field + a shuffle arg-min, so a heap of S entries is ~log32(S) <= 4 levels
+// deep instead of the 17 dependent levels of a binary heap.
 struct GHeap {
   GreedyWs w; int n;
   __device__ GEntry get(int i) const { GEntry e; e.prio = w.h_prio[i]; e.delta = w.h_delta[i]; e.value = w.h_value[i]; e.tau = w.h_tau[i]; e.srv = w.h_srv[i]; return e; }
-  __device__ void put(int i, const GEntry& e) { w.h_prio[i] = e.prio; w.h_delta[i] = e.delta; w.h_value[i] = e.value; w.h_tau[i] = e.tau; w.h_srv[i] = e.srv; }
+  __device__ void put(int i, const GEntry& e) {
+    if ((threadIdx.x & 31) == 0) { w.h_prio[i] = e.prio; w.h_delta[i] = e.delta; w.h_value[i] = e.value; w.h_tau[i] = e.tau; w.h_srv[i] = e.srv; }
+  }
   __device__ void push(const GEntry& e) {
     int i = n++;
     while (i > 0) {
-      int p = (i - 1) >> 1;
+      int p = (i - 1) >> 5;
       GEntry pe = get(p);
       if (!g_before(e, pe)) break;
       put(i, pe);
       i = p;
     }
     put(i, e);
+    __syncwarp();
   }
   __device__ GEntry pop() {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     GEntry top = get(0);
     GEntry last = get(--n);
     int i = 0;
     while (true) {
-      int l = 2 * i + 1, r = l + 1;
-      if (l >= n) break;
-      GEntry le = get(l);
-      int m = l; GEntry me = le;
-      if (r < n) { GEntry re = get(r); if (g_before(re, le)) { m = r; me = re; } }
-      if (!g_before(me, last)) break;
+      const int c0 = 32 * i + 1;
+      if (c0 >= n) break;
+      const int ci = c0 + lane;
+      const bool have = ci < n;
+      GEntry me;
+      if (have) me = get(ci);
+      else { me.prio = 0x7fffffff; me.delta = 0.0f; me.value = 0.0f; me.tau = 0; me.srv = -1; }
+      int who = lane;
+      for (int o = 16; o; o >>= 1) {
+        GEntry ot;
+        ot.prio = __shfl_xor_sync(full, me.prio, o); ot.delta = __shfl_xor_sync(full, me.delta, o);
+        ot.value = __shfl_xor_sync(full, me.value, o); ot.tau = __shfl_xor_sync(full, me.tau, o);
+        ot.srv = __shfl_xor_sync(full, me.srv, o);
+        const int ow = __shfl_xor_sync(full, who, o);
+        // total order for the butterfly: heap order, then the lower lane (equal entries cannot occur: tau is unique)
+        const bool take = (ot.srv >= 0) && (me.srv < 0 || g_before(ot, me) || (!g_before(me, ot) && ow < who));
+        if (take) { me = ot; who = ow; }
+      }
+      if (me.srv < 0 || !g_before(me, last)) break;
       put(i, me);
-      i = m;
+      i = c0 + who;
     }
     if (n > 0) put(i, last);
+    __syncwarp();
     return top;
   }
 };
@@ -247,10 +270,12 @@ __device__ void g_best_effort(const SysView& s, const CandView& c, const SolView
 
 __global__ void greedy_allocate_kernel(SysView s, CandView c, SolView o, GreedyWs w, const int* e_srv, int delayed,
                                        int policy) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0) return;   // one warp; every lane executes the sweep redundantly, the heap uses all 32
+  const bool writer = (threadIdx.x & 31) == 0;
   const int A = s.n_acc;
   const int n0 = *w.n_entries;
-  for (int t = 0; t < s.n_types; t++) w.avail[t] = s.type_count[t];   // greedy.go:38-39
+  if (writer) for (int t = 0; t < s.n_types; t++) w.avail[t] = s.type_count[t];   // greedy.go:38-39
+  __syncwarp();
   GHeap heap; heap.w = w; heap.n = 0;
   unsigned tau = 0;
   int head = 0, n_un = 0, group_un0 = 0;
@@ -262,7 +287,8 @@ __global__ void greedy_allocate_kernel(SysView s, CandView c, SolView o, GreedyW
     bool head_ok = head < n0 && (delayed || s.srv_priority[e_srv[head]] == group_prio);
     if (!head_ok && heap.n == 0) {
       if (!delayed) {
-        g_best_effort(s, c, o, w, w.unalloc + group_un0, n_un - group_un0, policy);
+        if (writer) g_best_effort(s, c, o, w, w.unalloc + group_un0, n_un - group_un0, policy);   // sequential: lane 0
+        __syncwarp();
         group_un0 = n_un;
         if (head < n0) { group_prio = s.srv_priority[e_srv[head]]; continue; }
       }
@@ -292,21 +318,22 @@ __global__ void greedy_allocate_kernel(SysView s, CandView c, SolView o, GreedyW
     int t = s.acc_type[acc];
     long long count = (long long)c.num_replicas[i] * g_upr(s, srv, acc);
     if (w.avail[t] >= count) {                                         // greedy.go:143-145
-      w.avail[t] -= count;
-      g_commit(s, c, o, srv, acc, c.num_replicas[i], c.cost[i], c.value[i]);
+      if (writer) { w.avail[t] -= count; g_commit(s, c, o, srv, acc, c.num_replicas[i], c.cost[i], c.value[i]); }
+      __syncwarp();
     } else {
       ci++;
-      w.cur_idx[srv] = ci;
+      if (writer) w.cur_idx[srv] = ci;
+      __syncwarp();
       const int n = w.ncand[srv];
       if (ci + 1 < n) e.delta = f_sub(c.value[(size_t)srv * A + ord[ci + 1]], c.value[(size_t)srv * A + ord[ci]]);
-      else if (ci == n) { w.unalloc[n_un++] = srv; continue; }
+      else if (ci == n) { if (writer) w.unalloc[n_un] = srv; n_un++; __syncwarp(); continue; }
       else e.delta = FLT_MAX;
       e.value = c.value[(size_t)srv * A + ord[ci]];
       e.tau = ++tau;
       heap.push(e);
     }
   }
-  if (delayed) g_best_effort(s, c, o, w, w.unalloc, n_un, policy);
+  if (delayed && writer) g_best_effort(s, c, o, w, w.unalloc, n_un, policy);
 }
 
 __global__ void __launch_bounds__(256) greedy_clear_solution_kernel(SolView o, int S) {

@@ -325,6 +325,26 @@ __global__ void greedy_allocate_kernel(SysView s, CandView c, SolView o, GreedyW
       if (writer) w.cur_idx[srv] = ci;
       __syncwarp();
       const int n = w.ncand[srv];
+      if (policy == 0 && ci < n) {
+        // Policy None: bestEffort() is a no-op, so an entry that can no longer be satisfied changes
+        // nothing whenever its remaining candidates are tried.  `available` only decreases, hence a
+        // candidate that does not fit NOW never will: if none of the remaining candidates fits now the
+        // entry is dropped at once (the lanes test the candidates in parallel).  Exact for this policy;
+        // for the others the order of the unallocated list matters and the literal sweep is kept.
+        bool fits = false;
+        for (int j0 = ci; j0 < n; j0 += 32) {
+          const int j = j0 + (int)(threadIdx.x & 31);
+          if (j < n) {
+            const int a2 = ord[j];
+            const size_t i2 = (size_t)srv * A + a2;
+            if (c.state[i2] == ALLOC_ACC) {
+              const long long cnt2 = (long long)c.num_replicas[i2] * g_upr(s, srv, a2);
+              if (w.avail[s.acc_type[a2]] >= cnt2) fits = true;
+            }
+          }
+        }
+        if (!__any_sync(0xffffffffu, fits)) { if (writer) w.unalloc[n_un] = srv; n_un++; __syncwarp(); continue; }
+      }
       if (ci + 1 < n) e.delta = f_sub(c.value[(size_t)srv * A + ord[ci + 1]], c.value[(size_t)srv * A + ord[ci]]);
       else if (ci == n) { if (writer) w.unalloc[n_un] = srv; n_un++; __syncwarp(); continue; }
       else e.delta = FLT_MAX;

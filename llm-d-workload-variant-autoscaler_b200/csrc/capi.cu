@@ -93,7 +93,7 @@ struct wva_ctx {
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
   int policy = 0;
-  DevBuf sys_arena, cand_arena, sol_arena, scratch, gtab, greedy_ws;
+  DevBuf sys_arena, cand_arena, sol_arena, scratch, gtab, greedy_ws, split_ws;
   PinBuf stage_in, stage_out;
   SysView sys = {};
   CandView cand = {};
@@ -163,7 +163,7 @@ int32_t wva_destroy(wva_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->sys_arena.release(); ctx->cand_arena.release(); ctx->sol_arena.release(); ctx->scratch.release();
-  ctx->gtab.release(); ctx->greedy_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->io_in.release(); ctx->io_out.release();
+  ctx->gtab.release(); ctx->greedy_ws.release(); ctx->split_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->io_in.release(); ctx->io_out.release();
   ctx->stage_in.release(); ctx->stage_out.release(); ctx->io_stage_in.release(); ctx->io_stage_out.release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -273,12 +273,34 @@ int32_t wva_load_system(wva_ctx* ctx, const wva_system* s) {
 template <int THREADS, bool SMEM>
 static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned long long n_pairs, int nmax, float* gtab,
                                 int* ovf_list) {
-  // lane_sizer_mode 1 = flattened state machine (sizer_kernel.cuh); otherwise lock-step rounds
-  auto k = (ctx->lane_sizer_mode == 1) ? sizer_kernel<THREADS, SMEM>
-           : (ctx->lane_sizer_mode == 2) ? sizer_lane_kernel<THREADS, SMEM, false> : sizer_lane_kernel<THREADS, SMEM, true>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list);
+  // lane_sizer_mode 1 = flattened state machine (sizer_kernel.cuh); 2 = lock-step rounds; 3 = lock-step with two
+  // chains per lane; 4 = lock-step, every pair split into a TTFT item and an ITL item (mid-size systems)
+  cudaError_t e;
+  if (ctx->lane_sizer_mode == 1) {
+    auto k = sizer_kernel<THREADS, SMEM>;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list);
+  } else {
+    SplitWs sw = {nullptr, nullptr, nullptr};
+    const bool split = ctx->lane_sizer_mode == 4;
+    if (split) {
+      size_t need = (size_t)n_pairs * 20 + 256;
+      e = ctx->split_ws.reserve(need);
+      if (e != cudaSuccess) return e;
+      sw.res = (float*)ctx->split_ws.p;
+      sw.solves = (int*)((char*)ctx->split_ws.p + (size_t)n_pairs * 8);
+      sw.cnt = (int*)((char*)ctx->split_ws.p + (size_t)n_pairs * 16);
+      e = cudaMemsetAsync(sw.cnt, 0, (size_t)n_pairs * 4, ctx->stream);
+      if (e != cudaSuccess) return e;
+    }
+    auto k = split ? sizer_lane_kernel<THREADS, SMEM, false, true>
+           : (ctx->lane_sizer_mode == 3) ? sizer_lane_kernel<THREADS, SMEM, true, false>
+                                         : sizer_lane_kernel<THREADS, SMEM, false, false>;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list, sw);
+  }
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -299,7 +321,7 @@ int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
   if (!ctx) return WVA_ERR_ARG;
   if (option == WVA_OPT_FORCE_LANE_SIZER) {
     ctx->force_lane_sizer = value != 0;
-    if (value >= 1 && value <= 3) ctx->lane_sizer_mode = value;
+    if (value >= 1 && value <= 4) ctx->lane_sizer_mode = value;
     return WVA_OK;
   }
   return WVA_ERR_ARG;
@@ -345,7 +367,8 @@ int32_t wva_calculate(wva_ctx* ctx) {
     }
     // small problems are latency bound: spread the pairs over every SM with as few lanes per SM
     // as needed instead of filling the first SMs (lanes pull one pair each from the queue)
-    const unsigned long long lanes_needed = (n_pairs + ctx->sm_count - 1) / ctx->sm_count;
+    const unsigned long long n_items = (ctx->lane_sizer_mode == 4) ? 2 * n_pairs : n_pairs;
+    const unsigned long long lanes_needed = (n_items + ctx->sm_count - 1) / ctx->sm_count;
     if (best_per_sm >= 1 && lanes_needed <= 256 && lanes_needed < (unsigned long long)best_threads * best_per_sm) {
       int t = 64;
       while ((unsigned long long)t < lanes_needed) t += 64;

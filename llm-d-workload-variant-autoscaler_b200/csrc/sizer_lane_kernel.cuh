@@ -16,10 +16,35 @@
 
 namespace wva {
 
-template <int THREADS, bool SMEM_TABLE, bool DUAL>
+// Split mode scratch: per pair two published results + a completion counter (zeroed before the launch).
+struct SplitWs {
+  float* res;     // [2 * n_pairs] lambda* of the TTFT / ITL item, < 0 = the search failed
+  int* solves;    // [2 * n_pairs]
+  int* cnt;       // [n_pairs]
+};
+
+// A split item finished its search: publish; the first finisher retires, the second merges and goes on.
+__device__ __forceinline__ bool split_publish(SizerLane& z, const SysView& s, const CandView& out, const SplitWs& sw) {
+  const size_t pair = (size_t)z.srv * s.n_acc + z.acc;
+  const size_t me = pair * 2 + (size_t)z.split;
+  sw.res[me] = z.failed ? -1.0f : (z.split == 0 ? z.sT.result : z.sI.result);
+  sw.solves[me] = z.solves;
+  __threadfence();
+  const int old = atomicAdd(&sw.cnt[pair], 1);
+  if (old == 0) return false;                          // partner still searching: it will finish the pair
+  __threadfence();
+  const float pr = *((volatile float*)&sw.res[me ^ 1]);
+  z.solves += *((volatile int*)&sw.solves[me ^ 1]);
+  z.merged = true;
+  if (z.failed || pr < 0.0f) { lane_fail(z, s, out); return false; }
+  if (z.split == 0) z.sI.result = pr; else z.sT.result = pr;
+  return sizer_after_search(z, s, out);                // -> the two Analyze solves
+}
+
+template <int THREADS, bool SMEM_TABLE, bool DUAL, bool SPLIT>
 __global__ void __launch_bounds__(THREADS)
 sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax, float* gtab,
-                  SizerCounters* ctr, int* overflow_list) {
+                  SizerCounters* ctr, int* overflow_list, SplitWs sw) {
   extern __shared__ float smem_tab[];
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
@@ -39,13 +64,14 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
     bool need_table = false;
     if (!live && !exhausted) {
       while (true) {
-        unsigned long long pair = atomicAdd(&ctr->next_pair, 1ull);
-        if (pair >= n_pairs) { exhausted = true; break; }
+        unsigned long long item = atomicAdd(&ctr->next_pair, 1ull);
+        if (item >= (SPLIT ? 2 * n_pairs : n_pairs)) { exhausted = true; break; }
+        const unsigned long long pair = SPLIT ? (item >> 1) : item;
         int srv = (int)(pair / (unsigned)s.n_acc), acc = (int)(pair % (unsigned)s.n_acc);
         int lim = 0;
-        int rc = sizer_setup(z, s, out, srv, acc, nmax, &lim);
+        int rc = sizer_setup(z, s, out, srv, acc, nmax, &lim, !SPLIT || (item & 1) == 0);
         if (lim) ctr->limit_hit = 1;
-        if (rc == SETUP_NEEDS_TABLE) { need_table = true; break; }
+        if (rc == SETUP_NEEDS_TABLE) { need_table = true; if (SPLIT) z.split = (int)(item & 1); break; }
       }
     }
     unsigned need = __ballot_sync(full, need_table);
@@ -67,6 +93,7 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
     if (need_table) {
       model_finish(z.m, tab, stride);
       live = DUAL ? dual_begin(z, s, out) : sizer_begin(z, s, out);
+      if (SPLIT) { if (live && z.stage == SZ_PUBLISH) live = split_publish(z, s, out, sw); }
       if (!live) my_solves += z.solves;
     }
     const unsigned live_mask = __ballot_sync(full, live);
@@ -127,6 +154,7 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
           live = false;
         } else {
           live = sizer_on_solve(z, s, out, st);
+          if (SPLIT) { if (live && z.stage == SZ_PUBLISH) live = split_publish(z, s, out, sw); }
         }
         if (!live) { my_solves += z.solves; my_states += z.states; }
       }

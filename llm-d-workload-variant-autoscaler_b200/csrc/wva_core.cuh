@@ -430,7 +430,7 @@ WVA_HD long long go_int_ceil(double x) {
 // setup() classifies the pair (nil / zero-load / needs sizing); step() advances the
 // current chain solve by one state and, when a solve completes, the bisection /
 // Size / Analyze control flow (queueanalyzer.go:181-258, utils.go:26-70).
-enum { SZ_LO = 0, SZ_HI = 1, SZ_SEARCH = 2, SZ_FINAL1 = 3, SZ_FINAL2 = 4 };
+enum { SZ_LO = 0, SZ_HI = 1, SZ_SEARCH = 2, SZ_FINAL1 = 3, SZ_FINAL2 = 4, SZ_PUBLISH = 5 };
 
 struct Search {   // one BinarySearch (utils.go:26-70)
   float lo, hi, target, x, result, y_lo;
@@ -453,6 +453,10 @@ struct SizerLane {
   int srv, acc, model;
   int min_replicas, n_inst;
   int solves;
+  // split mode (lane sizer on mid-size systems): a pair is two work items, one per search; the item that
+  // finishes second merges the partner's result and runs the two Analyze solves
+  int split;             // -1 whole pair, 0 TTFT item, 1 ITL item
+  bool merged, failed;
   long long states;
   long long num_replicas;
   float cost;
@@ -466,6 +470,7 @@ enum { SETUP_DONE = 0, SETUP_NEEDS_TABLE = 1 };
 WVA_HD int sizer_setup(SizerLane& z, const SysView& s, const CandView& out, int srv, int acc, int n_limit,
                        int* limit_hit, bool write = true) {
   z.srv = srv; z.acc = acc; z.solves = 0; z.states = 0;
+  z.split = -1; z.merged = false; z.failed = false;
   size_t idx = (size_t)srv * s.n_acc + acc;
   Alloc a; a.state = ALLOC_NONE; a.num_replicas = 0; a.batch_size = 0;
   a.cost = a.value = a.itl = a.ttft = a.rho = a.max_arrv = 0.0f;
@@ -550,14 +555,22 @@ WVA_HD void lane_fail(SizerLane& z, const SysView& s, const CandView& out) {
 WVA_HD bool sizer_begin(SizerLane& z, const SysView& s, const CandView& out);
 WVA_HD bool sizer_after_search(SizerLane& z, const SysView& s, const CandView& out);
 
+// a failure during the search phase: in split mode it is published for the partner item instead of written
+WVA_HD bool search_fail(SizerLane& z, const SysView& s, const CandView& out) {
+  if (z.split >= 0 && !z.merged) { z.failed = true; z.stage = SZ_PUBLISH; return true; }
+  lane_fail(z, s, out);
+  return false;
+}
+
 WVA_HD bool sizer_begin(SizerLane& z, const SysView& s, const CandView& out) {
-  z.sT.enabled = z.sT.target > 0.0f; z.sI.enabled = z.sI.target > 0.0f;
+  z.sT.enabled = z.sT.target > 0.0f && z.split != 1;
+  z.sI.enabled = z.sI.target > 0.0f && z.split != 0;
   z.sT.active = z.sT.enabled; z.sI.active = z.sI.enabled;
   z.sT.result = z.m.lambda_max; z.sI.result = z.m.lambda_max;
   z.sT.iter = z.sI.iter = 0;
   if (z.sT.enabled || z.sI.enabled) {
     // BinarySearch: xMin > xMax -> error (utils.go:29-31)
-    if (z.m.lambda_min > z.m.lambda_max) { lane_fail(z, s, out); return false; }
+    if (z.m.lambda_min > z.m.lambda_max) return search_fail(z, s, out);
     z.stage = SZ_LO;
     lane_start_solve(z, z.m.lambda_min);
     return true;
@@ -569,6 +582,7 @@ WVA_HD bool sizer_begin(SizerLane& z, const SysView& s, const CandView& out) {
 WVA_HD bool analyze_admits(const PairModel& m, float rate) { return rate > 0.0f && !(rate > m.rate_max); }
 
 WVA_HD bool sizer_after_search(SizerLane& z, const SysView& s, const CandView& out) {
+  if (z.split >= 0 && !z.merged) { z.stage = SZ_PUBLISH; return true; }   // publish; the second finisher goes on
   float l_tps = z.m.lambda_max;
   if (z.slo_tps > 0.0f) l_tps = f_mul(z.m.lambda_max, f_sub(1.0f, WVA_STABILITY_SAFETY));  // :232-235
   float lambda = fminf(fminf(z.sT.result, z.sI.result), l_tps);                             // :238
@@ -768,7 +782,7 @@ WVA_HD bool sizer_on_solve(SizerLane& z, const SysView& s, const CandView& out, 
       q.lo = m.lambda_min; q.hi = m.lambda_max; q.iter = 0;
       q.x = f_mul(0.5f, f_add(q.lo, q.hi));
     }
-    if (infeasible) { lane_fail(z, s, out); return false; }   // "target is below the bounded region"
+    if (infeasible) return search_fail(z, s, out);   // "target is below the bounded region"
     z.stage = SZ_SEARCH;
   } else if (z.stage == SZ_SEARCH) {
     float x = z.cur_x;

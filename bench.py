@@ -256,7 +256,7 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        sizer_name = "sizer_warp_kernel" if S * A <= 148 * 80 else "sizer_lane_kernel"
+        sizer_name = "sizer_warp_kernel" if S * A <= 148 * 80 else "sizer_lane_kernel"   # capi.cu wva_calculate
         if grid_ms >= calc_ms:
             dominant, dom_ms, alg_bytes, dom_states = "grid_kernel", grid_ms, S * A * R * ALG_BYTES_PER_EVAL, last["grid_states"]
         else:

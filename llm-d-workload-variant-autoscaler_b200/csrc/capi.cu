@@ -367,6 +367,9 @@ int32_t wva_calculate(wva_ctx* ctx) {
     }
     // small problems are latency bound: spread the pairs over every SM with as few lanes per SM
     // as needed instead of filling the first SMs (lanes pull one pair each from the queue)
+    // mid-size systems (measured: up to ~200 pairs per SM) still leave lanes idle: split every pair into a
+    // TTFT item and an ITL item, which halves the chain of dependent solves per work item
+    if (!ctx->force_lane_sizer) ctx->lane_sizer_mode = (n_pairs <= (unsigned long long)ctx->sm_count * 200) ? 4 : 2;
     const unsigned long long n_items = (ctx->lane_sizer_mode == 4) ? 2 * n_pairs : n_pairs;
     const unsigned long long lanes_needed = (n_items + ctx->sm_count - 1) / ctx->sm_count;
     if (best_per_sm >= 1 && lanes_needed <= 256 && lanes_needed < (unsigned long long)best_threads * best_per_sm) {

@@ -43,6 +43,15 @@ __device__ __forceinline__ double shfl_xor_d(unsigned mask, double v, int lanema
   return __hiloint2double(hi, lo);
 }
 
+// x / n for an integer 0 < n < 2^24, correctly rounded: n is float32-valued, so (E1) of wva_core.cuh applies
+// (3 FP64 ops + the shared reciprocal instead of the ~20-instruction div.rn.f64 sequence)
+__device__ __forceinline__ double div_small_int(double x, int n) {
+  const float nf = (float)n;
+  const double nd = (double)n;
+  if (n < (1 << 24) && (in_window(x) || x == 0.0)) return div_f32den(x, nd, rcp_f32den(nf, nd));
+  return d_div(x, nd);
+}
+
 template <bool DETAIL>
 __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out) {
   const unsigned full = 0xffffffffu;
@@ -102,7 +111,7 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
             }
           }
         }
-        if (ns > 0) { avgKv = d_div(sumKv, (double)ns); avgQ = d_div(sumQ, (double)ns); }  // :188-191
+        if (ns > 0) { avgKv = div_small_int(sumKv, ns); avgQ = div_small_int(sumQ, ns); }        // :188-191
         if (DETAIL) {
           if (out.var_replica_count) out.var_replica_count[v] = cnt;
           if (out.var_non_saturated) out.var_non_saturated[v] = ns;
@@ -119,11 +128,15 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
       __syncwarp();
       my_terms[lane] = make_double2(termKv, termQ);
       __syncwarp();
+      {
+        // lanes 0-15 run the KV chain, lanes 16-31 the queue chain (each exact and sequential)
+        const double* col = reinterpret_cast<const double*>(my_terms) + (lane >> 4);
+        double acc = (lane < 16) ? totalSpareKv : totalSpareQueue;
 #pragma unroll
-      for (int l = 0; l < 32; l++) {
-        const double2 t2 = my_terms[l];
-        totalSpareKv = d_add(totalSpareKv, t2.x);
-        totalSpareQueue = d_add(totalSpareQueue, t2.y);
+        for (int l = 0; l < 32; l++) acc = d_add(acc, col[2 * l]);
+        const double other = shfl_xor_d(full, acc, 16);
+        totalSpareKv = (lane < 16) ? acc : other;
+        totalSpareQueue = (lane < 16) ? other : acc;
       }
       nonSaturated += __reduce_add_sync(full, analysed ? ns : 0);
       totalReplicas += __reduce_add_sync(full, act ? cnt : 0);
@@ -140,15 +153,15 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
     bool up = false, downSafe = false, kvT = false, qT = false;
     if (totalReplicas > 0) {
       if (nonSaturated > 0) {
-        avgSpareKv = d_div(totalSpareKv, (double)nonSaturated);
-        avgSpareQueue = d_div(totalSpareQueue, (double)nonSaturated);
+        avgSpareKv = div_small_int(totalSpareKv, nonSaturated);
+        avgSpareQueue = div_small_int(totalSpareQueue, nonSaturated);
       }
       kvT = avgSpareKv < kvTrig;
       qT = avgSpareQueue < qTrig;
       up = kvT || qT;
       if (nonSaturated >= 2) {
         const double avgKvLoad = d_sub(kvThr, avgSpareKv), avgQLoad = d_sub(qThr, avgSpareQueue);
-        const double scale = d_div((double)nonSaturated, (double)(nonSaturated - 1));
+        const double scale = div_small_int((double)nonSaturated, nonSaturated - 1);
         const double remKv = d_sub(kvThr, d_mul(avgKvLoad, scale)), remQ = d_sub(qThr, d_mul(avgQLoad, scale));
         downSafe = (remKv >= kvTrig) && (remQ >= qTrig);
       }

@@ -65,24 +65,8 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
   __shared__ double2 terms[8][32];
   double2* my_terms = terms[threadIdx.x >> 5];
 
-  // Software pipeline over this warp's models: while model m is processed, the variant range of model
-  // m + 2*nwarps and this lane's replica range of model m + nwarps are already in flight, so only the
-  // replica stream itself (one memory round trip) is exposed per model.
-  const int* __restrict__ mvo = in.model_variant_off;
-  const long long M = in.n_models;
-  int p_v0 = 0, p_v1 = 0, p_lo = 0, p_hi = 0, q_v0 = 0, q_v1 = 0;
-  if (warp0 < M) {
-    p_v0 = mvo[warp0]; p_v1 = mvo[warp0 + 1];
-    if (p_v0 + lane < p_v1) { p_lo = vro[p_v0 + lane]; p_hi = vro[p_v0 + lane + 1]; }
-  }
-  if (warp0 + nwarps < M) { q_v0 = mvo[warp0 + nwarps]; q_v1 = mvo[warp0 + nwarps + 1]; }
-  for (long long m = warp0; m < M; m += nwarps) {
-    const int v0 = p_v0, v1 = p_v1, lo0 = p_lo, hi0 = p_hi;
-    // rotate the pipeline: next model's ranges
-    p_v0 = q_v0; p_v1 = q_v1; p_lo = 0; p_hi = 0;
-    if (m + nwarps < M && p_v0 + lane < p_v1) { p_lo = vro[p_v0 + lane]; p_hi = vro[p_v0 + lane + 1]; }
-    q_v0 = 0; q_v1 = 0;
-    if (m + 2 * nwarps < M) { q_v0 = mvo[m + 2 * nwarps]; q_v1 = mvo[m + 2 * nwarps + 1]; }
+  for (long long m = warp0; m < in.n_models; m += nwarps) {
+    const int v0 = in.model_variant_off[m], v1 = in.model_variant_off[m + 1];
     const double kvThr = in.cfg_kv_threshold[m], qThr = in.cfg_queue_threshold[m];
     const double kvTrig = in.cfg_kv_trigger[m], qTrig = in.cfg_queue_trigger[m];
     double totalSpareKv = 0.0, totalSpareQueue = 0.0;
@@ -97,7 +81,7 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
       double sumKv = 0.0, sumQ = 0.0, maxKv = 0.0, avgKv = 0.0, avgQ = 0.0;
       long long maxQ = 0;
       if (act) {
-        const int lo = (c0 == v0) ? lo0 : vro[v], hi = (c0 == v0) ? hi0 : vro[v + 1];   // first chunk: prefetched
+        const int lo = vro[v], hi = vro[v + 1];
         cnt = hi - lo;
         for (int base = lo; base < hi; base += 4) {
           double kvv[4]; long long qq[4];

@@ -72,6 +72,9 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
     double totalSpareKv = 0.0, totalSpareQueue = 0.0;
     int nonSaturated = 0, totalReplicas = 0, nAnalysed = 0;
     bool inTransition = false;
+    const bool single = v1 - v0 <= 32;          // the usual case: the lane's variant data stays in registers
+    int r_cur = 0, r_des = 0, r_pen = 0, r_cnt = 0;
+    double r_cost = 0.0;
 
     // ---- phase A: analyzeVariant per lane, ordered combine ---------------------------------
     for (int c0 = v0; c0 < v1; c0 += 32) {
@@ -80,6 +83,11 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
       int cnt = 0, ns = 0;
       double sumKv = 0.0, sumQ = 0.0, maxKv = 0.0, avgKv = 0.0, avgQ = 0.0;
       long long maxQ = 0;
+      // the variant's state is requested NOW, together with its replica range, so these loads overlap the
+      // replica stream instead of adding two more dependent memory round trips per model
+      const bool hs = act && (!in.var_has_state || in.var_has_state[v]);
+      const int cur = hs ? in.var_current[v] : 0, des = hs ? in.var_desired[v] : 0;
+      r_cur = cur; r_des = des; r_pen = hs ? in.var_pending[v] : 0; r_cost = act ? in.var_cost[v] : 0.0;
       if (act) {
         const int lo = vro[v], hi = vro[v + 1];
         cnt = hi - lo;
@@ -142,8 +150,7 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
       totalReplicas += __reduce_add_sync(full, act ? cnt : 0);
       nAnalysed += __popc(__ballot_sync(full, analysed));
       // transition checks (analyzer.go:322-341); a variant without state reads the zero value
-      const bool hs = act && (!in.var_has_state || in.var_has_state[v]);
-      const int cur = hs ? in.var_current[v] : 0, des = hs ? in.var_desired[v] : 0;
+      r_cnt = cnt;
       const bool trans = analysed && ((des != 0 && des != cur) || (cnt != cur));
       if (__any_sync(full, trans)) inTransition = true;
     }
@@ -188,13 +195,19 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
       for (int c0 = v0; c0 < v1; c0 += 32) {
         const int v = c0 + lane;
         bool cand = false;
+        double vcost = 0.0;
         if (v < v1) {
-          const int cnt = vro[v + 1] - vro[v];
-          const bool hs = !in.var_has_state || in.var_has_state[v];
-          const int pen = hs ? in.var_pending[v] : 0;
+          int cnt, pen;
+          if (single) { cnt = r_cnt; pen = r_pen; vcost = r_cost; }
+          else {
+            cnt = vro[v + 1] - vro[v];
+            const bool hs2 = !in.var_has_state || in.var_has_state[v];
+            pen = hs2 ? in.var_pending[v] : 0;
+            vcost = in.var_cost[v];
+          }
           cand = cnt > 0 && (want_min ? (pen <= 0) : (cnt > 1));
         }
-        double c = cand ? in.var_cost[v] : 0.0;
+        double c = cand ? vcost : 0.0;
         int idx = cand ? v : -1;
         for (int o = 16; o; o >>= 1) {
           const double oc = shfl_xor_d(full, c, o);
@@ -216,13 +229,13 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
     for (int c0 = v0; c0 < v1; c0 += 32) {
       const int v = c0 + lane;
       if (v >= v1) continue;
-      const int cnt = vro[v + 1] - vro[v];
+      const int cnt = single ? r_cnt : vro[v + 1] - vro[v];
       const bool hs = !in.var_has_state || in.var_has_state[v];
       int tgt;
-      if (nAnalysed == 0) tgt = hs ? in.var_current[v] : -1;            // nil safety :303-309
+      if (nAnalysed == 0) tgt = hs ? (single ? r_cur : in.var_current[v]) : -1;   // nil safety :303-309
       else if (cnt == 0) tgt = -1;                                      // not in VariantAnalyses
       else if (inTransition) {                                          // :350-359
-        const int cur = hs ? in.var_current[v] : 0, des = hs ? in.var_desired[v] : 0;
+        const int cur = single ? r_cur : (hs ? in.var_current[v] : 0), des = single ? r_des : (hs ? in.var_desired[v] : 0);
         tgt = (des != 0 && des != cur) ? des : cur;
       } else tgt = cnt + (v == plus_v ? 1 : 0) - (v == minus_v ? 1 : 0);   // :362, :399, :428
       if (out.var_target) out.var_target[v] = tgt;

@@ -4,6 +4,7 @@ rep = sys.argv[1]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[0]
+units = dict(zip(rows[0], rows[1]))
 want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -28,5 +29,5 @@ for r in rows[2:]:
     d = dict(zip(hdr, r))
     for w in want:
         if w in d:
-            print(f"{w} = {d[w]}")
+            print(f"{w} = {d[w]} {units.get(w, '')}".rstrip())
     print("----")

@@ -105,21 +105,21 @@ __global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out
               const double kv = kvv[j];
               const long long q = qq[j];
               const double qd = (double)q;
-              const bool sat = kv >= kvThr || qd >= qThr;                       // analyzer.go:160-161
+              const bool sat = kv >= kvThr || qd >= qThr;                       // analyzer.go:163-164
               if (DETAIL) { if (out.rep_saturated) out.rep_saturated[base + j] = sat ? 1 : 0; }
               if (!sat) {
-                sumKv = d_add(sumKv, d_sub(kvThr, kv));                        // :167-171
+                sumKv = d_add(sumKv, d_sub(kvThr, kv));                        // :170-175
                 sumQ = d_add(sumQ, d_sub(qThr, qd));
                 ns++;
               }
               if (DETAIL) {
-                if (kv > maxKv) maxKv = kv;                                    // :177-182
+                if (kv > maxKv) maxKv = kv;                                    // :179-184
                 if (q > maxQ) maxQ = q;
               }
             }
           }
         }
-        if (ns > 0) { avgKv = div_small_int(sumKv, ns); avgQ = div_small_int(sumQ, ns); }        // :188-191
+        if (ns > 0) { avgKv = div_small_int(sumKv, ns); avgQ = div_small_int(sumQ, ns); }        // :190-193
         if (DETAIL) {
           if (out.var_replica_count) out.var_replica_count[v] = cnt;
           if (out.var_non_saturated) out.var_non_saturated[v] = ns;

@@ -132,7 +132,7 @@ sizer_warp_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
         }
       }
     }
-    // ---- Size() tail + CreateAllocation (queueanalyzer.go:232-247, allocation.go:124-154) --------------
+    // ---- Size() tail + CreateAllocation (queueanalyzer.go:232-247, allocation.go:123-153) --------------
     Alloc a = fail;
     if (!failed && !ovf_any) {
       float l_tps = m.lambda_max;

@@ -465,7 +465,7 @@ struct SizerLane {
 // result of setup()
 enum { SETUP_DONE = 0, SETUP_NEEDS_TABLE = 1 };
 
-// allocation.go:27-100: everything before the queue analyzer exists.  When the pair
+// allocation.go:27-99: everything before the queue analyzer exists.  When the pair
 // is decided without any chain solve the candidate is written and SETUP_DONE returned.
 WVA_HD int sizer_setup(SizerLane& z, const SysView& s, const CandView& out, int srv, int acc, int n_limit,
                        int* limit_hit, bool write = true) {
@@ -513,7 +513,7 @@ WVA_HD int sizer_setup(SizerLane& z, const SysView& s, const CandView& out, int 
     if (write) store_candidate(out, idx, a, 0);
     return SETUP_DONE;
   }
-  // allocation.go:79-88
+  // allocation.go:78-87
   long long Nll;
   if (s.srv_max_batch[srv] > 0) Nll = s.srv_max_batch[srv];
   else {
@@ -532,7 +532,7 @@ WVA_HD int sizer_setup(SizerLane& z, const SysView& s, const CandView& out, int 
   z.sT.target = ttft; z.sI.target = itl;
   // TargetPerf.check (utils.go:121-128)
   if (itl < 0.0f || ttft < 0.0f || z.slo_tps < 0.0f) { if (write) store_candidate(out, idx, a, 0); return SETUP_DONE; }
-  // allocation.go:127-132
+  // allocation.go:126-131
   z.total_rate = (z.slo_tps == 0.0f) ? f_div(arrival, 60.0f) : f_div(z.slo_tps, (float)out_tok);
   return SETUP_NEEDS_TABLE;
 }
@@ -688,8 +688,8 @@ WVA_HD bool dual_on_solve(SizerLane& z, const SysView& s, const CandView& out, c
     return dual_schedule(z, s, out);
   }
   if (z.stage == D2_FINAL1) {
-    z.rate_star = f_mul(st[0].throughput, 1000.0f);                                     // allocation.go:124
-    long long nr = go_int_ceil(d_div((double)z.total_rate, (double)z.rate_star));       // :133
+    z.rate_star = f_mul(st[0].throughput, 1000.0f);                                     // allocation.go:123
+    long long nr = go_int_ceil(d_div((double)z.total_rate, (double)z.rate_star));       // :132
     if (nr < (long long)z.min_replicas) nr = z.min_replicas;
     z.num_replicas = nr;
     long long tot = (long long)((unsigned long long)z.n_inst * (unsigned long long)nr);
@@ -701,7 +701,7 @@ WVA_HD bool dual_on_solve(SizerLane& z, const SysView& s, const CandView& out, c
     z.solves++;
     return true;
   }
-  Alloc a;                                                                              // allocation.go:147-154
+  Alloc a;                                                                              // allocation.go:146-153
   a.state = ALLOC_ACC;
   a.num_replicas = z.num_replicas;
   a.batch_size = m.N;
@@ -795,7 +795,7 @@ WVA_HD bool sizer_on_solve(SizerLane& z, const SysView& s, const CandView& out, 
     return sizer_after_search(z, s, out);
   }
   if (z.stage == SZ_FINAL1) {
-    // Size() -> metrics.Throughput; allocation.go:124-146
+    // Size() -> metrics.Throughput; allocation.go:123-145
     z.rate_star = f_mul(st.throughput, 1000.0f);
     long long nr = go_int_ceil(d_div((double)z.total_rate, (double)z.rate_star));
     if (nr < (long long)z.min_replicas) nr = z.min_replicas;
@@ -808,7 +808,7 @@ WVA_HD bool sizer_on_solve(SizerLane& z, const SysView& s, const CandView& out, 
     lane_start_solve(z, f_div(rate, 1000.0f));
     return true;
   }
-  // SZ_FINAL2: allocation.go:147-154
+  // SZ_FINAL2: allocation.go:146-153
   Alloc a;
   a.state = ALLOC_ACC;
   a.num_replicas = z.num_replicas;

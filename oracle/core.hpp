@@ -77,53 +77,53 @@ inline Allocation zeroLoadAllocation(const wva_system& s, int srv, int model, in
 // allocation.go:27-155.  Returns state NONE for Go's nil.
 inline Allocation CreateAllocation(const wva_system& s, int srv, int acc) {
   Allocation none;
-  if (acc < 0 || acc >= s.n_acc) return none;                       // :43-45
+  if (acc < 0 || acc >= s.n_acc) return none;                       // :42-44
   // load checks :51-54
   float arrival = s.srv_arrival[srv];
   int inTok = s.srv_in_tokens[srv], outTok = s.srv_out_tokens[srv];
   if (arrival < 0 || inTok < 0 || outTok < 0) return none;
   int model = s.srv_model[srv];
-  if (model < 0 || model >= s.n_models) return none;                // :58-60
+  if (model < 0 || model >= s.n_models) return none;                // :57-59
   size_t pi = (size_t)model * s.n_acc + acc;
-  if (!s.perf_present[pi]) return none;                             // :61-63
-  if (!s.srv_target_present[srv]) return none;                      // :66-71
-  if (arrival == 0 || outTok == 0) return zeroLoadAllocation(s, srv, model, acc);  // :74-76
+  if (!s.perf_present[pi]) return none;                             // :60-62
+  if (!s.srv_target_present[srv]) return none;                      // :65-70
+  if (arrival == 0 || outTok == 0) return zeroLoadAllocation(s, srv, model, acc);  // :73-75
 
-  int K = outTok;                                                   // :79
+  int K = outTok;                                                   // :78
   int N;
-  if (s.srv_max_batch[srv] > 0) N = s.srv_max_batch[srv];           // :83-84
-  else N = (int)std::max<int64_t>((int64_t)s.perf_max_batch[pi] * s.perf_at_tokens[pi] / K, 1);  // :86 (Go int is 64-bit; division truncates)
-  int maxQueue = N * MaxQueueToBatchRatio;                          // :88
+  if (s.srv_max_batch[srv] > 0) N = s.srv_max_batch[srv];           // :82-83
+  else N = (int)std::max<int64_t>((int64_t)s.perf_max_batch[pi] * s.perf_at_tokens[pi] / K, 1);  // :85 (Go int is 64-bit; division truncates)
+  int maxQueue = N * MaxQueueToBatchRatio;                          // :87
 
   Configuration qc;
   qc.MaxBatchSize = N;
   qc.MaxQueueSize = maxQueue;
   qc.parms = ServiceParms{s.perf_alpha[pi], s.perf_beta[pi], s.perf_gamma[pi]};
   RequestSize rq{(float)inTok, (float)K};
-  if (!QueueAnalyzer::checkConfig(qc) || !QueueAnalyzer::checkRequest(rq)) return none;  // :106-110
+  if (!QueueAnalyzer::checkConfig(qc) || !QueueAnalyzer::checkRequest(rq)) return none;  // :105-109
   QueueAnalyzer qa(qc, rq);
 
-  TargetPerf tp{s.srv_slo_ttft[srv], s.srv_slo_itl[srv], s.srv_slo_tps[srv]};  // :112-116
+  TargetPerf tp{s.srv_slo_ttft[srv], s.srv_slo_itl[srv], s.srv_slo_tps[srv]};  // :111-115
   AnalysisMetrics metrics;
-  if (!qa.Size(tp, nullptr, &metrics, nullptr)) {                   // :119-123
+  if (!qa.Size(tp, nullptr, &metrics, nullptr)) {                   // :118-122
     none.nSolves = (int)qa.model.solves;
     none.nStates = qa.model.statesVisited;
     return none;
   }
-  float rateStar = metrics.Throughput;                              // :124
+  float rateStar = metrics.Throughput;                              // :123
 
-  float totalRate;                                                  // :127-132
+  float totalRate;                                                  // :126-131
   if (tp.TargetTPS == 0) totalRate = arrival / 60;
   else totalRate = tp.TargetTPS / (float)K;
-  long long numReplicas = goIntCeil((double)totalRate / (double)rateStar);  // :133
-  numReplicas = std::max<long long>(numReplicas, s.srv_min_replicas[srv]);  // :134
+  long long numReplicas = goIntCeil((double)totalRate / (double)rateStar);  // :132
+  numReplicas = std::max<long long>(numReplicas, s.srv_min_replicas[srv]);  // :133
 
-  long long totalNumInstances =                                     // :137 (Go int multiply wraps)
+  long long totalNumInstances =                                     // :136 (Go int multiply wraps)
       (long long)((unsigned long long)NumInstances(s, model, acc) * (unsigned long long)numReplicas);
-  float cost = s.acc_cost[acc] * (float)totalNumInstances;          // :138
+  float cost = s.acc_cost[acc] * (float)totalNumInstances;          // :137
 
-  float rate = totalRate / (float)numReplicas;                      // :141
-  if (!qa.Analyze(rate, &metrics)) {                                // :142-146
+  float rate = totalRate / (float)numReplicas;                      // :140
+  if (!qa.Analyze(rate, &metrics)) {                                // :141-145
     none.nSolves = (int)qa.model.solves;
     none.nStates = qa.model.statesVisited;
     return none;
@@ -134,11 +134,11 @@ inline Allocation CreateAllocation(const wva_system& s, int srv, int acc) {
   a.numReplicas = numReplicas;
   a.batchSize = N;
   a.cost = cost;
-  a.itl = metrics.AvgTokenTime;                                     // :148
-  a.ttft = metrics.AvgWaitTime + metrics.AvgPrefillTime;            // :149 (quirk Q2)
+  a.itl = metrics.AvgTokenTime;                                     // :147
+  a.ttft = metrics.AvgWaitTime + metrics.AvgPrefillTime;            // :148 (quirk Q2)
   a.rho = metrics.Rho;
-  a.maxArrvRatePerReplica = rateStar / 1000;                        // :153
-  a.value = a.cost;                                                 // :154
+  a.maxArrvRatePerReplica = rateStar / 1000;                        // :152
+  a.value = a.cost;                                                 // :153
   a.nSolves = (int)qa.model.solves;
   a.nStates = qa.model.statesVisited;
   return a;

@@ -40,7 +40,7 @@ inline VariantAnalysis analyzeVariant(const wva_saturation_in& in, int64_t v, in
   for (int64_t i = lo; i < hi; i++) {
     double kv = in.rep_kv[i];
     int64_t q = in.rep_queue[i];
-    bool isSaturated = kv >= kvThr || (double)q >= qThr;  // :160-161
+    bool isSaturated = kv >= kvThr || (double)q >= qThr;  // :163-164
     if (repSaturated) repSaturated[i] = isSaturated ? 1 : 0;
     if (!isSaturated) {
       double spareKv = kvThr - kv;
@@ -49,11 +49,11 @@ inline VariantAnalysis analyzeVariant(const wva_saturation_in& in, int64_t v, in
       totalSpareQueue += spareQueue;
       nonSaturatedCount++;
     }
-    if (kv > a.MaxKvCacheUsage) a.MaxKvCacheUsage = kv;  // :177-182
+    if (kv > a.MaxKvCacheUsage) a.MaxKvCacheUsage = kv;  // :179-184
     if (q > a.MaxQueueLength) a.MaxQueueLength = q;
   }
   a.NonSaturatedCount = nonSaturatedCount;
-  if (nonSaturatedCount > 0) {  // :188-191
+  if (nonSaturatedCount > 0) {  // :190-193
     a.AvgSpareKvCapacity = totalSpareKv / (double)nonSaturatedCount;
     a.AvgSpareQueueLength = totalSpareQueue / (double)nonSaturatedCount;
   }
@@ -77,7 +77,7 @@ inline void SaturationV1(const wva_saturation_in& in, const wva_saturation_out& 
       va[(size_t)(v - v0)] = a;
       if (a.ReplicaCount > 0) {
         nAnalysed++;
-        nonSaturatedCount += a.NonSaturatedCount;                                     // :90-93
+        nonSaturatedCount += a.NonSaturatedCount;                                     // :87-92
         totalSpareKv += a.AvgSpareKvCapacity * (double)a.NonSaturatedCount;
         totalSpareQueue += a.AvgSpareQueueLength * (double)a.NonSaturatedCount;
       }
@@ -92,7 +92,7 @@ inline void SaturationV1(const wva_saturation_in& in, const wva_saturation_out& 
     double avgSpareKv = 0, avgSpareQueue = 0;
     bool shouldScaleUp = false, scaleDownSafe = false, kvTrig = false, qTrig = false;
     if (totalReplicas > 0) {  // len(replicaMetrics)==0 => early return, all false (:39-50)
-      if (nonSaturatedCount > 0) {  // :101-104
+      if (nonSaturatedCount > 0) {  // :98-101
         avgSpareKv = totalSpareKv / (double)nonSaturatedCount;
         avgSpareQueue = totalSpareQueue / (double)nonSaturatedCount;
       }

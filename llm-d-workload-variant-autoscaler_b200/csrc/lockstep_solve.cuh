@@ -41,18 +41,34 @@ struct LaneTable {   // one float32 column per lane ([n][thread], bank = lane); 
 struct P1 { double p, sum; int mn, mx; };
 struct P2 { double p, L, sumP, pi; int mn, mx; };
 
-__device__ __forceinline__ void p1_step(P1& s, double lam, double mu, double r) {
-  double x = d_mul(s.p, lam);
+// (E1) with a 3-deep dependency chain: the approximation q0 of x/mu = RN(p*lambda)/mu is formed as
+// p * RN(lambda*r) next to x = p*lambda instead of after it.  q0 only has to be within 2^-39.99 of the
+// quotient (it is within ~2^-45.9: r's 2^-46 plus three roundings); the remainder and the final fma use the
+// exact x, so the result is still the correctly rounded RN(x/mu).
+__device__ __forceinline__ double step_div(double p, double lam, double lamr, double mu, double r, int& mn, int& mx) {
+  double x = d_mul(p, lam);
+  double q0 = d_mul(p, lamr);
   int h = d_hi(x);
-  s.mn = min(s.mn, h); s.mx = max(s.mx, h);
-  s.p = div_f32den(x, mu, r);
+  mn = min(mn, h); mx = max(mx, h);
+  double rem = d_fma(-q0, mu, x);
+  return d_fma(rem, r, q0);
+}
+__device__ __forceinline__ void p1_step(P1& s, double lam, double mu, double r) {
+  s.p = step_div(s.p, lam, d_mul(lam, r), mu, r, s.mn, s.mx);
   s.sum = d_add(s.sum, s.p);
 }
+__device__ __forceinline__ void p1_step_c(P1& s, double lam, double lamr, double mu, double r) {   // constant rate (tail)
+  s.p = step_div(s.p, lam, lamr, mu, r, s.mn, s.mx);
+  s.sum = d_add(s.sum, s.p);
+}
+__device__ __forceinline__ void p2_step_c(P2& s, double lam, double lamr, double mu, double r, double sum, double rsum, double di) {
+  s.p = step_div(s.p, lam, lamr, mu, r, s.mn, s.mx);
+  s.pi = div_markstein2(s.p, sum, rsum);
+  s.L = d_add(s.L, d_mul(di, s.pi));
+  s.sumP = d_add(s.sumP, s.pi);
+}
 __device__ __forceinline__ void p2_step(P2& s, double lam, double mu, double r, double sum, double rsum, double di) {
-  double x = d_mul(s.p, lam);
-  int h = d_hi(x);
-  s.mn = min(s.mn, h); s.mx = max(s.mx, h);
-  s.p = div_f32den(x, mu, r);
+  s.p = step_div(s.p, lam, d_mul(lam, r), mu, r, s.mn, s.mx);
   s.pi = div_markstein2(s.p, sum, rsum);
   s.L = d_add(s.L, d_mul(di, s.pi));
   s.sumP = d_add(s.sumP, s.pi);
@@ -69,12 +85,13 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
   const unsigned full = 0xffffffffu;
   const int K = m.K, N = m.N, NH = N - 1;
   const double mu_l = m.mu_last, r_l = m.r_last;
-  double lam[NC], lamg[NC];
+  double lam[NC], lamg[NC], lamr_l[NC];
   bool tail_ok[NC], done[NC];
 #pragma unroll
   for (int c = 0; c < NC; c++) {
     lam[c] = active[c] ? (double)lambda[c] : 0.0;
     lamg[c] = d_mul((double)lambda[c], 1.000001);
+    lamr_l[c] = d_mul(lam[c], r_l);
     tail_ok[c] = d_bits(lamg[c]) <= d_bits(mu_l);
     done[c] = !active[c];
   }
@@ -127,12 +144,12 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
 #pragma unroll
       for (int j = 0; j < CH; j++) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) p1_step(a[c], lam[c], mu_l, r_l);
+        for (int c = 0; c < NC; c++) p1_step_c(a[c], lam[c], lamr_l[c], mu_l, r_l);
       }
     } else {
       for (int j = 0; j < cnt; j++) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) p1_step(a[c], lam[c], mu_l, r_l);
+        for (int c = 0; c < NC; c++) p1_step_c(a[c], lam[c], lamr_l[c], mu_l, r_l);
       }
     }
     bool any = false;
@@ -218,7 +235,7 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
 #pragma unroll
     for (int c = 0; c < NC; c++) {
       b[c].mn = 0x7fffffff; b[c].mx = 0;
-      p2_step(b[c], lam[c], mu_l, r_l, sum[c], rsum[c], di);
+      p2_step_c(b[c], lam[c], lamr_l[c], mu_l, r_l, sum[c], rsum[c], di);
       if (!done[c]) { states += 1; if (b[c].mn < WVA_HI_LO || b[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; } }
       Lserv[c] = d_add(b[c].L, d_mul(d_sub(1.0, b[c].sumP), (double)N));
       if (!done[c] && tail_ok[c]) {
@@ -239,13 +256,13 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
       for (int j = 0; j < CH; j++) {
         di = d_add(di, 1.0);
 #pragma unroll
-        for (int c = 0; c < NC; c++) p2_step(b[c], lam[c], mu_l, r_l, sum[c], rsum[c], di);
+        for (int c = 0; c < NC; c++) p2_step_c(b[c], lam[c], lamr_l[c], mu_l, r_l, sum[c], rsum[c], di);
       }
     } else {
       for (int j = 0; j < cnt; j++) {
         di = d_add(di, 1.0);
 #pragma unroll
-        for (int c = 0; c < NC; c++) p2_step(b[c], lam[c], mu_l, r_l, sum[c], rsum[c], di);
+        for (int c = 0; c < NC; c++) p2_step_c(b[c], lam[c], lamr_l[c], mu_l, r_l, sum[c], rsum[c], di);
       }
     }
     n += cnt;

@@ -238,6 +238,29 @@ int64_t emul_check_div_f32den(int64_t n, uint64_t seed) {
   }
   return bad;
 }
+// the 3-deep variant of (E1) used by lockstep_solve.cuh step_div: q0 = p * RN(lambda*r) formed beside x = p*lambda
+int64_t emul_check_step_div(int64_t n, uint64_t seed) {
+  std::mt19937_64 g(seed);
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    uint64_t a = g(), b = g(), c = g();
+    uint64_t pm = a & 0xFFFFFFFFFFFFFull; int pe = 1023 + (int)((a >> 52) % 400) - 200;
+    uint64_t pb = ((uint64_t)pe << 52) | pm; double p; memcpy(&p, &pb, 8);
+    uint32_t mm = (uint32_t)(b & 0x7FFFFF); int me = 127 + (int)((b >> 23) % 40) - 20;
+    uint32_t mb = ((uint32_t)me << 23) | mm; float m32; memcpy(&m32, &mb, 4);
+    uint32_t lm = (uint32_t)(c & 0x7FFFFF); int le = 127 + (int)((c >> 23) % 40) - 20;
+    uint32_t lb = ((uint32_t)le << 23) | lm; float l32; memcpy(&l32, &lb, 4);
+    if ((i & 7) == 0) { mb |= 0x7FFFFFu; memcpy(&m32, &mb, 4); }
+    double mu = (double)m32, lam = (double)l32;
+    double r = rcp_f32den(m32, mu);
+    double lamr = d_mul(lam, r);
+    double x = d_mul(p, lam), q0 = d_mul(p, lamr);
+    double rem = d_fma(-q0, mu, x);
+    double q = d_fma(rem, r, q0);
+    if (q != x / mu) bad++;
+  }
+  return bad;
+}
 int64_t emul_check_div_markstein2(int64_t n, uint64_t seed) {
   std::mt19937_64 g(seed);
   int64_t bad = 0;

@@ -22,6 +22,8 @@ def emul(pkg):
     lib.emul_calculate.argtypes = [C.POINTER(abi.System), C.POINTER(abi.Candidates)] + [C.POINTER(C.c_int64)] * 3
     lib.emul_check_div_f32den.restype = C.c_int64
     lib.emul_check_div_f32den.argtypes = [C.c_int64, C.c_uint64]
+    lib.emul_check_step_div.restype = C.c_int64
+    lib.emul_check_step_div.argtypes = [C.c_int64, C.c_uint64]
     lib.emul_check_div_markstein2.restype = C.c_int64
     lib.emul_check_div_markstein2.argtypes = [C.c_int64, C.c_uint64]
 
@@ -63,6 +65,7 @@ def test_exact_division_tricks(emul):
     """(E1)/(E2) of csrc/wva_core.cuh against the IEEE operator, incl. all-ones / power-of-two divisors."""
     assert emul.emul_check_div_f32den(5_000_000, 1) == 0
     assert emul.emul_check_div_markstein2(5_000_000, 2) == 0
+    assert emul.emul_check_step_div(5_000_000, 3) == 0
 
 
 @pytest.mark.parametrize("S,A,N,stream", [(10, 4, 32, 1), (40, 8, 16, 7), (12, 6, 128, 2), (4, 4, 256, 3),

@@ -1,0 +1,21 @@
+"""Small end-to-end pass for compute-sanitizer (memcheck / racecheck / initcheck): every kernel family once."""
+import importlib, sys, os
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pkg = importlib.import_module("llm-d-workload-variant-autoscaler_b200")
+d = pkg.synth.queue_system(24, 6, 32, stream=5)
+with pkg.Engine(0) as e:
+    for mode in (0, 1, 2, 3, 4):
+        e.set_option(1, mode)
+        e.load_system(d); e.calculate()
+    e.set_option(1, 0)
+    e.solve(); un = e.solution()
+    e.analyze_grid(40)
+    lim = pkg.synth.limit_capacity(d, un["type_count"], 0.5); lim["saturation_policy"] = "PriorityRoundRobin"
+    e.load_system(lim); e.calculate(); e.solve(); e.solution()
+    lim["saturation_policy"] = "None"; lim["delayed_best_effort"] = True
+    e.load_system(lim); e.calculate(); e.solve()
+    e.saturation_v1(pkg.synth.saturation_batch(50, 7, stream=9))
+    e.limit(pkg.synth.limiter_batch(500, 4, stream=9))
+    e.mm1k_eval(np.ones(10, np.float32), np.full(10, 2, np.float32), np.full(10, 20, np.int32))
+print("sanitize_run done")

@@ -254,6 +254,7 @@ int32_t wva_load_system(wva_ctx* ctx, const wva_system* s) {
            o_val = C.take(S * 4), o_itl = C.take(S * 4), o_ttft = C.take(S * 4), o_rho = C.take(S * 4), o_mar = C.take(S * 4),
            o_tc = C.take(T * 8), o_tk = C.take(T * 8);
     CK(ctx->sol_arena.reserve(C.off + 256));
+    CK(cudaMemsetAsync(ctx->sol_arena.p, 0, ctx->sol_arena.cap, ctx->stream));   // padding is copied out with the arena
     char* c = (char*)ctx->sol_arena.p;
     SolView& sv = ctx->sol;
     sv.state = (unsigned char*)(c + o_state); sv.acc = (int*)(c + o_acc); sv.num_replicas = (int*)(c + o_nr);

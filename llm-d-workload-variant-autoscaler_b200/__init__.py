@@ -7,6 +7,7 @@ There is no CPU fallback: constructing an Engine without the built CUDA library
 or without a GPU raises.
 """
 from . import _abi, sharding, synth  # noqa: F401
-from . import engine, manager  # noqa: F401
+from . import engine, manager, pipeline  # noqa: F401
 from .engine import Engine, WvaError, lib_path, load_library  # noqa: F401
 from .manager import Manager, flatten_spec  # noqa: F401
+from .pipeline import Limiter, SaturationAnalyzer  # noqa: F401

@@ -166,3 +166,130 @@ def test_unlimited_base_device(pkg, engine, oracle):
     spec["optimizerData"]["optimizer"]["unlimited"] = True
     _, out, _ = _device_vs_oracle(pkg, engine, oracle, spec)
     assert set(out["allocations"]) == {"server1", "server2", "server3"}
+
+
+# ---- the pipeline interfaces: SaturationAnalyzer and Limiter, records with the reference's field names ------------------------
+CFG = {"KvCacheThreshold": 0.8, "QueueLengthThreshold": 5, "KvSpareTrigger": 0.1, "QueueSpareTrigger": 3}
+
+
+def _rm(variant, kvs, queues, cost=10.0, acc="A100"):
+    return [{"PodName": f"{variant}-pod-{i}", "VariantName": variant, "ModelID": "test-model", "Namespace": "test-ns",
+             "AcceleratorName": acc, "Cost": cost, "KvCacheUsage": kv, "QueueLength": q}
+            for i, (kv, q) in enumerate(zip(kvs, queues))]
+
+
+def _states(rows):
+    return [{"VariantName": v, "CurrentReplicas": c, "DesiredReplicas": d, "PendingReplicas": p} for v, c, d, p in rows]
+
+
+@pytest.mark.gpu
+def test_analyze_model_saturation_reference_cases(pkg, engine):
+    """internal/saturation/analyzer_test.go:17-323, through the interface the engine loop calls."""
+    an = pkg.pipeline.SaturationAnalyzer(engine)
+    # :17-60 scale-up on KV (spare 0.05 / 0.04 < 0.1), :62-100 on queue (spare 2 < 3), :102-140 no trigger
+    a = an.analyze_model_saturation("test-model", "test-ns", _rm("v1", [.75, .76], [2, 2]), CFG)
+    assert a["ShouldScaleUp"] and a["ScaleUpReason"].startswith("KV spare Saturation low (0.045 < 0.100)")
+    assert a["TotalReplicas"] == 2 and a["NonSaturatedCount"] == 2
+    a = an.analyze_model_saturation("test-model", "test-ns", _rm("v1", [.5, .5], [3, 3]), CFG)
+    assert a["ShouldScaleUp"] and a["ScaleUpReason"] == "queue spare Saturation low (2.0 < 3.0)"
+    a = an.analyze_model_saturation("test-model", "test-ns", _rm("v1", [.5, .5], [1, 1]), CFG)
+    assert not a["ShouldScaleUp"] and a["ScaleUpReason"] == ""
+    # :142-192 two variants aggregate; :228-276 saturated replicas are named
+    a = an.analyze_model_saturation("test-model", "test-ns", _rm("v1", [.70, .75], [2, 3]) + _rm("v2", [.60, .65], [1, 2], acc="H100"), CFG)
+    assert a["TotalReplicas"] == 4 and a["NonSaturatedCount"] == 4 and len(a["VariantAnalyses"]) == 2
+    assert [v["VariantName"] for v in a["VariantAnalyses"]] == ["v1", "v2"] and a["VariantAnalyses"][1]["AcceleratorName"] == "H100"
+    a = an.analyze_model_saturation("test-model", "test-ns", _rm("v1", [.85, .50, .60], [2, 6, 2]), CFG)
+    va = a["VariantAnalyses"][0]
+    assert va["SaturatedReplicas"] == ["v1-pod-0", "v1-pod-1"] and va["NonSaturatedCount"] == 1
+    assert va["MaxKvCacheUsage"] == .85 and va["MaxQueueLength"] == 6
+    # :194-226 scale-down safety; :278-323 no metrics
+    assert an.analyze_model_saturation("m", "n", _rm("v1", [.2, .3, .25], [1, 1, 1]), CFG)["ScaleDownSafe"]
+    assert not an.analyze_model_saturation("m", "n", _rm("v1", [.7, .75], [2, 2]), CFG)["ScaleDownSafe"]
+    assert not an.analyze_model_saturation("m", "n", _rm("v1", [.5], [2]), CFG)["ScaleDownSafe"]
+    e = an.analyze_model_saturation("m", "n", [], CFG)
+    assert e["TotalReplicas"] == 0 and not e["ShouldScaleUp"] and not e["ScaleDownSafe"] and e["VariantAnalyses"] == []
+    assert an.calculate_saturation_targets(e, _states([("v1", 3, 0, 0)])) == {"v1": 3}
+
+
+@pytest.mark.gpu
+def test_calculate_saturation_targets_reference_cases(pkg, engine):
+    """analyzer_test.go:367-509: cheapest +1, most expensive -1, model-level transition blocking, metrics mismatch."""
+    an = pkg.pipeline.SaturationAnalyzer(engine)
+    three = lambda kv, q: (_rm("v1-expensive", [kv] * 2, [q] * 2, 20) + _rm("v2-cheap", [kv] * 2, [q] * 2, 5)
+                           + _rm("v3-medium", [kv] * 2, [q] * 2, 15))
+    two = lambda kv, q: _rm("v1-expensive", [kv] * 2, [q] * 2, 20) + _rm("v2-cheap", [kv] * 2, [q] * 2, 5)
+    up = an.analyze_model_saturation("test-model", "test-ns", three(.75, 2), CFG)
+    assert up["ShouldScaleUp"]
+    s3 = _states([("v1-expensive", 2, 0, 0), ("v2-cheap", 2, 0, 0), ("v3-medium", 2, 0, 0)])
+    assert an.calculate_saturation_targets(up, s3) == {"v1-expensive": 2, "v2-cheap": 3, "v3-medium": 2}
+    down = an.analyze_model_saturation("test-model", "test-ns", three(.2, 1), CFG)
+    assert not down["ShouldScaleUp"] and down["ScaleDownSafe"]
+    assert an.calculate_saturation_targets(down, s3) == {"v1-expensive": 1, "v2-cheap": 2, "v3-medium": 2}
+    up2 = an.analyze_model_saturation("test-model", "test-ns", two(.75, 2), CFG)
+    assert an.calculate_saturation_targets(up2, _states([("v1-expensive", 2, 4, 0), ("v2-cheap", 2, 0, 0)])) == \
+        {"v1-expensive": 4, "v2-cheap": 2}
+    assert an.calculate_saturation_targets(up2, _states([("v1-expensive", 3, 0, 0), ("v2-cheap", 2, 0, 0)])) == \
+        {"v1-expensive": 3, "v2-cheap": 2}
+    # pending replicas on the cheapest variant: the next cheapest takes the replica (analyzer.go:363-392)
+    s3p = _states([("v1-expensive", 2, 0, 0), ("v2-cheap", 2, 0, 1), ("v3-medium", 2, 0, 0)])
+    assert an.calculate_saturation_targets(up, s3p) == {"v1-expensive": 2, "v2-cheap": 2, "v3-medium": 3}
+
+
+@pytest.mark.gpu
+def test_analyze_batch_equals_single_calls(pkg, engine, oracle):
+    """Every model of a cycle in one launch == one call per model; == the oracle on the packed batch."""
+    an = pkg.pipeline.SaturationAnalyzer(engine)
+    rng = np.random.default_rng(5)
+    models = []
+    for m in range(40):
+        rm, st = [], []
+        for v in range(int(rng.integers(1, 5))):
+            n = int(rng.integers(1, 6))
+            rm += _rm(f"m{m}-v{v}", rng.uniform(0, 1, n).round(3).tolist(), rng.integers(0, 8, n).tolist(),
+                      cost=float(rng.choice([5, 10, 20])))
+            st.append((f"m{m}-v{v}", n + int(rng.integers(0, 2)), int(rng.choice([0, 0, n])), int(rng.integers(0, 2))))
+        models.append({"modelID": f"m{m}", "namespace": "ns", "replicaMetrics": rm, "config": CFG, "variantStates": _states(st)})
+    batch = an.analyze_batch(models)
+    for m, (a, t) in zip(models, batch):
+        a1 = an.analyze_model_saturation(m["modelID"], "ns", m["replicaMetrics"], CFG)
+        t1 = an.calculate_saturation_targets(a1, m["variantStates"])
+        a1.pop("_src")
+        assert a == a1 and t == t1
+    d, _, _ = an._pack([(m["replicaMetrics"], m["config"], m["variantStates"]) for m in models])
+    want = oracle.saturation_v1(d)
+    flat = [t[v] for m, (a, t) in zip(models, batch) for v in sorted(t)]
+    assert flat == [int(x) for x in want["var_target"] if x >= 0]
+
+
+def _dec(name, acc, cur, tgt, gpr=2, spare=0.1, cost=10.0):
+    return {"VariantName": name, "AcceleratorName": acc, "CurrentReplicas": cur, "TargetReplicas": tgt,
+            "GPUsPerReplica": gpr, "SpareCapacity": spare, "Cost": cost, "Action": "scale-up"}
+
+
+@pytest.mark.gpu
+def test_limiter_reference_cases(pkg, engine):
+    """default_limiter_test.go:152-335 and greedy_saturation_algorithm_test.go:54-270 through `Limiter.limit`."""
+    lim = pkg.pipeline.Limiter(engine, "gpu-limiter", {"A100": 12})
+    ds = [_dec("a", "A100", 1, 2, spare=.3), _dec("b", "A100", 1, 2, spare=.05), _dec("c", "A100", 1, 2, spare=.5)]
+    lim.limit(ds)                                             # 6 GPUs in use, 6 free: everyone gets its replica
+    assert [d["GPUsAllocated"] for d in ds] == [2, 2, 2] and not any(d["WasLimited"] for d in ds)
+    assert ds[0]["DecisionSteps"][-1]["Reason"] == "allocated 2 GPUs for +1 replicas" and "LimitedBy" not in ds[0]
+    lim = pkg.pipeline.Limiter(engine, "gpu-limiter", lambda: {"A100": 10})
+    ds = [_dec("a", "A100", 1, 2, spare=.3), _dec("b", "A100", 1, 2, spare=.05), _dec("c", "A100", 1, 2, spare=.5)]
+    lim.limit(ds)                                             # 4 free: most saturated first (.05, .3), .5 is limited
+    assert [d["TargetReplicas"] for d in ds] == [2, 2, 1] and [d["WasLimited"] for d in ds] == [False, False, True]
+    assert ds[2]["LimitedBy"] == "gpu-limiter" and ds[2]["DecisionSteps"][-1]["WasConstrained"]
+    assert ds[2]["DecisionSteps"][-1]["Reason"] == "no scale-up (target=1, current=1)"
+    lim = pkg.pipeline.Limiter(engine, "gpu-limiter", {"A100": 5})
+    ds = [_dec("a", "A100", 1, 3, spare=.1, cost=5.0)]
+    lim.limit(ds)                                             # 3 free, 2 per replica: one replica
+    assert ds[0]["TargetReplicas"] == 2 and ds[0]["GPUsAllocated"] == 2 and ds[0]["WasLimited"]
+    assert ds[0]["DecisionSteps"][-1]["Reason"] == "limited: allocated 2 GPUs for +1 replicas"
+    lim = pkg.pipeline.Limiter(engine, "gpu-limiter", {"A100": 12, "H100": 0})   # 10 in use, 2 free
+    ds = [_dec("exp", "A100", 1, 2, spare=.2, cost=20.0), _dec("cheap", "A100", 1, 2, spare=.2, cost=5.0),
+          _dec("h", "H100", 0, 2), _dec("nopool", "L40", 1, 2), _dec("noacc", "", 1, 2), _dec("down", "A100", 3, 1)]
+    lim.limit(ds)
+    assert [d["TargetReplicas"] for d in ds[:2]] == [1, 2]    # equal spare: the cheaper variant first
+    assert ds[2]["TargetReplicas"] == 0 and ds[3]["TargetReplicas"] == 1 and ds[4]["TargetReplicas"] == 1
+    assert ds[5]["TargetReplicas"] == 1 and not ds[5]["WasLimited"]   # scale-down passes through
+    pkg.pipeline.Limiter(engine, "gpu-limiter", {"A100": 1}).limit([])   # empty: no inventory refresh, no launch

@@ -373,6 +373,9 @@ func (a *SaturationAnalyzer) run(modelID, ns string, rm []interfaces.ReplicaMetr
 	an := &interfaces.ModelSaturationAnalysis{ModelID: modelID, Namespace: ns, TotalReplicas: int(mTot[0]),
 		NonSaturatedCount: int(mNon[0]), AvgSpareKvCapacity: mKv[0], AvgSpareQueueLength: mQ[0],
 		ShouldScaleUp: flags[0]&C.WVA_SAT_SCALE_UP != 0, ScaleDownSafe: flags[0]&C.WVA_SAT_SCALE_DOWN_SAFE != 0}
+	if an.ShouldScaleUp {
+		an.ScaleUpReason = scaleUpReason(mKv[0], mQ[0], cfg)
+	}
 	targets := map[string]int{}
 	for i, v := range b.variants {
 		if ms := b.metrics[v]; len(ms) > 0 {
@@ -392,6 +395,20 @@ func (a *SaturationAnalyzer) run(modelID, ns string, rm []interfaces.ReplicaMetr
 	}
 	analysisInputs[an] = analysisSrc{rm: rm, cfg: cfg}
 	return an, targets, nil
+}
+
+// scaleUpReason formats the reason exactly as analyzer.go:199-225; the decision itself comes from the device.
+func scaleUpReason(kv, q float64, cfg interfaces.SaturationScalingConfig) string {
+	kvT, qT := kv < cfg.KvSpareTrigger, q < cfg.QueueSpareTrigger
+	switch {
+	case kvT && qT:
+		return fmt.Sprintf("both KV spare (%.3f < %.3f) and queue spare (%.1f < %.1f)", kv, cfg.KvSpareTrigger, q, cfg.QueueSpareTrigger)
+	case kvT:
+		return fmt.Sprintf("KV spare Saturation low (%.3f < %.3f)", kv, cfg.KvSpareTrigger)
+	case qT:
+		return fmt.Sprintf("queue spare Saturation low (%.1f < %.1f)", q, cfg.QueueSpareTrigger)
+	}
+	return ""
 }
 
 func ptrOrNil[T any](s []T) unsafe.Pointer {

@@ -275,7 +275,8 @@ template <int THREADS, bool SMEM>
 static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned long long n_pairs, int nmax, float* gtab,
                                 int* ovf_list) {
   // lane_sizer_mode 1 = flattened state machine (sizer_kernel.cuh); 2 = lock-step rounds; 3 = lock-step with two
-  // chains per lane; 4 = lock-step, every pair split into a TTFT item and an ITL item (mid-size systems)
+  // chains per lane; 4 = lock-step, every pair split into a TTFT item and an ITL item (mid-size systems); 5 = split
+  // items whose second chain evaluates the predicted next bisection point (wva_core.cuh spec2_*)
   cudaError_t e;
   if (ctx->lane_sizer_mode == 1) {
     auto k = sizer_kernel<THREADS, SMEM>;
@@ -284,7 +285,7 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
     k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list);
   } else {
     SplitWs sw = {nullptr, nullptr, nullptr};
-    const bool split = ctx->lane_sizer_mode == 4;
+    const bool split = ctx->lane_sizer_mode == 4 || ctx->lane_sizer_mode == 5;
     if (split) {
       size_t need = (size_t)n_pairs * 20 + 256;
       e = ctx->split_ws.reserve(need);
@@ -295,7 +296,8 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
       e = cudaMemsetAsync(sw.cnt, 0, (size_t)n_pairs * 4, ctx->stream);
       if (e != cudaSuccess) return e;
     }
-    auto k = split ? sizer_lane_kernel<THREADS, SMEM, false, true>
+    auto k = (ctx->lane_sizer_mode == 5) ? sizer_lane_kernel<THREADS, SMEM, true, true>
+           : split ? sizer_lane_kernel<THREADS, SMEM, false, true>
            : (ctx->lane_sizer_mode == 3) ? sizer_lane_kernel<THREADS, SMEM, true, false>
                                          : sizer_lane_kernel<THREADS, SMEM, false, false>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -322,7 +324,7 @@ int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
   if (!ctx) return WVA_ERR_ARG;
   if (option == WVA_OPT_FORCE_LANE_SIZER) {
     ctx->force_lane_sizer = value != 0;
-    if (value >= 1 && value <= 4) ctx->lane_sizer_mode = value;
+    if (value >= 1 && value <= 5) ctx->lane_sizer_mode = value;
     return WVA_OK;
   }
   return WVA_ERR_ARG;
@@ -371,7 +373,7 @@ int32_t wva_calculate(wva_ctx* ctx) {
     // mid-size systems (measured: up to ~200 pairs per SM) still leave lanes idle: split every pair into a
     // TTFT item and an ITL item, which halves the chain of dependent solves per work item
     if (!ctx->force_lane_sizer) ctx->lane_sizer_mode = (n_pairs <= (unsigned long long)ctx->sm_count * 200) ? 4 : 2;
-    const unsigned long long n_items = (ctx->lane_sizer_mode == 4) ? 2 * n_pairs : n_pairs;
+    const unsigned long long n_items = (ctx->lane_sizer_mode >= 4) ? 2 * n_pairs : n_pairs;
     const unsigned long long lanes_needed = (n_items + ctx->sm_count - 1) / ctx->sm_count;
     if (best_per_sm >= 1 && lanes_needed <= 256 && lanes_needed < (unsigned long long)best_threads * best_per_sm) {
       int t = 64;

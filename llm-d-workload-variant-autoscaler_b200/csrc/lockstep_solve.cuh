@@ -38,6 +38,9 @@ struct LaneTable {   // one float32 column per lane ([n][thread], bank = lane); 
   __device__ __forceinline__ double mu_at(int n) const { return (double)t[(size_t)n * stride]; }
 };
 
+// high word of v * 2^-54 for a normal v >= 2^-900: the exponent field moves, nothing rounds
+__device__ __forceinline__ int hi_scale_m54(double v) { return d_hi(v) - (54 << 20); }
+
 struct P1 { double p, sum; int mn, mx; };
 struct P2 { double p, L, sumP, pi; int mn, mx; };
 
@@ -81,7 +84,7 @@ __device__ __forceinline__ void p2_step(P2& s, double lam, double mu, double r, 
 template <int NC, class Tab>
 __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab, const float* lambda,
                                               const bool* active, SolveStats* st, int& states, bool& bad) {
-  constexpr int CH = 8 / NC;                           // states per unrolled chunk
+  constexpr int CH = 16 / NC;                          // states per unrolled chunk (per chain)
   const unsigned full = 0xffffffffu;
   const int K = m.K, N = m.N, NH = N - 1;
   const double mu_l = m.mu_last, r_l = m.r_last;
@@ -125,13 +128,15 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
     bool any = false;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-      if (!done[c]) {
-        states += cnt;
-        const bool eok = (n >= m.mono) && (d_bits(lamg[c]) <= d_bits(mu0));
-        if (a[c].mn < WVA_HI_LO || a[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; }
-        else if (eok && d_hi(a[c].p) < d_hi(d_mul(a[c].sum, 0x1p-54))) done[c] = true;
-      }
-      any = any || !done[c];
+      // branch-free chunk epilogue (the lanes of a warp are in different situations: a branchy one runs twice)
+      const bool live = !done[c];
+      states += live ? cnt : 0;
+      const bool eok = (n >= m.mono) & (d_bits(lamg[c]) <= d_bits(mu0));
+      const bool oob = (a[c].mn < WVA_HI_LO) | (a[c].mx >= WVA_HI_HI);
+      const bool tiny = eok & (d_hi(a[c].p) < hi_scale_m54(a[c].sum));
+      bad = bad | (live & oob);
+      done[c] = done[c] | oob | tiny;
+      any = any | !done[c];
     }
     n += cnt;
     all_done = !__any_sync(full, any);
@@ -155,12 +160,13 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
     bool any = false;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-      if (!done[c]) {
-        states += cnt;
-        if (a[c].mn < WVA_HI_LO || a[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; }
-        else if (tail_ok[c] && d_hi(a[c].p) < d_hi(d_mul(a[c].sum, 0x1p-54))) done[c] = true;
-      }
-      any = any || !done[c];
+      const bool live = !done[c];
+      states += live ? cnt : 0;
+      const bool oob = (a[c].mn < WVA_HI_LO) | (a[c].mx >= WVA_HI_HI);
+      const bool tiny = tail_ok[c] & (d_hi(a[c].p) < hi_scale_m54(a[c].sum));
+      bad = bad | (live & oob);
+      done[c] = done[c] | oob | tiny;
+      any = any | !done[c];
     }
     n += cnt;
     all_done = !__any_sync(full, any);
@@ -210,16 +216,15 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
     bool any = false;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-      if (!done[c]) {
-        states += cnt;
-        const bool eok = (n >= m.mono) && (d_bits(lamg[c]) <= d_bits(mu0));
-        if (b[c].mn < WVA_HI_LO || b[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; }
-        else if (eok) {
-          int thr = min(d_hi(d_mul(b[c].L, cK)), d_hi(d_mul(b[c].sumP, 0x1p-54)));
-          if (d_hi(b[c].pi) < thr) done[c] = true;
-        }
-      }
-      any = any || !done[c];
+      const bool live = !done[c];
+      states += live ? cnt : 0;
+      const bool eok = (n >= m.mono) & (d_bits(lamg[c]) <= d_bits(mu0));
+      const bool oob = (b[c].mn < WVA_HI_LO) | (b[c].mx >= WVA_HI_HI);
+      const int thr = min(d_hi(d_mul(b[c].L, cK)), hi_scale_m54(b[c].sumP));
+      const bool tiny = eok & (d_hi(b[c].pi) < thr);
+      bad = bad | (live & oob);
+      done[c] = done[c] | oob | tiny;
+      any = any | !done[c];
     }
     n += cnt;
     all_done = !__any_sync(full, any);
@@ -236,13 +241,17 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
     for (int c = 0; c < NC; c++) {
       b[c].mn = 0x7fffffff; b[c].mx = 0;
       p2_step_c(b[c], lam[c], lamr_l[c], mu_l, r_l, sum[c], rsum[c], di);
-      if (!done[c]) { states += 1; if (b[c].mn < WVA_HI_LO || b[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; } }
-      Lserv[c] = d_add(b[c].L, d_mul(d_sub(1.0, b[c].sumP), (double)N));
-      if (!done[c] && tail_ok[c]) {
-        int thr = min(d_hi(d_mul(b[c].L, cK)), d_hi(d_mul(b[c].sumP, 0x1p-54)));
-        if (d_hi(b[c].pi) < thr) done[c] = true;
+      {
+        const bool live = !done[c];
+        states += live ? 1 : 0;
+        const bool oob = (b[c].mn < WVA_HI_LO) | (b[c].mx >= WVA_HI_HI);
+        Lserv[c] = d_add(b[c].L, d_mul(d_sub(1.0, b[c].sumP), (double)N));
+        const int thr = min(d_hi(d_mul(b[c].L, cK)), hi_scale_m54(b[c].sumP));
+        const bool tiny = tail_ok[c] & (d_hi(b[c].pi) < thr);
+        bad = bad | (live & oob);
+        done[c] = done[c] | oob | tiny;
       }
-      any = any || !done[c];
+      any = any | !done[c];
     }
     n = N;
     all_done = !__any_sync(full, any);
@@ -269,16 +278,16 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
     bool any = false;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-      if (!done[c]) {
-        states += cnt;
-        if (b[c].mn < WVA_HI_LO || b[c].mx >= WVA_HI_HI) { bad = true; done[c] = true; }
-        else if (n == K) { reached_K[c] = true; done[c] = true; }
-        else if (tail_ok[c]) {
-          int thr = min(d_hi(d_mul(b[c].L, cK)), d_hi(d_mul(b[c].sumP, 0x1p-54)));
-          if (d_hi(b[c].pi) < thr) done[c] = true;
-        }
-      }
-      any = any || !done[c];
+      const bool live = !done[c];
+      states += live ? cnt : 0;
+      const bool oob = (b[c].mn < WVA_HI_LO) | (b[c].mx >= WVA_HI_HI);
+      const bool at_K = n == K;
+      const int thr = min(d_hi(d_mul(b[c].L, cK)), hi_scale_m54(b[c].sumP));
+      const bool tiny = tail_ok[c] & (d_hi(b[c].pi) < thr);
+      bad = bad | (live & oob);
+      reached_K[c] = reached_K[c] | (live & !oob & at_K);
+      done[c] = done[c] | oob | at_K | tiny;
+      any = any | !done[c];
     }
     all_done = !__any_sync(full, any);
   }

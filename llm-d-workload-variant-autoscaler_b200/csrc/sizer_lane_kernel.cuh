@@ -24,6 +24,7 @@ struct SplitWs {
 };
 
 // A split item finished its search: publish; the first finisher retires, the second merges and goes on.
+template <bool DUAL>
 __device__ __forceinline__ bool split_publish(SizerLane& z, const SysView& s, const CandView& out, const SplitWs& sw) {
   const size_t pair = (size_t)z.srv * s.n_acc + z.acc;
   const size_t me = pair * 2 + (size_t)z.split;
@@ -38,7 +39,7 @@ __device__ __forceinline__ bool split_publish(SizerLane& z, const SysView& s, co
   z.merged = true;
   if (z.failed || pr < 0.0f) { lane_fail(z, s, out); return false; }
   if (z.split == 0) z.sI.result = pr; else z.sT.result = pr;
-  return sizer_after_search(z, s, out);                // -> the two Analyze solves
+  return DUAL ? spec2_after_search(z, s, out) : sizer_after_search(z, s, out);   // -> the two Analyze solves
 }
 
 template <int THREADS, bool SMEM_TABLE, bool DUAL, bool SPLIT>
@@ -92,8 +93,8 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
     __syncwarp();
     if (need_table) {
       model_finish(z.m, tab, stride);
-      live = DUAL ? dual_begin(z, s, out) : sizer_begin(z, s, out);
-      if (SPLIT) { if (live && z.stage == SZ_PUBLISH) live = split_publish(z, s, out, sw); }
+      live = DUAL ? (SPLIT ? spec2_begin(z, s, out) : dual_begin(z, s, out)) : sizer_begin(z, s, out);
+      if (SPLIT) { if (live && z.stage == SZ_PUBLISH) live = split_publish<DUAL>(z, s, out, sw); }
       if (!live) my_solves += z.solves;
     }
     const unsigned live_mask = __ballot_sync(full, live);
@@ -133,7 +134,8 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
           lane_fail(z, s, out);
           live = false;
         } else {
-          live = dual_on_solve(z, s, out, st2, sv);
+          live = SPLIT ? spec2_on_solve(z, s, out, st2, sv) : dual_on_solve(z, s, out, st2, sv);
+          if (SPLIT) { if (live && z.stage == SZ_PUBLISH) live = split_publish<true>(z, s, out, sw); }
         }
         if (!live) { my_solves += z.solves; my_states += z.states; }
       }
@@ -154,7 +156,7 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
           live = false;
         } else {
           live = sizer_on_solve(z, s, out, st);
-          if (SPLIT) { if (live && z.stage == SZ_PUBLISH) live = split_publish(z, s, out, sw); }
+          if (SPLIT) { if (live && z.stage == SZ_PUBLISH) live = split_publish<false>(z, s, out, sw); }
         }
         if (!live) { my_solves += z.solves; my_states += z.states; }
       }

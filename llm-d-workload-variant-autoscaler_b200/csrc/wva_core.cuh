@@ -434,6 +434,7 @@ enum { SZ_LO = 0, SZ_HI = 1, SZ_SEARCH = 2, SZ_FINAL1 = 3, SZ_FINAL2 = 4, SZ_PUB
 
 struct Search {   // one BinarySearch (utils.go:26-70)
   float lo, hi, target, x, result, y_lo;
+  float y_hi;       // speculative split driver: f(hi) (y_lo = f(lo)), the evaluations at the current bounds
   int iter;
   bool active;      // still bisecting
   bool enabled;     // target > 0
@@ -714,6 +715,107 @@ WVA_HD bool dual_on_solve(SizerLane& z, const SysView& s, const CandView& out, c
   a.value = transition_penalty(s.srv_cur_acc[z.srv], s.srv_cur_replicas[z.srv], s.srv_cur_cost[z.srv], a, z.acc);
   store_candidate(out, (size_t)z.srv * s.n_acc + z.acc, a, z.solves);
   return false;
+}
+
+// ---- speculative split driver: ONE search per lane, two chains per round -------------------------------
+// Mid-size systems have fewer (pair, search) items than the GPU has lanes x latency-hiding depth, so the lane's
+// second chain is spent on the bisection step AFTER the current one: chain 0 evaluates the midpoint x, chain 1
+// the midpoint of the half the search is predicted to keep (the prediction compares the target with the value
+// interpolated between the evaluations at the two bounds).  The midpoints are pure float32 arithmetic on
+// (lo, hi), so chain 1's point is exactly what BinarySearch would evaluate next if the prediction holds; the
+// walk consumes y0 as the reference does and consumes y1 only if the next x is bit-identical to the point
+// chain 1 evaluated.  A wrong guess wastes one chain, never changes a decision.  Results are bit-identical to
+// the sequential search; a correct guess halves the rounds on the critical path (E7 with a 2-leaf tree).
+WVA_HD bool spec2_after_search(SizerLane& z, const SysView& s, const CandView& out) {
+  if (z.split >= 0 && !z.merged) { z.stage = SZ_PUBLISH; return true; }   // publish; the second finisher goes on
+  if (!dual_after_search(z, s, out)) return false;
+  z.stage = SZ_FINAL1;
+  return true;
+}
+
+// the half BinarySearch keeps if f(x) equals the interpolated value: true = [lo, x]
+WVA_HD bool spec2_predict_left(const Search& q) {
+  // harmonic interpolation (exact for the hyperbolic growth of waiting time towards saturation) when both
+  // evaluations are positive, arithmetic otherwise; any rule is correct, a better one only saves rounds
+  float y = (q.y_lo > 0.0f && q.y_hi > 0.0f) ? f_div(f_mul(2.0f, f_mul(q.y_lo, q.y_hi)), f_add(q.y_lo, q.y_hi))
+                                             : f_mul(0.5f, f_add(q.y_lo, q.y_hi));
+  return (q.increasing && q.target < y) || (!q.increasing && q.target > y);
+}
+
+WVA_HD bool spec2_schedule(SizerLane& z, const SysView& s, const CandView& out) {
+  Search& q = z.split == 1 ? z.sI : z.sT;
+  if (!q.active) return spec2_after_search(z, s, out);
+  z.stage = SZ_SEARCH;
+  z.x2[0] = q.x; z.act2[0] = true;
+  z.x2[1] = spec2_predict_left(q) ? f_mul(0.5f, f_add(q.lo, q.x)) : f_mul(0.5f, f_add(q.x, q.hi));
+  z.act2[1] = q.iter + 1 < WVA_MAX_ITER && z.x2[1] != q.x;
+  z.solves += z.act2[1] ? 2 : 1;
+  return true;
+}
+
+WVA_HD bool spec2_begin(SizerLane& z, const SysView& s, const CandView& out) {
+  z.sT.enabled = z.sT.target > 0.0f && z.split != 1;
+  z.sI.enabled = z.sI.target > 0.0f && z.split != 0;
+  z.sT.active = z.sT.enabled; z.sI.active = z.sI.enabled;
+  z.sT.result = z.m.lambda_max; z.sI.result = z.m.lambda_max;
+  z.sT.iter = z.sI.iter = 0;
+  if (z.sT.enabled || z.sI.enabled) {
+    if (z.m.lambda_min > z.m.lambda_max) return search_fail(z, s, out);   // utils.go:29-31
+    z.stage = SZ_LO;
+    z.x2[0] = z.m.lambda_min; z.x2[1] = z.m.lambda_max; z.act2[0] = z.act2[1] = true;
+    z.solves += 2;
+    return true;
+  }
+  return spec2_after_search(z, s, out);
+}
+
+// one consumed evaluation; keeps (y_lo, y_hi) = f at the bounds
+WVA_HD void spec2_consume(Search& q, float x, float y) {
+  const bool left = (q.increasing && q.target < y) || (!q.increasing && q.target > y);
+  search_consume(q, x, y);
+  if (q.active) { if (left) q.y_hi = y; else q.y_lo = y; }
+}
+
+// st[c] = statistics of the solve at z.x2[c] (valid where z.act2[c])
+WVA_HD bool spec2_on_solve(SizerLane& z, const SysView& s, const CandView& out, const SolveStats* st, int n_states) {
+  z.states += n_states;
+  const PairModel& m = z.m;
+  if (z.stage == SZ_LO || z.stage == SZ_SEARCH) {
+    Search& q = z.split == 1 ? z.sI : z.sT;
+    float y[2];
+    for (int c = 0; c < 2; c++) {
+      float pf = prefill_time(m, st[c].avgNumInServers);
+      float dec = f_div(f_sub(st[c].avgServTime, pf), m.out_tok);
+      y[c] = z.split == 1 ? dec : f_add(f_add(st[c].avgWaitTime, pf), dec);
+    }
+    if (z.stage == SZ_LO) {   // both end points (utils.go:33-57)
+      if (q.active) {
+        if (within_tolerance(y[0], q.target, WVA_BS_EPSILON)) { q.result = m.lambda_min; q.active = false; }
+        else if (within_tolerance(y[1], q.target, WVA_BS_EPSILON)) { q.result = m.lambda_max; q.active = false; }
+        else {
+          q.increasing = y[0] < y[1];
+          if ((q.increasing && q.target < y[0]) || (!q.increasing && q.target > y[0])) return search_fail(z, s, out);
+          if ((q.increasing && q.target > y[1]) || (!q.increasing && q.target < y[1])) { q.result = m.lambda_max; q.active = false; }
+          else {
+            q.lo = m.lambda_min; q.hi = m.lambda_max; q.iter = 0; q.y_lo = y[0]; q.y_hi = y[1];
+            q.x = f_mul(0.5f, f_add(q.lo, q.hi));
+          }
+        }
+      }
+      return spec2_schedule(z, s, out);
+    }
+    spec2_consume(q, z.x2[0], y[0]);
+    if (q.active && z.act2[1] && q.x == z.x2[1]) spec2_consume(q, z.x2[1], y[1]);
+    return spec2_schedule(z, s, out);
+  }
+  if (z.stage == SZ_FINAL1) {
+    z.stage = D2_FINAL1;
+    if (!dual_on_solve(z, s, out, st, 0)) return false;
+    z.stage = SZ_FINAL2;
+    return true;
+  }
+  z.stage = D2_FINAL2;
+  return dual_on_solve(z, s, out, st, 0);
 }
 
 // ---- speculative bisection (used by the warp-per-pair sizer; see sizer_warp_kernel.cuh) ----

@@ -166,6 +166,70 @@ extern "C" int emul_calculate_dual(const wva_system* sys, wva_candidates* out) {
   return 0;
 }
 
+// System.Calculate through the SPECULATIVE SPLIT driver (spec2_*): every pair is two items (TTFT search, ITL
+// search), each advancing with two chains per round; the item that finishes second merges and runs the two
+// Analyze solves — the host replay of sizer_lane_kernel<.., DUAL = true, SPLIT = true> incl. split_publish.
+// stats: [0] search rounds, [1] bisection steps consumed, [2] rounds with a speculative chain, [3] guesses used
+extern "C" int emul_calculate_spec2(const wva_system* sys, wva_candidates* out, int64_t* stats) {
+  SysView s = make_view(sys);
+  CandView o;
+  o.state = out->state; o.num_replicas = out->num_replicas; o.batch_size = out->batch_size; o.cost = out->cost;
+  o.value = out->value; o.itl = out->itl; o.ttft = out->ttft; o.rho = out->rho; o.max_arrv_rate = out->max_arrv_rate;
+  o.n_solves = out->n_solves;
+  std::vector<float> tab;
+  for (int i = 0; i < 4; i++) stats[i] = 0;
+  for (int srv = 0; srv < s.n_servers; srv++)
+    for (int acc = 0; acc < s.n_acc; acc++) {
+      SizerLane item[2];
+      bool dead = false;   // a lane failed the pair outright
+      int lim = 0, n_pub = 0;
+      if (sizer_setup(item[0], s, o, srv, acc, 1 << 20, &lim, true) == SETUP_DONE) continue;
+      sizer_setup(item[1], s, o, srv, acc, 1 << 20, &lim, false);
+      tab.assign((size_t)item[0].m.N, 0.0f);
+      model_fill_table(item[0].m, tab.data(), 1, 0, 1);
+      for (int k = 0; k < 2 && !dead; k++) {
+        SizerLane& z = item[k];
+        z.split = k;
+        model_finish(z.m, tab.data(), 1);
+        bool live = spec2_begin(z, s, o);
+        while (live && z.stage != SZ_PUBLISH) {
+          SolveStats st2[2] = {};
+          bool ovf = false;
+          const bool searching = z.stage == SZ_SEARCH;
+          Search& q = k ? z.sI : z.sT;
+          const int it0 = q.iter; const bool spec = z.act2[1];
+          for (int c = 0; c < 2; c++)
+            if (z.act2[c]) st2[c] = host_solve(z.m, z.x2[c], &ovf);
+          live = spec2_on_solve(z, s, o, st2, 0);
+          if (searching) {
+            const int used = q.iter - it0;
+            stats[0]++; if (spec) stats[2]++;
+            stats[1] += used > 0 ? used : 1;
+            if (spec && used >= 2) stats[3]++;
+          }
+        }
+        if (live) n_pub++; else dead = true;
+      }
+      if (dead || n_pub < 2) continue;
+      // split_publish: the second finisher (here: item 1) merges
+      SizerLane& z = item[1];
+      SizerLane& p = item[0];
+      z.solves += p.solves;
+      z.merged = true;
+      if (z.failed || p.failed) { lane_fail(z, s, o); continue; }
+      z.sT.result = p.sT.result;
+      bool live = spec2_after_search(z, s, o);
+      while (live) {
+        SolveStats st2[2] = {};
+        bool ovf = false;
+        for (int c = 0; c < 2; c++)
+          if (z.act2[c]) st2[c] = host_solve(z.m, z.x2[c], &ovf);
+        live = spec2_on_solve(z, s, o, st2, 0);
+      }
+    }
+  return 0;
+}
+
 extern "C" {
 
 // System.Calculate through the lane state machine, one lane at a time.

@@ -45,7 +45,7 @@ def test_calculate_matches_oracle(pkg, engine, oracle, S, A, N, stream):
 
 @pytest.mark.parametrize("S,A,N,stream", [(10, 4, 32, 1), (64, 8, 16, 7), (48, 16, 128, 2), (16, 8, 256, 3),
                                           (33, 5, 1, 11)])
-@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
 def test_calculate_lane_kernel_matches_oracle(pkg, engine, oracle, S, A, N, stream, mode):
     """Small systems default to the warp-per-pair sizer; force the lane-per-pair kernels (mode 3 = lock-step
     rounds with two chains per lane, what large systems use; 2 = one chain; 1 = flattened state machine) and hold them to the same bar."""

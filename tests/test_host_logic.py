@@ -51,6 +51,17 @@ def emul(pkg):
         lib.emul_calculate_dual(C.byref(st), C.byref(cst))
         return cand
 
+    lib.emul_calculate_spec2.argtypes = [C.POINTER(abi.System), C.POINTER(abi.Candidates), C.POINTER(C.c_int64)]
+
+    def calculate_spec2(sysd):
+        st, keep = abi.make_system(sysd)
+        cst, cand = abi.alloc_candidates(st.n_servers, st.n_acc)
+        stats = (C.c_int64 * 4)()
+        lib.emul_calculate_spec2(C.byref(st), C.byref(cst), stats)
+        cand["_stats"] = list(stats)
+        return cand
+
+    lib.calculate_spec2 = calculate_spec2
     lib.calculate = calculate
     lib.calculate_dual = calculate_dual
     lib.calculate_spec = calculate_spec
@@ -107,6 +118,24 @@ def test_dual_chain_driver_matches_oracle(pkg, oracle, emul, S, A, N, stream):
         assert np.array_equal(e[k], o[k]), k
     for k in F32_FIELDS:
         assert _bit_equal(e[k], o[k]), k
+
+
+@pytest.mark.parametrize("S,A,N,stream", [(10, 4, 32, 1), (40, 8, 16, 7), (10, 6, 128, 2), (20, 3, 1, 11), (16, 3, 5, 12)])
+def test_speculative_split_driver_matches_oracle(pkg, oracle, emul, S, A, N, stream):
+    """One search per item, the second chain on the predicted next bisection point (spec2_*): a wrong guess must
+    never change a decision, a right one must be consumed exactly as BinarySearch would have evaluated it."""
+    sysd = pkg.synth.queue_system(S, A, N, stream=stream)
+    sysd["srv_slo_itl"][::5] = 0.0       # TTFT-only servers
+    sysd["srv_slo_ttft"][1::5] = 0.0     # ITL-only servers
+    e = emul.calculate_spec2(sysd)
+    o = oracle.calculate(sysd)
+    for k in ("state", "num_replicas", "batch_size"):
+        assert np.array_equal(e[k], o[k]), k
+    for k in F32_FIELDS:
+        assert _bit_equal(e[k], o[k]), k
+    rounds, steps, spec_rounds, hits = e["_stats"]
+    if N >= 16:
+        assert steps > 1.3 * rounds, (rounds, steps, spec_rounds, hits)   # the guesses do pay
 
 
 def test_overflow_rescale_path_matches_oracle(pkg, oracle, emul):

@@ -8,6 +8,8 @@ S = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 d = pkg.synth.queue_system(S, 16, 128, n_classes=3, stream=2, R=128)
 with pkg.Engine(0) as e:
     e.load_system(d)
+    if os.environ.get("WVA_MODE"):
+        e.set_option(1, int(os.environ["WVA_MODE"]))
     for _ in range(reps):
         if what in ("all", "sizer"):
             e.calculate(); print("calculate", e.timing())

@@ -77,17 +77,108 @@ __device__ __forceinline__ void p2_step(P2& s, double lam, double mu, double r, 
   s.sumP = d_add(s.sumP, s.pi);
 }
 
+// ---- software-pipelined chunks --------------------------------------------------------------------------
+// ptxas keeps the FP64 ops of an unrolled chunk in source order (measured: ncu source page, r1), and a warp issues
+// in order, so a chunk written state after state stalls ~8 cycles on every dependent op: the 5-deep normalising
+// division and the two accumulations of state j sit between the recurrence steps of states j and j+1 although
+// they are off the recurrence.  Here the ops are EMITTED in pipeline order instead: stage s of state j at slot
+// 3*j + s (the recurrence p -> p' is 3 ops deep), so every slot holds ops of different states (and chains) that
+// are independent of each other and only consume results of earlier slots.  Same ops, same operands, same
+// rounding — only the order in the instruction stream changes.
+//   stage 0: x = p*lam, q0 = p*lamr (+ exponent window)   1: rem = fma(-q0, mu, x)   2: p' = fma(rem, r, q0)
+//   pass 1   3: sum += p'
+//   pass 2   3..7: pi = RN(p'/sum) (two-step Markstein)   8: t = i*pi, sumP += pi   9: L += t
+template <int NC, int CH, bool HEAD>
+__device__ __forceinline__ void p1_chunk(P1 (&a)[NC], const double (&lam)[NC], const double (&lamr_c)[NC],
+                                         const double (&mu)[HEAD ? CH : 1], const double (&r)[HEAD ? CH : 1]) {
+  double x[NC][CH], q0[NC][CH], rem[NC][CH], pn[NC][CH + 1], lamr[NC][HEAD ? CH : 1];
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    pn[c][0] = a[c].p;
+#pragma unroll
+    for (int j = 0; j < (HEAD ? CH : 1); j++) lamr[c][j] = HEAD ? d_mul(lam[c], r[j]) : lamr_c[c];
+  }
+#pragma unroll
+  for (int slot = 0; slot < 3 * CH + 1; slot++) {
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+      const int st = slot - 3 * j;
+      const int k = HEAD ? j : 0;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        if (st == 0) {
+          x[c][j] = d_mul(pn[c][j], lam[c]);
+          q0[c][j] = d_mul(pn[c][j], lamr[c][k]);
+          const int h = d_hi(x[c][j]);
+          a[c].mn = min(a[c].mn, h); a[c].mx = max(a[c].mx, h);
+        }
+        if (st == 1) rem[c][j] = d_fma(-q0[c][j], mu[k], x[c][j]);
+        if (st == 2) pn[c][j + 1] = d_fma(rem[c][j], r[k], q0[c][j]);
+        if (st == 3) a[c].sum = d_add(a[c].sum, pn[c][j + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) a[c].p = pn[c][CH];
+}
+
+template <int NC, int CH, bool HEAD>
+__device__ __forceinline__ void p2_chunk(P2 (&b)[NC], const double (&lam)[NC], const double (&lamr_c)[NC],
+                                         const double (&mu)[HEAD ? CH : 1], const double (&r)[HEAD ? CH : 1],
+                                         const double (&sum)[NC], const double (&rsum)[NC], double& di) {
+  double x[NC][CH], q0[NC][CH], rem[NC][CH], pn[NC][CH + 1], q[NC][CH], r1[NC][CH], q1[NC][CH], r2[NC][CH], pi[NC][CH],
+      t[NC][CH], dj[CH], lamr[NC][HEAD ? CH : 1];
+#pragma unroll
+  for (int j = 0; j < CH; j++) dj[j] = d_add(di, (double)(j + 1));   // float64(i): exact integers
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    pn[c][0] = b[c].p;
+#pragma unroll
+    for (int j = 0; j < (HEAD ? CH : 1); j++) lamr[c][j] = HEAD ? d_mul(lam[c], r[j]) : lamr_c[c];
+  }
+#pragma unroll
+  for (int slot = 0; slot < 3 * CH + 7; slot++) {
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+      const int st = slot - 3 * j;
+      const int k = HEAD ? j : 0;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        if (st == 0) {
+          x[c][j] = d_mul(pn[c][j], lam[c]);
+          q0[c][j] = d_mul(pn[c][j], lamr[c][k]);
+          const int h = d_hi(x[c][j]);
+          b[c].mn = min(b[c].mn, h); b[c].mx = max(b[c].mx, h);
+        }
+        if (st == 1) rem[c][j] = d_fma(-q0[c][j], mu[k], x[c][j]);
+        if (st == 2) pn[c][j + 1] = d_fma(rem[c][j], r[k], q0[c][j]);
+        if (st == 3) q[c][j] = d_mul(pn[c][j + 1], rsum[c]);                       // div_markstein2, step by step
+        if (st == 4) r1[c][j] = d_fma(-q[c][j], sum[c], pn[c][j + 1]);
+        if (st == 5) q1[c][j] = d_fma(r1[c][j], rsum[c], q[c][j]);
+        if (st == 6) r2[c][j] = d_fma(-q1[c][j], sum[c], pn[c][j + 1]);
+        if (st == 7) pi[c][j] = d_fma(r2[c][j], rsum[c], q1[c][j]);
+        if (st == 8) { t[c][j] = d_mul(dj[j], pi[c][j]); b[c].sumP = d_add(b[c].sumP, pi[c][j]); }
+        if (st == 9) b[c].L = d_add(b[c].L, t[c][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) { b[c].p = pn[c][CH]; b[c].pi = pi[c][CH - 1]; }
+  di = dj[CH - 1];
+}
+
 // Chains c with active[c] solve at lambda[c]; the others ride along (lambda 0).  On return `bad`
 // is set for a lane when one of its solves left the exponent window (caller: redo the pair on the
 // slow path).  __noinline__: callers invoke this from several places; one copy keeps the unrolled
 // loops in the instruction cache.
 template <int NC, class Tab>
-__device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab, const float* lambda,
-                                              const bool* active, SolveStats* st, int& states, bool& bad) {
+__device__ __forceinline__ void lockstep_solve_inl(const PairModel& m, const Tab& tab, const float* lambda,
+                                                   const bool* active, SolveStats* st, int& states, bool& bad) {
   constexpr int CH = 16 / NC;                          // states per unrolled chunk (per chain)
   const unsigned full = 0xffffffffu;
   const int K = m.K, N = m.N, NH = N - 1;
   const double mu_l = m.mu_last, r_l = m.r_last;
+  const double mu_c[1] = {mu_l}, r_c[1] = {r_l};
   double lam[NC], lamg[NC], lamr_l[NC];
   bool tail_ok[NC], done[NC];
 #pragma unroll
@@ -112,12 +203,10 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
 #pragma unroll
     for (int c = 0; c < NC; c++) { a[c].mn = 0x7fffffff; a[c].mx = 0; }
     if (cnt == CH) {
+      double mu[CH], r[CH];
 #pragma unroll
-      for (int j = 0; j < CH; j++) {
-        double mu, r; tab.load(n + j, mu, r);
-#pragma unroll
-        for (int c = 0; c < NC; c++) p1_step(a[c], lam[c], mu, r);
-      }
+      for (int j = 0; j < CH; j++) tab.load(n + j, mu[j], r[j]);
+      p1_chunk<NC, CH, true>(a, lam, lamr_l, mu, r);
     } else {
       for (int j = 0; j < cnt; j++) {
         double mu, r; tab.load(n + j, mu, r);
@@ -146,11 +235,7 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
 #pragma unroll
     for (int c = 0; c < NC; c++) { a[c].mn = 0x7fffffff; a[c].mx = 0; }
     if (cnt == CH) {
-#pragma unroll
-      for (int j = 0; j < CH; j++) {
-#pragma unroll
-        for (int c = 0; c < NC; c++) p1_step_c(a[c], lam[c], lamr_l[c], mu_l, r_l);
-      }
+      p1_chunk<NC, CH, false>(a, lam, lamr_l, mu_c, r_c);
     } else {
       for (int j = 0; j < cnt; j++) {
 #pragma unroll
@@ -198,13 +283,10 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
 #pragma unroll
     for (int c = 0; c < NC; c++) { b[c].mn = 0x7fffffff; b[c].mx = 0; }
     if (cnt == CH) {
+      double mu[CH], r[CH];
 #pragma unroll
-      for (int j = 0; j < CH; j++) {
-        double mu, r; tab.load(n + j, mu, r);
-        di = d_add(di, 1.0);
-#pragma unroll
-        for (int c = 0; c < NC; c++) p2_step(b[c], lam[c], mu, r, sum[c], rsum[c], di);
-      }
+      for (int j = 0; j < CH; j++) tab.load(n + j, mu[j], r[j]);
+      p2_chunk<NC, CH, true>(b, lam, lamr_l, mu, r, sum, rsum, di);
     } else {
       for (int j = 0; j < cnt; j++) {
         double mu, r; tab.load(n + j, mu, r);
@@ -261,12 +343,7 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
 #pragma unroll
     for (int c = 0; c < NC; c++) { b[c].mn = 0x7fffffff; b[c].mx = 0; }
     if (cnt == CH) {
-#pragma unroll
-      for (int j = 0; j < CH; j++) {
-        di = d_add(di, 1.0);
-#pragma unroll
-        for (int c = 0; c < NC; c++) p2_step_c(b[c], lam[c], lamr_l[c], mu_l, r_l, sum[c], rsum[c], di);
-      }
+      p2_chunk<NC, CH, false>(b, lam, lamr_l, mu_c, r_c, sum, rsum, di);
     } else {
       for (int j = 0; j < cnt; j++) {
         di = d_add(di, 1.0);
@@ -303,6 +380,12 @@ __device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab
     float w = f_sub(s.avgRespTime, s.avgServTime);
     s.avgWaitTime = (w < 0.0f) ? 0.0f : w;
   }
+}
+
+template <int NC, class Tab>
+__device__ __noinline__ void lockstep_solve_n(const PairModel& m, const Tab& tab, const float* lambda,
+                                              const bool* active, SolveStats* st, int& states, bool& bad) {
+  lockstep_solve_inl<NC, Tab>(m, tab, lambda, active, st, states, bad);
 }
 
 template <class Tab>

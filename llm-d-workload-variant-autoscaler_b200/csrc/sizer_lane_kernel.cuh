@@ -115,7 +115,7 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
       float xs[2] = {z.x2[0], z.x2[1]};
       bool act[2] = {live && z.act2[0], live && z.act2[1]};
       if (uniform) {
-        lockstep_solve_n<2, LaneTable>(z.m, lt, xs, act, st2, sv, bad);
+        lockstep_solve_inl<2, LaneTable>(z.m, lt, xs, act, st2, sv, bad);   // single call site: inlined, own register budget
       } else if (live) {
         for (int c = 0; c < 2; c++) {
           if (!act[c]) continue;

@@ -174,7 +174,16 @@ int64_t wva_launch_count(const wva_ctx* ctx);
 
 /* options (wva_set_option): tuning / test hooks, never needed for correctness */
 #define WVA_OPT_FORCE_LANE_SIZER 1 /* 0: pick by system size; 1: lane-per-pair, flattened state machine;
-                                      2: lane-per-pair, lock-step rounds (what large systems use) */
+                                      2: lane-per-pair, lock-step rounds (what large systems use); 3: two chains
+                                      per lane (TTFT and ITL searches together); 4: every pair split into a TTFT
+                                      item and an ITL item; 5: split items whose second chain evaluates the
+                                      predicted next bisection point */
+#define WVA_OPT_LENGTH_SORT 2      /* 1: the lane sizer visits the work items in probe-sorted order
+                                      (csrc/sizer_probe.cuh); 0 (default): natural (server, accelerator) order.  Order
+                                      only — results are identical either way */
+#define WVA_OPT_GANG_REFILL 3      /* 1: a warp of the lane sizer takes 32 new items only when all its
+                                      lanes are idle (lanes stay in the same bisection step); 0 (default): lanes refill
+                                      one by one.  Scheduling only */
 int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value);
 
 /* ---- queueing sizing + allocator ---------------------------------------- */

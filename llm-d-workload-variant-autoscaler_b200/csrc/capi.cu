@@ -7,6 +7,7 @@
 #include "sizer_kernel.cuh"
 #include "sizer_warp_kernel.cuh"
 #include "sizer_lane_kernel.cuh"
+#include "sizer_probe.cuh"
 #include "solve_kernels.cuh"
 #include "grid_kernel.cuh"
 #include "saturation_kernel.cuh"
@@ -89,11 +90,13 @@ struct wva_ctx {
   // queueing system
   bool loaded = false, calculated = false, solved = false;
   bool force_lane_sizer = false;
+  bool gang_refill = false;         // lock-step lane sizer: a warp refills only when all its lanes are idle (opt-in)
+  bool length_sort = false;         // lane sizer pulls items through the probe-sorted permutation (sizer_probe.cuh; opt-in)
   int lane_sizer_mode = 2;   // 1 flattened, 2 lock-step (default), 3 lock-step with two chains per lane (slower: measured)
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
   int policy = 0;
-  DevBuf sys_arena, cand_arena, sol_arena, scratch, gtab, greedy_ws, split_ws;
+  DevBuf sys_arena, cand_arena, sol_arena, scratch, gtab, greedy_ws, split_ws, order_ws;
   PinBuf stage_in, stage_out;
   SysView sys = {};
   CandView cand = {};
@@ -163,7 +166,7 @@ int32_t wva_destroy(wva_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->sys_arena.release(); ctx->cand_arena.release(); ctx->sol_arena.release(); ctx->scratch.release();
-  ctx->gtab.release(); ctx->greedy_ws.release(); ctx->split_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->io_in.release(); ctx->io_out.release();
+  ctx->gtab.release(); ctx->greedy_ws.release(); ctx->split_ws.release(); ctx->order_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->io_in.release(); ctx->io_out.release();
   ctx->stage_in.release(); ctx->stage_out.release(); ctx->io_stage_in.release(); ctx->io_stage_out.release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -296,13 +299,36 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
       e = cudaMemsetAsync(sw.cnt, 0, (size_t)n_pairs * 4, ctx->stream);
       if (e != cudaSuccess) return e;
     }
+    // length-sorted queue: float32 probe -> (N, expected chain length) keys -> descending radix sort of the item ids
+    const unsigned* order = nullptr;
+    const unsigned long long n_items = split ? 2 * n_pairs : n_pairs;
+    if (ctx->length_sort && n_items >= 64 && n_items < (1ull << 31)) {
+      size_t tmp = 0;
+      cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr,
+                                                (unsigned*)nullptr, (int)n_items, 0, 32, ctx->stream);
+      const size_t arr = ((size_t)n_items * 4 + 255) & ~(size_t)255;
+      e = ctx->order_ws.reserve(4 * arr + tmp + 256);
+      if (e != cudaSuccess) return e;
+      unsigned* k_in = (unsigned*)ctx->order_ws.p;
+      unsigned* k_out = (unsigned*)((char*)ctx->order_ws.p + arr);
+      unsigned* v_in = (unsigned*)((char*)ctx->order_ws.p + 2 * arr);
+      unsigned* v_out = (unsigned*)((char*)ctx->order_ws.p + 3 * arr);
+      void* d_tmp = (char*)ctx->order_ws.p + 4 * arr;
+      const unsigned pb = (unsigned)((n_items + 127) / 128);
+      if (split) sizer_probe_kernel<true><<<pb, 128, 0, ctx->stream>>>(ctx->sys, n_items, nmax, k_in, v_in);
+      else sizer_probe_kernel<false><<<pb, 128, 0, ctx->stream>>>(ctx->sys, n_items, nmax, k_in, v_in);
+      e = cub::DeviceRadixSort::SortPairsDescending(d_tmp, tmp, k_in, k_out, v_in, v_out, (int)n_items, 0, 32, ctx->stream);
+      if (e != cudaSuccess) return e;
+      ctx->launches += 4;
+      order = v_out;
+    }
     auto k = (ctx->lane_sizer_mode == 5) ? sizer_lane_kernel<THREADS, SMEM, true, true>
            : split ? sizer_lane_kernel<THREADS, SMEM, false, true>
            : (ctx->lane_sizer_mode == 3) ? sizer_lane_kernel<THREADS, SMEM, true, false>
                                          : sizer_lane_kernel<THREADS, SMEM, false, false>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list, sw);
+    k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list, sw, order, ctx->gang_refill ? 1 : 0);
   }
   ctx->launches++;
   return cudaGetLastError();
@@ -327,6 +353,8 @@ int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
     if (value >= 1 && value <= 5) ctx->lane_sizer_mode = value;
     return WVA_OK;
   }
+  if (option == WVA_OPT_LENGTH_SORT) { ctx->length_sort = value != 0; return WVA_OK; }
+  if (option == WVA_OPT_GANG_REFILL) { ctx->gang_refill = value != 0; return WVA_OK; }
   return WVA_ERR_ARG;
 }
 
@@ -372,7 +400,11 @@ int32_t wva_calculate(wva_ctx* ctx) {
     // as needed instead of filling the first SMs (lanes pull one pair each from the queue)
     // mid-size systems (measured: up to ~200 pairs per SM) still leave lanes idle: split every pair into a
     // TTFT item and an ITL item, which halves the chain of dependent solves per work item
-    if (!ctx->force_lane_sizer) ctx->lane_sizer_mode = (n_pairs <= (unsigned long long)ctx->sm_count * 200) ? 4 : 2;
+    // measured crossovers on B200 (natural queue order, r1): split items up to ~180 pairs per SM, split items with a
+    // speculative second chain (mode 5) up to ~380, whole pairs (mode 2, the searches share evaluations) beyond
+    if (!ctx->force_lane_sizer)
+      ctx->lane_sizer_mode = (n_pairs <= (unsigned long long)ctx->sm_count * 180) ? 4
+                           : (n_pairs <= (unsigned long long)ctx->sm_count * 380) ? 5 : 2;
     const unsigned long long n_items = (ctx->lane_sizer_mode >= 4) ? 2 * n_pairs : n_pairs;
     const unsigned long long lanes_needed = (n_items + ctx->sm_count - 1) / ctx->sm_count;
     if (best_per_sm >= 1 && lanes_needed <= 256 && lanes_needed < (unsigned long long)best_threads * best_per_sm) {
@@ -383,10 +415,10 @@ int32_t wva_calculate(wva_ctx* ctx) {
     cudaError_t e;
     // Small / medium systems are bound by the critical path of their slowest pair: use the
     // warp-per-pair sizer (speculative bisection, sizer_warp_kernel.cuh) while the system is small
-    // (measured crossover against the lock-step lane sizer: ~80 pairs per SM) and its per-warp
+    // (measured crossover against the lock-step lane sizer: ~32 pairs per SM) and its per-warp
     // tables (20 B x nmax) fit in shared memory.
     const size_t warp_tab = (size_t)nmax * 20;
-    if (n_pairs <= (unsigned long long)ctx->sm_count * 80 && warp_tab * 4 + 1024 <= SMEM_PER_SM && !ctx->force_lane_sizer) {
+    if (n_pairs <= (unsigned long long)ctx->sm_count * 32 && warp_tab * 4 + 1024 <= SMEM_PER_SM && !ctx->force_lane_sizer) {
       if (warp_tab * 8 <= 48 * 1024) {
         int per_sm = (int)(SMEM_PER_SM / (warp_tab * 8 + 1024)); if (per_sm > 6) per_sm = 6; if (per_sm < 1) per_sm = 1;
         e = launch_sizer_warp<8>(ctx, ctx->sm_count * per_sm, warp_tab * 8, n_pairs, nmax, d_ovf);
@@ -418,6 +450,9 @@ int32_t wva_calculate(wva_ctx* ctx) {
   ctx->timing.calculate_ms = elapsed(ctx, 2, 3);
   ctx->timing.chain_solves = (int64_t)hc.solves;
   ctx->timing.chain_states = (int64_t)hc.states;
+  if (getenv("WVA_SIZER_DEBUG") && hc.lockstep_slots)
+    fprintf(stderr, "sizer: live lane-steps %llu of %llu lock-step slots (%.1f %%)\n", hc.states, hc.lockstep_slots,
+            100.0 * (double)hc.states / (double)hc.lockstep_slots);
   ctx->timing.overflow_pairs = (int64_t)hc.overflow_pairs;
   if (hc.limit_hit) { ctx->last_error = "a (server, accelerator) pair needs a max batch size above 65536"; return WVA_ERR_LIMIT; }
   if (hc.overflow_pairs) {

@@ -18,6 +18,9 @@ struct SizerCounters {
   unsigned long long states;         // birth-death states visited
   unsigned long long overflow_pairs; // pairs that hit the float64 overflow-rescale branch
   int limit_hit;                     // some pair needs N beyond the build limit
+  int pad_;
+  unsigned long long lockstep_slots; // lock-step lane sizer: 32 x (longest chain of the warp), summed over rounds
+                                     // (states / lockstep_slots = share of the lane-steps that did live work)
 };
 
 // Largest max-batch-size N any pair that needs sizing will use (allocation.go:79-88):

@@ -45,7 +45,7 @@ __device__ __forceinline__ bool split_publish(SizerLane& z, const SysView& s, co
 template <int THREADS, bool SMEM_TABLE, bool DUAL, bool SPLIT>
 __global__ void __launch_bounds__(THREADS)
 sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax, float* gtab,
-                  SizerCounters* ctr, int* overflow_list, SplitWs sw) {
+                  SizerCounters* ctr, int* overflow_list, SplitWs sw, const unsigned* order, int gang) {
   extern __shared__ float smem_tab[];
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
@@ -57,16 +57,30 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
   SizerLane z;
   z.m.N = 1; z.m.K = 11; z.m.mono = 0; z.m.mu_last = 1.0; z.m.r_last = 1.0;
   SolveStats st;
-  bool live = false, exhausted = false;
-  unsigned long long my_solves = 0, my_states = 0;
+  bool live = false, exhausted = false, first_wave = true;
+  unsigned long long my_solves = 0, my_states = 0, my_slots = 0;
 
   while (true) {
     // ---- refill ------------------------------------------------------------------------------
     bool need_table = false;
-    if (!live && !exhausted) {
+    // gang refill: the warp takes 32 new items only when all of its lanes are idle, so its lanes stay in the SAME
+    // bisection step (a chain at the first midpoint is ~10x shorter than one at lambda_max: lanes in different
+    // steps made every round as long as the longest step)
+    const bool may_refill = !gang || !__any_sync(full, live);
+    if (!live && !exhausted && may_refill) {
       while (true) {
-        unsigned long long item = atomicAdd(&ctr->next_pair, 1ull);
+        // queue position: with a sorted queue the first wave is dealt statically, consecutive groups of 32 to
+        // DIFFERENT SMs (warp w of block b takes group w * gridDim + b), so the longest items do not share an SM;
+        // later positions come from the global counter
+        unsigned long long item;
+        if (order && first_wave) {
+          item = ((unsigned long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32ull + (unsigned)lane;
+          first_wave = false;
+        } else {
+          item = atomicAdd(&ctr->next_pair, 1ull) + (order ? (unsigned long long)gridDim.x * THREADS : 0ull);
+        }
         if (item >= (SPLIT ? 2 * n_pairs : n_pairs)) { exhausted = true; break; }
+        if (order) item = order[item];                 // length-sorted queue (sizer_probe.cuh)
         const unsigned long long pair = SPLIT ? (item >> 1) : item;
         int srv = (int)(pair / (unsigned)s.n_acc), acc = (int)(pair % (unsigned)s.n_acc);
         int lim = 0;
@@ -161,12 +175,17 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
         if (!live) { my_solves += z.solves; my_states += z.states; }
       }
     }
+    {
+      int mxs = sv;
+      for (int o = 16; o; o >>= 1) mxs = max(mxs, __shfl_xor_sync(full, mxs, o));
+      if (lane == 0) my_slots += 32ull * (unsigned long long)mxs;
+    }
   }
   for (int o = 16; o; o >>= 1) {
     my_solves += __shfl_down_sync(full, my_solves, o);
     my_states += __shfl_down_sync(full, my_states, o);
   }
-  if (lane == 0) { atomicAdd(&ctr->solves, my_solves); atomicAdd(&ctr->states, my_states); }
+  if (lane == 0) { atomicAdd(&ctr->solves, my_solves); atomicAdd(&ctr->states, my_states); atomicAdd(&ctr->lockstep_slots, my_slots); }
 }
 
 }  // namespace wva

@@ -3,6 +3,7 @@
 // against the oracle on a machine without a GPU.  Never linked into the product.
 #include "../../include/wva_b200.h"
 #include "../../llm-d-workload-variant-autoscaler_b200/csrc/wva_core.cuh"
+#include "../../llm-d-workload-variant-autoscaler_b200/csrc/sizer_probe.cuh"
 #include <vector>
 #include <cstdio>
 #include <cstdlib>
@@ -227,6 +228,62 @@ extern "C" int emul_calculate_spec2(const wva_system* sys, wva_candidates* out, 
         live = spec2_on_solve(z, s, o, st2, 0);
       }
     }
+  return 0;
+}
+
+// The float32 probe keys of sizer_probe.cuh for every split item (analysis: how well do they predict the chain length)
+extern "C" int emul_probe_keys(const wva_system* sys, uint32_t* keys) {
+  SysView s = make_view(sys);
+  const unsigned long long n = 2ull * s.n_servers * s.n_acc;
+  for (unsigned long long i = 0; i < n; i++) keys[i] = probe_item_key(s, i, true, 1 << 20);
+  return 0;
+}
+
+extern "C" int emul_probe_debug(const wva_system* sys, int item) {
+  SysView s = make_view(sys);
+  const int pair = item >> 1, srv = pair / s.n_acc, acc = pair % s.n_acc;
+  SizerLane z; CandView none = {}; int lim = 0;
+  int rc = sizer_setup(z, s, none, srv, acc, 1 << 20, &lim, false);
+  PairModel& m = z.m;
+  m.lambda_min = serv_rate(m, 1) * WVA_EPSILON; m.lambda_max = serv_rate(m, m.N) * (1.0f - WVA_EPSILON);
+  printf("rc %d N %d K %d lmin %g lmax %g tT %g tI %g mu1 %g muN %g\n", rc, m.N, m.K, m.lambda_min, m.lambda_max, z.sT.target, z.sI.target, serv_rate(m,1), serv_rate(m,m.N));
+  for (float f : {0.0f, 0.25f, 0.5f, 0.75f, 0.9f, 1.0f}) {
+    float x = m.lambda_min + f * (m.lambda_max - m.lambda_min);
+    ProbeEval e = probe_eval(m, nullptr, x), e2 = e;
+    bool ovf; SolveStats st; float t, i, pf; 
+    std::vector<float> tab(m.N); model_fill_table(m, tab.data(), 1, 0, 1); PairModel mm = m; model_finish(mm, tab.data(), 1);
+    st = host_solve(mm, x, &ovf); host_eval(mm, st, &t, &i, &pf);
+    printf("  x %g probe ttft %g itl %g len %d len54 %d | exact ttft %g itl %g\n", x, e.ttft, e.itl, e.len, e2.len, t, i);
+  }
+  return 0;
+}
+
+// Analysis helper: per split item (2 * pair + kind), the number of states of each chain solve of its search, in
+// order (trace[item * W] = count, then the lengths) — used to study how the lock-step rounds of a warp line up.
+extern "C" int emul_trace_split(const wva_system* sys, int32_t* trace, int W) {
+  SysView s = make_view(sys);
+  CandView o = {};
+  std::vector<float> tab;
+  for (int srv = 0; srv < s.n_servers; srv++)
+    for (int acc = 0; acc < s.n_acc; acc++)
+      for (int k = 0; k < 2; k++) {
+        int32_t* t = trace + ((size_t)(srv * s.n_acc + acc) * 2 + k) * W;
+        t[0] = 0;
+        SizerLane z; int lim = 0;
+        if (sizer_setup(z, s, o, srv, acc, 1 << 20, &lim, false) == SETUP_DONE) continue;
+        tab.assign((size_t)z.m.N, 0.0f);
+        model_fill_table(z.m, tab.data(), 1, 0, 1);
+        model_finish(z.m, tab.data(), 1);
+        z.split = k;
+        bool live = sizer_begin(z, s, o);
+        while (live && z.stage != SZ_PUBLISH) {
+          SolveStats st{};
+          while (!chain_step(z.c, z.m, st)) {}
+          if (z.c.phase == CH_OVERFLOW) break;
+          if (t[0] + 1 < W) t[++t[0]] = z.c.states;
+          live = sizer_on_solve(z, s, o, st);
+        }
+      }
   return 0;
 }
 

@@ -6,11 +6,15 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 A = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 modes = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0, 1, 2]
+gang = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 d = pkg.synth.queue_system(S, A, N, n_classes=3, stream=3, R=N)
 with pkg.Engine(0) as e:
     e.load_system(d)
     ref = None
     for mode in modes:
+        e.set_option(2, 0 if mode < 0 else 1)      # negative mode: natural order (length sort off)
+        mode = abs(mode)
+        e.set_option(3, gang)
         e.set_option(1, mode)
         for rep in range(2):
             e.calculate()

@@ -317,6 +317,79 @@ int32_t wva_limit(wva_ctx* ctx, int64_t n_decisions, int32_t n_types,
                   const int32_t* type_limit, int32_t* out_target,
                   int32_t* out_gpus_allocated, uint8_t* out_was_limited);
 
+/* ---- V2 pipeline: token-capacity analyzer, cost-aware optimizer, enforcer ------- */
+/*
+ * SaturationAnalyzer.Analyze (internal/engines/analyzers/saturation_v2/analyzer.go:59-138: computeReplicaCapacity
+ * :142-211, aggregateByVariant :266-349, estimateSchedulerQueueDemand :471-501, median :505-519) for a batch of
+ * models.  The arithmetic only: what the reference keeps in string-keyed state stays with the caller —
+ * the k2 priority chain (computeK2 :218-262, rolling history) resolves rep_k2 per replica, the capacity store
+ * resolves var_fallback_capacity for variants without ready replicas (:317-324).
+ * Variants of a model in VariantStates order; replicas of a variant in ReplicaMetrics order.
+ */
+typedef struct {
+  int64_t n_models, n_variants, n_replicas;
+  const int32_t* model_variant_off;     /* [M+1] */
+  const int32_t* variant_replica_off;   /* [V+1] */
+  const int64_t* rep_total_kv_tokens;   /* [P] ReplicaMetrics.TotalKvCapacityTokens; <= 0: no capacity data, replica skipped */
+  const int64_t* rep_tokens_in_use;     /* [P] */
+  const int64_t* rep_queue_length;      /* [P] */
+  const double* rep_avg_input_tokens;   /* [P] */
+  const double* rep_avg_output_tokens;  /* [P] */
+  const double* rep_prefix_hit_rate;    /* [P] */
+  const int64_t* rep_k2;                /* [P] compute-bound capacity from the caller's chain; < 0 = fall back to k1 */
+  const int32_t* rep_slice_order;       /* [P] or NULL: replica indices of each model in ReplicaMetrics slice order
+                                           (model m owns positions [vro[mvo[m]], vro[mvo[m+1]])); NULL = as laid out */
+  const int32_t* var_current;           /* [V] VariantReplicaState.CurrentReplicas */
+  const int32_t* var_pending;           /* [V] PendingReplicas */
+  const double* var_fallback_capacity;  /* [V] per-replica capacity when the variant has no replica with data; 0 = none */
+  const double* cfg_kv_threshold;       /* [M] SaturationScalingConfig.KvCacheThreshold */
+  const double* cfg_scale_up_threshold; /* [M] ScaleUpThreshold */
+  const double* cfg_scale_down_boundary;/* [M] ScaleDownBoundary */
+  const int64_t* sched_queue_size;      /* [M] or NULL: SchedulerQueueMetrics.QueueSize (NULL = no scheduler queue) */
+  const int64_t* sched_queue_bytes;     /* [M] or NULL */
+} wva_saturation_v2_in;
+
+typedef struct {            /* any pointer may be NULL */
+  int64_t* rep_k1;          /* [P] MemoryBoundCapacity */
+  int64_t* rep_effective;   /* [P] EffectiveCapacity = min(k1, k2) */
+  int64_t* rep_demand;      /* [P] ReplicaDemand */
+  uint8_t* rep_saturated;   /* [P] IsSaturated */
+  int32_t* var_ready;       /* [V] VariantCapacity.ReplicaCount */
+  double* var_per_replica_capacity; /* [V] */
+  double* var_total_capacity;       /* [V] */
+  double* var_total_demand;         /* [V] */
+  double* var_utilization;          /* [V] */
+  double* mod_total_supply;         /* [M] AnalyzerResult.TotalSupply */
+  double* mod_total_demand;         /* [M] */
+  double* mod_utilization;          /* [M] */
+  double* mod_required_capacity;    /* [M] */
+  double* mod_spare_capacity;       /* [M] */
+} wva_saturation_v2_out;
+int32_t wva_saturation_v2(wva_ctx* ctx, const wva_saturation_v2_in* in, const wva_saturation_v2_out* out);
+
+/*
+ * CostAwareOptimizer.Optimize (internal/engines/pipeline/cost_aware_optimizer.go:39-197) for a batch of models:
+ * scale-up on the most cost-efficient variants (cost / perReplicaCapacity ascending, ceil), scale-down on the most
+ * expensive (cost descending, floor, the cheapest variant keeps one replica while no other variant has any).
+ * Variants in VariantCapacities slice order (ties of the reference's unstable sorts resolve to that order).
+ * var_target[v] = -1 for the variants of a model without a result (req.Result == nil: no decisions).
+ */
+int32_t wva_cost_aware_optimize(wva_ctx* ctx, int64_t n_models, int64_t n_variants, const int32_t* model_variant_off,
+                                const double* mod_required_capacity, const double* mod_spare_capacity,
+                                const uint8_t* mod_has_result /* or NULL */, const int32_t* var_current,
+                                const double* var_cost, const double* var_per_replica_capacity, int32_t* var_target);
+
+/*
+ * Enforcer.EnforcePolicy (internal/engines/pipeline/enforcer.go:55-183) for a batch of models: scale-to-zero when it
+ * is enabled and the model had no requests in its retention period (request count and lookup error supplied by the
+ * caller), else keep one replica on the cheapest variant when every target is 0.  var_target is updated in place
+ * (-1 = the variant is not in the targets map); mod_applied[m] = the bool EnforcePolicy returns.
+ */
+int32_t wva_enforce(wva_ctx* ctx, int64_t n_models, int64_t n_variants, const int32_t* model_variant_off,
+                    const uint8_t* mod_scale_to_zero_enabled, const double* mod_request_count,
+                    const uint8_t* mod_request_error /* or NULL */, const double* var_cost,
+                    const uint8_t* var_has_cost /* or NULL */, int32_t* var_target, uint8_t* mod_applied);
+
 /* ---- observability -------------------------------------------------------- */
 int32_t wva_last_timing(const wva_ctx* ctx, wva_timing* out);
 

@@ -227,3 +227,64 @@ def alloc_saturation_out(M: int, V: int, P: int):
         setattr(st, name, ptr(a))
         out[name] = a[:n]
     return st, out
+
+
+# ---- V2 pipeline ---------------------------------------------------------------------------------------------------
+_i64p = C.POINTER(C.c_int64)
+
+
+class SaturationV2In(C.Structure):
+    _fields_ = [("n_models", C.c_int64), ("n_variants", C.c_int64), ("n_replicas", C.c_int64),
+                ("model_variant_off", _i32p), ("variant_replica_off", _i32p),
+                ("rep_total_kv_tokens", _i64p), ("rep_tokens_in_use", _i64p), ("rep_queue_length", _i64p),
+                ("rep_avg_input_tokens", _f64p), ("rep_avg_output_tokens", _f64p), ("rep_prefix_hit_rate", _f64p),
+                ("rep_k2", _i64p), ("rep_slice_order", _i32p),
+                ("var_current", _i32p), ("var_pending", _i32p), ("var_fallback_capacity", _f64p),
+                ("cfg_kv_threshold", _f64p), ("cfg_scale_up_threshold", _f64p), ("cfg_scale_down_boundary", _f64p),
+                ("sched_queue_size", _i64p), ("sched_queue_bytes", _i64p)]
+
+
+class SaturationV2Out(C.Structure):
+    _fields_ = [("rep_k1", _i64p), ("rep_effective", _i64p), ("rep_demand", _i64p), ("rep_saturated", _u8p),
+                ("var_ready", _i32p), ("var_per_replica_capacity", _f64p), ("var_total_capacity", _f64p),
+                ("var_total_demand", _f64p), ("var_utilization", _f64p),
+                ("mod_total_supply", _f64p), ("mod_total_demand", _f64p), ("mod_utilization", _f64p),
+                ("mod_required_capacity", _f64p), ("mod_spare_capacity", _f64p)]
+
+
+SAT_V2_IN = {"model_variant_off": (np.int32, "M1"), "variant_replica_off": (np.int32, "V1"),
+             "rep_total_kv_tokens": (np.int64, "P"), "rep_tokens_in_use": (np.int64, "P"), "rep_queue_length": (np.int64, "P"),
+             "rep_avg_input_tokens": (np.float64, "P"), "rep_avg_output_tokens": (np.float64, "P"),
+             "rep_prefix_hit_rate": (np.float64, "P"), "rep_k2": (np.int64, "P"), "rep_slice_order": (np.int32, "P"),
+             "var_current": (np.int32, "V"), "var_pending": (np.int32, "V"), "var_fallback_capacity": (np.float64, "V"),
+             "cfg_kv_threshold": (np.float64, "M"), "cfg_scale_up_threshold": (np.float64, "M"),
+             "cfg_scale_down_boundary": (np.float64, "M"), "sched_queue_size": (np.int64, "M"), "sched_queue_bytes": (np.int64, "M")}
+SAT_V2_OPTIONAL = ("rep_slice_order", "sched_queue_size", "sched_queue_bytes")
+SAT_V2_OUT = {"rep_k1": (np.int64, "P"), "rep_effective": (np.int64, "P"), "rep_demand": (np.int64, "P"),
+              "rep_saturated": (np.uint8, "P"), "var_ready": (np.int32, "V"), "var_per_replica_capacity": (np.float64, "V"),
+              "var_total_capacity": (np.float64, "V"), "var_total_demand": (np.float64, "V"), "var_utilization": (np.float64, "V"),
+              "mod_total_supply": (np.float64, "M"), "mod_total_demand": (np.float64, "M"), "mod_utilization": (np.float64, "M"),
+              "mod_required_capacity": (np.float64, "M"), "mod_spare_capacity": (np.float64, "M")}
+
+
+def make_saturation_v2(d: dict):
+    M, V, P = int(d["n_models"]), int(d["n_variants"]), int(d["n_replicas"])
+    n = {"M": M, "V": V, "P": P, "M1": M + 1, "V1": V + 1}
+    ist, ost, keep, out = SaturationV2In(), SaturationV2Out(), [], {}
+    ist.n_models, ist.n_variants, ist.n_replicas = M, V, P
+    for name, (dt, dim) in SAT_V2_IN.items():
+        if name in SAT_V2_OPTIONAL and d.get(name) is None:
+            setattr(ist, name, None)
+            continue
+        a = np.ascontiguousarray(d[name], dtype=dt).reshape(-1)
+        if a.size != n[dim]:
+            raise ValueError(f"{name}: expected {n[dim]} elements, got {a.size}")
+        if a.size == 0:
+            a = np.zeros(1, dt)
+        keep.append(a)
+        setattr(ist, name, ptr(a))
+    for name, (dt, dim) in SAT_V2_OUT.items():
+        a = np.zeros(max(n[dim], 1), dtype=dt)
+        setattr(ost, name, ptr(a))
+        out[name] = a[:n[dim]]
+    return ist, ost, keep, out

@@ -12,6 +12,7 @@
 #include "grid_kernel.cuh"
 #include "saturation_kernel.cuh"
 #include "limiter_kernel.cuh"
+#include "pipeline_v2_kernel.cuh"
 #include "greedy_kernel.cuh"
 #include "greedy_solve.cuh"
 #include "mm1k_kernel.cuh"

@@ -411,3 +411,157 @@ extern "C" int32_t wva_microbench_fp64(wva_ctx* ctx, double* dfma_per_s, double*
   *ddiv_per_s = (double)blocks * threads * 4.0 * it_div / (best_div * 1e-3);
   return WVA_OK;
 }
+
+// ------------------------------------------------------------------ V2 pipeline (pipeline_v2_kernel.cuh)
+namespace {
+// host arrays -> one device arena, results back: a tiny staging helper for the three batched V2 entry points
+struct Stage {
+  wva_ctx* ctx; Layout L; std::vector<std::pair<size_t, std::pair<const void*, size_t>>> in;
+  size_t add(const void* host, size_t bytes) { size_t o = L.take(bytes ? bytes : 1); if (host && bytes) in.push_back({o, {host, bytes}}); return o; }
+  int32_t upload() {
+    if (ctx->io_in.reserve(L.off + 256) != cudaSuccess) return WVA_ERR_NOMEM;
+    for (auto& e : in)
+      if (cudaMemcpyAsync((char*)ctx->io_in.p + e.first, e.second.first, e.second.second, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        return WVA_ERR_CUDA;
+    return WVA_OK;
+  }
+  template <class T> const T* at(size_t off, const void* host) const { return host ? (const T*)((char*)ctx->io_in.p + off) : nullptr; }
+};
+inline unsigned warp_grid(wva_ctx* ctx, long long n_models) {
+  long long blocks = (n_models + 7) / 8;                    // 8 warps (models) per 256-thread block
+  const long long cap = (long long)ctx->sm_count * 32;
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+}  // namespace
+
+extern "C" int32_t wva_saturation_v2(wva_ctx* ctx, const wva_saturation_v2_in* in, const wva_saturation_v2_out* out) {
+  if (!ctx || !in || !out || in->n_models < 0 || in->n_variants < 0 || in->n_replicas < 0) return WVA_ERR_ARG;
+  const size_t M = (size_t)in->n_models, V = (size_t)in->n_variants, P = (size_t)in->n_replicas;
+  if (M == 0) return WVA_OK;
+  if (in->n_variants > 0x7fffffffLL || in->n_replicas > 0x7fffffffLL) return WVA_ERR_LIMIT;
+  if (!in->model_variant_off || !in->variant_replica_off || !in->cfg_kv_threshold || !in->cfg_scale_up_threshold ||
+      !in->cfg_scale_down_boundary || (V && (!in->var_current || !in->var_pending || !in->var_fallback_capacity)) ||
+      (P && (!in->rep_total_kv_tokens || !in->rep_tokens_in_use || !in->rep_queue_length || !in->rep_avg_input_tokens ||
+             !in->rep_avg_output_tokens || !in->rep_prefix_hit_rate || !in->rep_k2)) ||
+      ((in->sched_queue_size == nullptr) != (in->sched_queue_bytes == nullptr)))
+    return WVA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  Stage s{ctx};
+  const size_t o_mvo = s.add(in->model_variant_off, (M + 1) * 4), o_vro = s.add(in->variant_replica_off, (V + 1) * 4),
+               o_tk = s.add(in->rep_total_kv_tokens, P * 8), o_tu = s.add(in->rep_tokens_in_use, P * 8),
+               o_ql = s.add(in->rep_queue_length, P * 8), o_ai = s.add(in->rep_avg_input_tokens, P * 8),
+               o_ao = s.add(in->rep_avg_output_tokens, P * 8), o_hr = s.add(in->rep_prefix_hit_rate, P * 8),
+               o_k2 = s.add(in->rep_k2, P * 8), o_so = s.add(in->rep_slice_order, P * 4), o_vc = s.add(in->var_current, V * 4),
+               o_vp = s.add(in->var_pending, V * 4), o_vf = s.add(in->var_fallback_capacity, V * 8),
+               o_kt = s.add(in->cfg_kv_threshold, M * 8), o_su = s.add(in->cfg_scale_up_threshold, M * 8),
+               o_sd = s.add(in->cfg_scale_down_boundary, M * 8), o_qs = s.add(in->sched_queue_size, M * 8),
+               o_qb = s.add(in->sched_queue_bytes, M * 8);
+  int32_t rc = s.upload();
+  if (rc != WVA_OK) return rc;
+  Layout O;
+  const size_t q_k1 = O.take(P * 8), q_ef = O.take(P * 8), q_de = O.take(P * 8), q_sa = O.take(P), q_vr = O.take(V * 4),
+               q_vcap = O.take(V * 8), q_vt = O.take(V * 8), q_vd = O.take(V * 8), q_vu = O.take(V * 8), q_ms = O.take(M * 8),
+               q_md = O.take(M * 8), q_mu = O.take(M * 8), q_mr = O.take(M * 8), q_mp = O.take(M * 8);
+  CK(ctx->io_out.reserve(O.off + 256));
+  char* dd = (char*)ctx->io_out.p;
+  SatV2In di;
+  di.n_models = in->n_models; di.n_variants = in->n_variants; di.n_replicas = in->n_replicas;
+  di.model_variant_off = s.at<int>(o_mvo, in->model_variant_off); di.variant_replica_off = s.at<int>(o_vro, in->variant_replica_off);
+  di.rep_total_kv = s.at<long long>(o_tk, in->rep_total_kv_tokens); di.rep_tokens_in_use = s.at<long long>(o_tu, in->rep_tokens_in_use);
+  di.rep_queue_len = s.at<long long>(o_ql, in->rep_queue_length); di.rep_k2 = s.at<long long>(o_k2, in->rep_k2);
+  di.rep_avg_in = s.at<double>(o_ai, in->rep_avg_input_tokens); di.rep_avg_out = s.at<double>(o_ao, in->rep_avg_output_tokens);
+  di.rep_hit = s.at<double>(o_hr, in->rep_prefix_hit_rate); di.rep_slice_order = s.at<int>(o_so, in->rep_slice_order);
+  di.var_current = s.at<int>(o_vc, in->var_current); di.var_pending = s.at<int>(o_vp, in->var_pending);
+  di.var_fallback = s.at<double>(o_vf, in->var_fallback_capacity);
+  di.cfg_kv_threshold = s.at<double>(o_kt, in->cfg_kv_threshold); di.cfg_scale_up = s.at<double>(o_su, in->cfg_scale_up_threshold);
+  di.cfg_scale_down = s.at<double>(o_sd, in->cfg_scale_down_boundary);
+  di.sched_size = s.at<long long>(o_qs, in->sched_queue_size); di.sched_bytes = s.at<long long>(o_qb, in->sched_queue_bytes);
+  SatV2Out dout;
+  dout.rep_k1 = out->rep_k1 ? (long long*)(dd + q_k1) : nullptr; dout.rep_effective = out->rep_effective ? (long long*)(dd + q_ef) : nullptr;
+  dout.rep_demand = out->rep_demand ? (long long*)(dd + q_de) : nullptr; dout.rep_saturated = out->rep_saturated ? (unsigned char*)(dd + q_sa) : nullptr;
+  dout.var_ready = out->var_ready ? (int*)(dd + q_vr) : nullptr; dout.var_cap = out->var_per_replica_capacity ? (double*)(dd + q_vcap) : nullptr;
+  dout.var_total_cap = out->var_total_capacity ? (double*)(dd + q_vt) : nullptr; dout.var_total_demand = out->var_total_demand ? (double*)(dd + q_vd) : nullptr;
+  dout.var_util = out->var_utilization ? (double*)(dd + q_vu) : nullptr;
+  dout.mod_supply = out->mod_total_supply ? (double*)(dd + q_ms) : nullptr; dout.mod_demand = out->mod_total_demand ? (double*)(dd + q_md) : nullptr;
+  dout.mod_util = out->mod_utilization ? (double*)(dd + q_mu) : nullptr; dout.mod_required = out->mod_required_capacity ? (double*)(dd + q_mr) : nullptr;
+  dout.mod_spare = out->mod_spare_capacity ? (double*)(dd + q_mp) : nullptr;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  saturation_v2_kernel<<<warp_grid(ctx, in->n_models), 256, 0, ctx->stream>>>(di, dout);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  auto back = [&](void* host, size_t off, size_t bytes) -> cudaError_t {
+    return (host && bytes) ? cudaMemcpyAsync(host, dd + off, bytes, cudaMemcpyDeviceToHost, ctx->stream) : cudaSuccess;
+  };
+  CK(back(out->rep_k1, q_k1, P * 8)); CK(back(out->rep_effective, q_ef, P * 8)); CK(back(out->rep_demand, q_de, P * 8));
+  CK(back(out->rep_saturated, q_sa, P)); CK(back(out->var_ready, q_vr, V * 4)); CK(back(out->var_per_replica_capacity, q_vcap, V * 8));
+  CK(back(out->var_total_capacity, q_vt, V * 8)); CK(back(out->var_total_demand, q_vd, V * 8)); CK(back(out->var_utilization, q_vu, V * 8));
+  CK(back(out->mod_total_supply, q_ms, M * 8)); CK(back(out->mod_total_demand, q_md, M * 8)); CK(back(out->mod_utilization, q_mu, M * 8));
+  CK(back(out->mod_required_capacity, q_mr, M * 8)); CK(back(out->mod_spare_capacity, q_mp, M * 8));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.saturation_ms = elapsed(ctx, 2, 3);
+  return WVA_OK;
+}
+
+extern "C" int32_t wva_cost_aware_optimize(wva_ctx* ctx, int64_t n_models, int64_t n_variants, const int32_t* model_variant_off,
+                                           const double* mod_required, const double* mod_spare, const uint8_t* mod_has_result,
+                                           const int32_t* var_current, const double* var_cost, const double* var_cap,
+                                           int32_t* var_target) {
+  if (!ctx || n_models < 0 || n_variants < 0) return WVA_ERR_ARG;
+  if (n_models == 0) return WVA_OK;
+  if (n_variants > 0x7fffffffLL) return WVA_ERR_LIMIT;
+  if (!model_variant_off || !mod_required || !mod_spare || (n_variants && (!var_current || !var_cost || !var_cap || !var_target)))
+    return WVA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t M = (size_t)n_models, V = (size_t)n_variants;
+  Stage s{ctx};
+  const size_t o_mvo = s.add(model_variant_off, (M + 1) * 4), o_rq = s.add(mod_required, M * 8), o_sp = s.add(mod_spare, M * 8),
+               o_hr = s.add(mod_has_result, M), o_cu = s.add(var_current, V * 4), o_co = s.add(var_cost, V * 8), o_ca = s.add(var_cap, V * 8);
+  int32_t rc = s.upload();
+  if (rc != WVA_OK) return rc;
+  CK(ctx->io_out.reserve(V * 4 + 256));
+  int* d_t = (int*)ctx->io_out.p;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  cost_aware_kernel<<<warp_grid(ctx, n_models), 256, 0, ctx->stream>>>(n_models, s.at<int>(o_mvo, model_variant_off), s.at<double>(o_rq, mod_required),
+      s.at<double>(o_sp, mod_spare), s.at<unsigned char>(o_hr, mod_has_result), s.at<int>(o_cu, var_current), s.at<double>(o_co, var_cost),
+      s.at<double>(o_ca, var_cap), d_t);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  if (V) CK(cudaMemcpyAsync(var_target, d_t, V * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.limit_ms = elapsed(ctx, 2, 3);
+  return WVA_OK;
+}
+
+extern "C" int32_t wva_enforce(wva_ctx* ctx, int64_t n_models, int64_t n_variants, const int32_t* model_variant_off,
+                               const uint8_t* mod_s2z, const double* mod_request_count, const uint8_t* mod_request_error,
+                               const double* var_cost, const uint8_t* var_has_cost, int32_t* var_target, uint8_t* mod_applied) {
+  if (!ctx || n_models < 0 || n_variants < 0) return WVA_ERR_ARG;
+  if (n_models == 0) return WVA_OK;
+  if (n_variants > 0x7fffffffLL) return WVA_ERR_LIMIT;
+  if (!model_variant_off || !mod_s2z || !mod_request_count || (n_variants && (!var_cost || !var_target))) return WVA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t M = (size_t)n_models, V = (size_t)n_variants;
+  Stage s{ctx};
+  const size_t o_mvo = s.add(model_variant_off, (M + 1) * 4), o_z = s.add(mod_s2z, M), o_rc = s.add(mod_request_count, M * 8),
+               o_re = s.add(mod_request_error, M), o_co = s.add(var_cost, V * 8), o_hc = s.add(var_has_cost, V), o_tg = s.add(var_target, V * 4);
+  int32_t rc = s.upload();
+  if (rc != WVA_OK) return rc;
+  CK(ctx->io_out.reserve(M + 256));
+  unsigned char* d_app = (unsigned char*)ctx->io_out.p;
+  int* d_t = (int*)((char*)ctx->io_in.p + o_tg);
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  enforce_kernel<<<warp_grid(ctx, n_models), 256, 0, ctx->stream>>>(n_models, s.at<int>(o_mvo, model_variant_off), s.at<unsigned char>(o_z, mod_s2z),
+      s.at<double>(o_rc, mod_request_count), s.at<unsigned char>(o_re, mod_request_error), s.at<double>(o_co, var_cost),
+      s.at<unsigned char>(o_hc, var_has_cost), d_t, d_app);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  if (V) CK(cudaMemcpyAsync(var_target, d_t, V * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mod_applied) CK(cudaMemcpyAsync(mod_applied, d_app, M, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.limit_ms = elapsed(ctx, 2, 3);
+  return WVA_OK;
+}

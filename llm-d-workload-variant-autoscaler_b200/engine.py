@@ -73,6 +73,9 @@ def load_library():
     L.wva_mm1k_eval.argtypes = [ctxp, C.c_int64] + [C.c_void_p] * 11
     L.wva_saturation_v1.argtypes = [ctxp, C.POINTER(abi.SaturationIn), C.POINTER(abi.SaturationOut)]
     L.wva_limit.argtypes = [ctxp, C.c_int64, C.c_int32] + [C.c_void_p] * 10
+    L.wva_saturation_v2.argtypes = [ctxp, C.POINTER(abi.SaturationV2In), C.POINTER(abi.SaturationV2Out)]
+    L.wva_cost_aware_optimize.argtypes = [ctxp, C.c_int64, C.c_int64] + [C.c_void_p] * 8
+    L.wva_enforce.argtypes = [ctxp, C.c_int64, C.c_int64] + [C.c_void_p] * 8
     L.wva_last_timing.argtypes = [ctxp, C.POINTER(abi.Timing)]
     L.wva_microbench_fp64.argtypes = [ctxp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
@@ -82,7 +85,8 @@ def load_library():
 EXPORTS = ["wva_set_option", "wva_create", "wva_destroy", "wva_strerror", "wva_last_error", "wva_launch_count",
            "wva_load_system", "wva_calculate", "wva_solve", "wva_get_candidates", "wva_get_solution",
            "wva_analyze_grid", "wva_grid_run", "wva_grid_fetch", "wva_mm1k_eval", "wva_saturation_v1",
-           "wva_saturation_upload", "wva_saturation_run", "wva_saturation_fetch", "wva_limit", "wva_last_timing",
+           "wva_saturation_upload", "wva_saturation_run", "wva_saturation_fetch", "wva_limit", "wva_saturation_v2",
+           "wva_cost_aware_optimize", "wva_enforce", "wva_last_timing",
            "wva_microbench_fp64"]
 
 
@@ -224,6 +228,43 @@ class Engine:
                                        out["target"].ctypes.data, out["gpus_allocated"].ctypes.data,
                                        out["was_limited"].ctypes.data), "wva_limit")
         return {k: v[:D] for k, v in out.items()}
+
+    # ---- V2 pipeline ------------------------------------------------------------------------------
+    def saturation_v2(self, d: dict):
+        """SaturationAnalyzer.Analyze arithmetic for a batch of models (see include/wva_b200.h)."""
+        ist, ost, keep, out = abi.make_saturation_v2(d)
+        self._check(self.lib.wva_saturation_v2(self.ctx, C.byref(ist), C.byref(ost)), "wva_saturation_v2")
+        return out
+
+    @staticmethod
+    def _batch(d, spec):
+        return {k: (None if d.get(k) is None else np.ascontiguousarray(d[k], dt).reshape(-1)) for k, dt in spec}
+
+    def cost_aware_optimize(self, d: dict):
+        a = self._batch(d, (("model_variant_off", np.int32), ("mod_required_capacity", np.float64), ("mod_spare_capacity", np.float64),
+                            ("mod_has_result", np.uint8), ("var_current", np.int32), ("var_cost", np.float64),
+                            ("var_per_replica_capacity", np.float64)))
+        M, V = len(a["mod_required_capacity"]), len(a["var_current"])
+        tgt = np.zeros(max(V, 1), np.int32)
+        p = lambda k: None if a[k] is None or a[k].size == 0 else a[k].ctypes.data
+        self._check(self.lib.wva_cost_aware_optimize(self.ctx, M, V, p("model_variant_off"), p("mod_required_capacity"),
+                                                     p("mod_spare_capacity"), p("mod_has_result"), p("var_current"), p("var_cost"),
+                                                     p("var_per_replica_capacity"), tgt.ctypes.data), "wva_cost_aware_optimize")
+        return tgt[:V]
+
+    def enforce(self, d: dict):
+        a = self._batch(d, (("model_variant_off", np.int32), ("mod_scale_to_zero_enabled", np.uint8), ("mod_request_count", np.float64),
+                            ("mod_request_error", np.uint8), ("var_cost", np.float64), ("var_has_cost", np.uint8)))
+        M, V = len(a["mod_request_count"]), len(a["var_cost"])
+        tgt = np.ascontiguousarray(d["var_target"], np.int32).reshape(-1).copy()
+        if tgt.size == 0:
+            tgt = np.zeros(1, np.int32)
+        app = np.zeros(max(M, 1), np.uint8)
+        p = lambda k: None if a[k] is None or a[k].size == 0 else a[k].ctypes.data
+        self._check(self.lib.wva_enforce(self.ctx, M, V, p("model_variant_off"), p("mod_scale_to_zero_enabled"), p("mod_request_count"),
+                                         p("mod_request_error"), p("var_cost"), p("var_has_cost"), tgt.ctypes.data, app.ctypes.data),
+                    "wva_enforce")
+        return tgt[:V], app[:M]
 
     # ---- observability ------------------------------------------------------------------------
     def timing(self) -> dict:

@@ -6,6 +6,7 @@
 #include "core.hpp"
 #include "saturation.hpp"
 #include "solver.hpp"
+#include "pipeline_v2.hpp"
 #include <cstring>
 #include <climits>
 #ifdef _OPENMP
@@ -204,6 +205,73 @@ int oracle_limit(int64_t D, int T, const int32_t* acc_type, const int32_t* curre
                  int32_t* out_target, int32_t* out_gpus, uint8_t* out_limited) {
   Limit(D, T, acc_type, current, target, gpr, spare, cost, type_limit, out_target, out_gpus, out_limited);
   return 0;
+}
+
+// ---- V2 pipeline (pipeline_v2.hpp) ----
+int oracle_saturation_v2(const wva_saturation_v2_in* in, const wva_saturation_v2_out* out) {
+  using namespace oracle_v2;
+  std::vector<int> ready; std::vector<double> a, b, c, d;
+  for (int64_t m = 0; m < in->n_models; m++) {
+    const int v0 = in->model_variant_off[m], v1 = in->model_variant_off[m + 1], V = v1 - v0;
+    V2ModelIn mi;
+    mi.V = V; mi.vro = in->variant_replica_off + v0;
+    mi.rep_total_kv = (const long long*)in->rep_total_kv_tokens; mi.rep_tokens_in_use = (const long long*)in->rep_tokens_in_use;
+    mi.rep_queue_len = (const long long*)in->rep_queue_length; mi.rep_k2 = (const long long*)in->rep_k2;
+    mi.rep_avg_in = in->rep_avg_input_tokens; mi.rep_avg_out = in->rep_avg_output_tokens; mi.rep_hit = in->rep_prefix_hit_rate;
+    mi.slice_order = in->rep_slice_order;
+    mi.var_current = in->var_current + v0; mi.var_pending = in->var_pending + v0; mi.var_fallback = in->var_fallback_capacity + v0;
+    mi.kv_threshold = in->cfg_kv_threshold[m]; mi.scale_up_threshold = in->cfg_scale_up_threshold[m];
+    mi.scale_down_boundary = in->cfg_scale_down_boundary[m];
+    mi.has_queue = in->sched_queue_size != nullptr;
+    mi.queue_size = mi.has_queue ? in->sched_queue_size[m] : 0; mi.queue_bytes = mi.has_queue ? in->sched_queue_bytes[m] : 0;
+    ready.assign(V + 1, 0); a.assign(V + 1, 0); b.assign(V + 1, 0); c.assign(V + 1, 0); d.assign(V + 1, 0);
+    V2ModelOut mo;
+    mo.rep_k1 = (long long*)out->rep_k1; mo.rep_effective = (long long*)out->rep_effective; mo.rep_demand = (long long*)out->rep_demand;
+    mo.rep_saturated = out->rep_saturated;
+    mo.var_ready = ready.data(); mo.var_cap = a.data(); mo.var_total_cap = b.data(); mo.var_total_demand = c.data(); mo.var_util = d.data();
+    saturation_v2_model(mi, mo);
+    for (int v = 0; v < V; v++) {
+      if (out->var_ready) out->var_ready[v0 + v] = ready[v];
+      if (out->var_per_replica_capacity) out->var_per_replica_capacity[v0 + v] = a[v];
+      if (out->var_total_capacity) out->var_total_capacity[v0 + v] = b[v];
+      if (out->var_total_demand) out->var_total_demand[v0 + v] = c[v];
+      if (out->var_utilization) out->var_utilization[v0 + v] = d[v];
+    }
+    if (out->mod_total_supply) out->mod_total_supply[m] = mo.total_supply;
+    if (out->mod_total_demand) out->mod_total_demand[m] = mo.total_demand;
+    if (out->mod_utilization) out->mod_utilization[m] = mo.utilization;
+    if (out->mod_required_capacity) out->mod_required_capacity[m] = mo.required;
+    if (out->mod_spare_capacity) out->mod_spare_capacity[m] = mo.spare;
+  }
+  return 0;
+}
+
+int oracle_cost_aware_optimize(int64_t M, int64_t V, const int32_t* mvo, const double* required, const double* spare,
+                               const uint8_t* has_result, const int32_t* current, const double* cost, const double* cap,
+                               int32_t* target) {
+  (void)V;
+  for (int64_t m = 0; m < M; m++) {
+    const int v0 = mvo[m], v1 = mvo[m + 1];
+    if (has_result && !has_result[m]) { for (int v = v0; v < v1; v++) target[v] = -1; continue; }
+    oracle_v2::cost_aware_model(v1 - v0, required[m], spare[m], current + v0, cost + v0, cap + v0, target + v0);
+  }
+  return 0;
+}
+
+int oracle_enforce(int64_t M, int64_t V, const int32_t* mvo, const uint8_t* s2z, const double* request_count,
+                   const uint8_t* request_error, const double* cost, const uint8_t* has_cost, int32_t* target, uint8_t* applied) {
+  (void)V;
+  for (int64_t m = 0; m < M; m++) {
+    const int v0 = mvo[m], v1 = mvo[m + 1];
+    const bool app = oracle_v2::enforce_model(v1 - v0, target + v0, cost + v0, has_cost ? has_cost + v0 : nullptr, s2z[m] != 0,
+                                              request_count[m], request_error && request_error[m]);
+    if (applied) applied[m] = app ? 1 : 0;
+  }
+  return 0;
+}
+
+long long oracle_estimate_capacity_from_params(long long max_batched_tokens, long long max_num_seqs, double avg_in, double avg_out) {
+  return oracle_v2::estimate_capacity_from_params(max_batched_tokens, max_num_seqs, avg_in, avg_out);
 }
 
 // ---- known-answer-test helpers (pin the oracle to the reference's own tests) ----

@@ -36,6 +36,11 @@ class Oracle:
         L.oracle_mm1k_eval.argtypes = [C.c_int64] + [C.c_void_p] * 11
         L.oracle_saturation_v1.argtypes = [C.POINTER(abi.SaturationIn), C.POINTER(abi.SaturationOut)]
         L.oracle_limit.argtypes = [C.c_int64, C.c_int] + [C.c_void_p] * 10
+        L.oracle_saturation_v2.argtypes = [C.POINTER(abi.SaturationV2In), C.POINTER(abi.SaturationV2Out)]
+        L.oracle_cost_aware_optimize.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 8
+        L.oracle_enforce.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 8
+        L.oracle_estimate_capacity_from_params.argtypes = [C.c_longlong, C.c_longlong, C.c_double, C.c_double]
+        L.oracle_estimate_capacity_from_params.restype = C.c_longlong
         for fn in ("oracle_prefill_time", "oracle_decode_time", "oracle_iteration_time"):
             getattr(L, fn).argtypes = [_f] * 6
             getattr(L, fn).restype = _f
@@ -124,6 +129,37 @@ class Oracle:
                               out["target"].ctypes.data, out["gpus_allocated"].ctypes.data,
                               out["was_limited"].ctypes.data)
         return {k: v[:D] for k, v in out.items()}
+
+    # ---- V2 pipeline -----------------------------------------------------------------------------
+    def saturation_v2(self, d):
+        ist, ost, keep, out = abi.make_saturation_v2(d)
+        assert self.lib.oracle_saturation_v2(C.byref(ist), C.byref(ost)) == 0
+        return out
+
+    def cost_aware_optimize(self, d):
+        g = lambda k, dt: None if d.get(k) is None else np.ascontiguousarray(d[k], dt).reshape(-1)
+        mvo, rq, sp = g("model_variant_off", np.int32), g("mod_required_capacity", np.float64), g("mod_spare_capacity", np.float64)
+        hr, cu, co, ca = g("mod_has_result", np.uint8), g("var_current", np.int32), g("var_cost", np.float64), g("var_per_replica_capacity", np.float64)
+        tgt = np.zeros(max(len(cu), 1), np.int32)
+        p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+        self.lib.oracle_cost_aware_optimize(len(rq), len(cu), p(mvo), p(rq), p(sp), p(hr), p(cu), p(co), p(ca), tgt.ctypes.data)
+        return tgt[:len(cu)]
+
+    def enforce(self, d):
+        g = lambda k, dt: None if d.get(k) is None else np.ascontiguousarray(d[k], dt).reshape(-1)
+        mvo, z, rc, re = g("model_variant_off", np.int32), g("mod_scale_to_zero_enabled", np.uint8), g("mod_request_count", np.float64), g("mod_request_error", np.uint8)
+        co, hc = g("var_cost", np.float64), g("var_has_cost", np.uint8)
+        tgt = np.ascontiguousarray(d["var_target"], np.int32).reshape(-1).copy()
+        V = tgt.size
+        if V == 0:
+            tgt = np.zeros(1, np.int32)
+        app = np.zeros(max(len(rc), 1), np.uint8)
+        p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+        self.lib.oracle_enforce(len(rc), V, p(mvo), p(z), p(rc), p(re), p(co), p(hc), tgt.ctypes.data, app.ctypes.data)
+        return tgt[:V], app[:len(rc)]
+
+    def estimate_capacity_from_params(self, max_batched_tokens, max_num_seqs, avg_in, avg_out):
+        return int(self.lib.oracle_estimate_capacity_from_params(int(max_batched_tokens), int(max_num_seqs), float(avg_in), float(avg_out)))
 
     # ---- KAT helpers ----------------------------------------------------------------------
     def prefill_time(self, a, b, g, i, o, n):

@@ -73,31 +73,52 @@ __global__ void __launch_bounds__(256) saturation_v2_kernel(SatV2In in, SatV2Out
       if (act) {
         const int lo = in.variant_replica_off[v], hi = in.variant_replica_off[v + 1];
         int n_data = 0;
-        for (int r = lo; r < hi; r++) {                                                // computeReplicaCapacity, slice order
-          long long k1, eff, demand;
-          const bool has = v2_replica(in, r, kv_thr, k1, eff, demand);
-          if (has) { n_data++; demand_sum = d_add(demand_sum, (double)demand); }       // :309-312
-          if (out.rep_k1) out.rep_k1[r] = k1;
-          if (out.rep_effective) out.rep_effective[r] = eff;
-          if (out.rep_demand) out.rep_demand[r] = demand;
-          if (out.rep_saturated) out.rep_saturated[r] = (has && demand >= eff) ? 1 : 0;   // :180
+        long long e8[8];                                                               // effective capacities of a small variant
+        const bool small = hi - lo <= 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) e8[j] = 0x7fffffffffffffffLL;
+        for (int r0 = lo; r0 < hi; r0 += 8) {                                          // computeReplicaCapacity, slice order
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int r = r0 + j;
+            if (r >= hi) break;
+            long long k1, eff, demand;
+            const bool has = v2_replica(in, r, kv_thr, k1, eff, demand);
+            if (has) { n_data++; demand_sum = d_add(demand_sum, (double)demand); if (small) e8[j] = eff; }   // :309-312
+            if (out.rep_k1) out.rep_k1[r] = k1;
+            if (out.rep_effective) out.rep_effective[r] = eff;
+            if (out.rep_demand) out.rep_demand[r] = demand;
+            if (out.rep_saturated) out.rep_saturated[r] = (has && demand >= eff) ? 1 : 0;   // :180
+          }
         }
         if (n_data > 0) {
-          // median (analyzer.go:505-519) by rank counting: no scratch, n is a handful.  The element of rank k is
-          // the one with exactly k elements before it in (value, index) order.
+          // median (analyzer.go:505-519) by rank counting: the element of rank k has exactly k elements before it in
+          // (value, index) order.  Up to 8 replicas: on the registers just filled (absent slots hold +inf and rank last);
+          // more: re-evaluating the replicas, no scratch.
           const int k_hi = n_data / 2, k_lo = (n_data % 2 == 0) ? k_hi - 1 : k_hi;
           long long m_lo = 0, m_hi = 0;
-          for (int r = lo; r < hi; r++) {
-            long long k1, e, d;
-            if (!v2_replica(in, r, kv_thr, k1, e, d)) continue;
-            int rank = 0;
-            for (int q = lo; q < hi; q++) {
-              long long k1q, eq, dq;
-              if (!v2_replica(in, q, kv_thr, k1q, eq, dq)) continue;
-              if (eq < e || (eq == e && q < r)) rank++;
+          if (small) {
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+              int rank = 0;
+#pragma unroll
+              for (int b = 0; b < 8; b++) rank += (e8[b] < e8[a] || (e8[b] == e8[a] && b < a)) ? 1 : 0;
+              if (rank == k_lo) m_lo = e8[a];
+              if (rank == k_hi) m_hi = e8[a];
             }
-            if (rank == k_lo) m_lo = e;
-            if (rank == k_hi) m_hi = e;
+          } else {
+            for (int r = lo; r < hi; r++) {
+              long long k1, e, d;
+              if (!v2_replica(in, r, kv_thr, k1, e, d)) continue;
+              int rank = 0;
+              for (int q = lo; q < hi; q++) {
+                long long k1q, eq, dq;
+                if (!v2_replica(in, q, kv_thr, k1q, eq, dq)) continue;
+                if (eq < e || (eq == e && q < r)) rank++;
+              }
+              if (rank == k_lo) m_lo = e;
+              if (rank == k_hi) m_hi = e;
+            }
           }
           cap = (double)((n_data % 2 == 0) ? (m_lo + m_hi) / 2 : m_hi);
         } else {

@@ -26,6 +26,8 @@ import (
 	"sort"
 	"unsafe"
 
+	intconfig "github.com/llm-d/llm-d-workload-variant-autoscaler/internal/config"
+	"github.com/llm-d/llm-d-workload-variant-autoscaler/internal/engines/pipeline"
 	"github.com/llm-d/llm-d-workload-variant-autoscaler/internal/interfaces"
 	"github.com/llm-d/llm-d-workload-variant-autoscaler/pkg/config"
 )
@@ -487,3 +489,134 @@ func stepReason(d *interfaces.VariantDecision) string {
 		return fmt.Sprintf("allocated %d GPUs for +%d replicas", d.GPUsAllocated, ch)
 	}
 }
+
+// ---- V2 pipeline (SURVEY 8f.1-2) ----------------------------------------------------------------------------------------
+//
+// CostAwareOptimizer satisfies pipeline.ScalingOptimizer (optimizer_interfaces.go:23-30) like the reference's
+// CostAwareOptimizer (cost_aware_optimizer.go:39-72): every model of the cycle in one launch.  Index space per model =
+// Result.VariantCapacities slice order (ties of the reference's unstable sorts resolve to it).
+type CostAwareOptimizer struct{ ctx *Ctx }
+
+func NewCostAwareOptimizer(ctx *Ctx) *CostAwareOptimizer { return &CostAwareOptimizer{ctx: ctx} }
+func (o *CostAwareOptimizer) Name() string                { return "cost-aware" }
+
+func (o *CostAwareOptimizer) Optimize(ctx context.Context, reqs []pipeline.ModelScalingRequest,
+	_ []*pipeline.ResourceConstraints) []interfaces.VariantDecision {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	mvo := []int32{0}
+	var required, spare, cost, capacity []float64
+	var has []uint8
+	var cur []int32
+	for _, r := range reqs {
+		st := map[string]interfaces.VariantReplicaState{}
+		for _, s := range r.VariantStates {
+			st[s.VariantName] = s
+		}
+		if r.Result != nil {
+			for _, vc := range r.Result.VariantCapacities {
+				cur = append(cur, int32(st[vc.VariantName].CurrentReplicas))
+				cost, capacity = append(cost, vc.Cost), append(capacity, vc.PerReplicaCapacity)
+			}
+			required, spare, has = append(required, r.Result.RequiredCapacity), append(spare, r.Result.SpareCapacity), append(has, 1)
+		} else {
+			required, spare, has = append(required, 0), append(spare, 0), append(has, 0)
+		}
+		mvo = append(mvo, int32(len(cur)))
+	}
+	target := make([]int32, len(cur))
+	rc := C.wva_cost_aware_optimize(o.ctx.c, C.int64_t(len(reqs)), C.int64_t(len(cur)), (*C.int32_t)(unsafe.Pointer(&mvo[0])),
+		(*C.double)(ptrOrNil(required)), (*C.double)(ptrOrNil(spare)), (*C.uint8_t)(ptrOrNil(has)), (*C.int32_t)(ptrOrNil(cur)),
+		(*C.double)(ptrOrNil(cost)), (*C.double)(ptrOrNil(capacity)), (*C.int32_t)(ptrOrNil(target)))
+	if o.ctx.err(rc, "wva_cost_aware_optimize") != nil {
+		return nil // the engine's safety net emits the previous decisions (engine.go:1022-1095)
+	}
+	var out []interfaces.VariantDecision
+	for m, r := range reqs {
+		if r.Result == nil {
+			continue
+		}
+		st := map[string]interfaces.VariantReplicaState{}
+		for _, s := range r.VariantStates {
+			st[s.VariantName] = s
+		}
+		for k, vc := range r.Result.VariantCapacities {
+			t, c := int(target[int(mvo[m])+k]), st[vc.VariantName].CurrentReplicas
+			d := interfaces.VariantDecision{VariantName: vc.VariantName, ModelID: r.ModelID, Namespace: r.Namespace,
+				AcceleratorName: vc.AcceleratorName, Cost: vc.Cost, CurrentReplicas: c, TargetReplicas: t}
+			switch { // buildDecisions, cost_aware_optimizer.go:241-276
+			case t > c:
+				d.Action, d.Reason = interfaces.ActionScaleUp, fmt.Sprintf("V2 scale-up (optimizer: cost-aware, required: %.0f)", r.Result.RequiredCapacity)
+			case t < c:
+				d.Action, d.Reason = interfaces.ActionScaleDown, fmt.Sprintf("V2 scale-down (optimizer: cost-aware, spare: %.0f)", r.Result.SpareCapacity)
+			default:
+				d.Action, d.Reason = interfaces.ActionNoChange, "V2 steady state"
+			}
+			out = append(out, d)
+		}
+	}
+	return out
+}
+
+// Enforcer mirrors pipeline.Enforcer.EnforcePolicy (enforcer.go:55-83).  The request-count lookup and the
+// scale-to-zero configuration stay in Go; index order = ascending variant name (the tie-break compares names).
+type Enforcer struct {
+	ctx          *Ctx
+	requestCount pipeline.RequestCountFuncType
+}
+
+func NewEnforcer(ctx *Ctx, f pipeline.RequestCountFuncType) *Enforcer { return &Enforcer{ctx: ctx, requestCount: f} }
+
+func (e *Enforcer) EnforcePolicy(ctx context.Context, modelID, namespace string, targets map[string]int,
+	analyses []interfaces.VariantSaturationAnalysis, s2z intconfig.ScaleToZeroConfigData) (map[string]int, bool) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	names := make([]string, 0, len(targets))
+	for n := range targets {
+		names = append(names, n)
+	}
+	sort.Strings(names)
+	costOf := map[string]float64{}
+	for _, va := range analyses {
+		costOf[va.VariantName] = va.Cost
+	}
+	enabled := intconfig.IsScaleToZeroEnabled(s2z, modelID)
+	var count float64
+	var failed uint8
+	if enabled {
+		c, err := e.requestCount(ctx, modelID, namespace, intconfig.ScaleToZeroRetentionPeriod(s2z, modelID))
+		if err != nil {
+			failed = 1
+		}
+		count = c
+	}
+	mvo := []int32{0, int32(len(names))}
+	cost, has, tgt := make([]float64, len(names)), make([]uint8, len(names)), make([]int32, len(names))
+	for i, n := range names {
+		if c, ok := costOf[n]; ok {
+			cost[i], has[i] = c, 1
+		}
+		tgt[i] = int32(targets[n])
+	}
+	on := uint8(0)
+	if enabled {
+		on = 1
+	}
+	var applied uint8
+	rc := C.wva_enforce(e.ctx.c, 1, C.int64_t(len(names)), (*C.int32_t)(unsafe.Pointer(&mvo[0])), (*C.uint8_t)(unsafe.Pointer(&on)),
+		(*C.double)(unsafe.Pointer(&count)), (*C.uint8_t)(unsafe.Pointer(&failed)), (*C.double)(ptrOrNil(cost)),
+		(*C.uint8_t)(ptrOrNil(has)), (*C.int32_t)(ptrOrNil(tgt)), (*C.uint8_t)(unsafe.Pointer(&applied)))
+	if e.ctx.err(rc, "wva_enforce") != nil {
+		return targets, false
+	}
+	for i, n := range names {
+		targets[n] = int(tgt[i])
+	}
+	return targets, applied != 0
+}
+
+// The V2 analyzer wrapper (`wva_saturation_v2`) belongs INSIDE package saturation_v2: the k2 priority chain, its
+// rolling history and the capacity store are unexported there (analyzer.go:17-24, history.go, capacity_store.go) and
+// stay as they are; `computeReplicaCapacity` keeps calling `computeK2` and the store, the five arithmetic lines around
+// them and `aggregateByVariant`'s sums / median move behind the call.  `pipeline.py SaturationAnalyzerV2` is the
+// executable statement of that split.

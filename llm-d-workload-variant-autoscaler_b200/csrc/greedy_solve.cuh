@@ -104,6 +104,9 @@ __global__ void __launch_bounds__(128) greedy_prepare_kernel(SysView s, CandView
     w.r_nrep[p + j] = live ? c.num_replicas[p + a] : 0;
     w.r_upr[p + j] = live ? (long long)num_instances(s, s.srv_model[srv], a) * s.acc_multiplicity[a] : 0;   // greedy.go:139
   }
+  for (int j = n; j < A; j++) {   // ranks past the list are read (and masked) by the 32-wide record loads of the sweep
+    w.r_kd[p + j] = 0; w.r_kv[p + j] = 0; w.r_type[p + j] = -1; w.r_nrep[p + j] = 0; w.r_upr[p + j] = 0;
+  }
   w.ncand[srv] = n;
   w.kind[srv] = 0;
   w.flag[srv] = n > 0 ? 1 : 0;

@@ -390,6 +390,18 @@ int32_t wva_enforce(wva_ctx* ctx, int64_t n_models, int64_t n_variants, const in
                     const uint8_t* mod_request_error /* or NULL */, const double* var_cost,
                     const uint8_t* var_has_cost /* or NULL */, int32_t* var_target, uint8_t* mod_applied);
 
+/*
+ * The three V2 stages for every model of a cycle in one call: wva_saturation_v2 -> wva_cost_aware_optimize (every
+ * model has a result) -> wva_enforce, chained on the device — one upload of the metrics, three launches, one download
+ * of the decisions.  What engine_v2.go / engine.go:461-520 does model by model through maps.  Index space =
+ * VariantStates order; var_name_rank[v] = rank of the variant's name within its model (the enforcer's tie-break
+ * compares names, enforcer.go:161), NULL when the states are already in name order.  `out` (or any member) may be NULL.
+ */
+int32_t wva_pipeline_v2(wva_ctx* ctx, const wva_saturation_v2_in* in, const double* var_cost, const int32_t* var_name_rank,
+                        const uint8_t* mod_scale_to_zero_enabled, const double* mod_request_count,
+                        const uint8_t* mod_request_error /* or NULL */, const wva_saturation_v2_out* out,
+                        int32_t* var_target, uint8_t* mod_applied /* or NULL */);
+
 /* ---- observability -------------------------------------------------------- */
 int32_t wva_last_timing(const wva_ctx* ctx, wva_timing* out);
 

@@ -555,7 +555,7 @@ extern "C" int32_t wva_enforce(wva_ctx* ctx, int64_t n_models, int64_t n_variant
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   enforce_kernel<<<warp_grid(ctx, n_models), 256, 0, ctx->stream>>>(n_models, s.at<int>(o_mvo, model_variant_off), s.at<unsigned char>(o_z, mod_s2z),
       s.at<double>(o_rc, mod_request_count), s.at<unsigned char>(o_re, mod_request_error), s.at<double>(o_co, var_cost),
-      s.at<unsigned char>(o_hc, var_has_cost), d_t, d_app);
+      s.at<unsigned char>(o_hc, var_has_cost), nullptr, d_t, d_app);
   ctx->launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -563,5 +563,93 @@ extern "C" int32_t wva_enforce(wva_ctx* ctx, int64_t n_models, int64_t n_variant
   if (mod_applied) CK(cudaMemcpyAsync(mod_applied, d_app, M, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->timing.limit_ms = elapsed(ctx, 2, 3);
+  return WVA_OK;
+}
+
+// analyzer -> cost-aware optimizer -> enforcer for every model of a cycle: one upload, three launches chained on the
+// device (the optimizer reads the analyzer's capacities and signals, the enforcer the optimizer's targets), one download
+extern "C" int32_t wva_pipeline_v2(wva_ctx* ctx, const wva_saturation_v2_in* in, const double* var_cost, const int32_t* var_name_rank,
+                                   const uint8_t* mod_s2z, const double* mod_request_count, const uint8_t* mod_request_error,
+                                   const wva_saturation_v2_out* out, int32_t* var_target, uint8_t* mod_applied) {
+  if (!ctx || !in || in->n_models < 0 || in->n_variants < 0 || in->n_replicas < 0) return WVA_ERR_ARG;
+  const size_t M = (size_t)in->n_models, V = (size_t)in->n_variants, P = (size_t)in->n_replicas;
+  if (M == 0) return WVA_OK;
+  if (in->n_variants > 0x7fffffffLL || in->n_replicas > 0x7fffffffLL) return WVA_ERR_LIMIT;
+  if (!in->model_variant_off || !in->variant_replica_off || !in->cfg_kv_threshold || !in->cfg_scale_up_threshold ||
+      !in->cfg_scale_down_boundary || !mod_s2z || !mod_request_count ||
+      (V && (!in->var_current || !in->var_pending || !in->var_fallback_capacity || !var_cost || !var_target)) ||
+      (P && (!in->rep_total_kv_tokens || !in->rep_tokens_in_use || !in->rep_queue_length || !in->rep_avg_input_tokens ||
+             !in->rep_avg_output_tokens || !in->rep_prefix_hit_rate || !in->rep_k2)) ||
+      ((in->sched_queue_size == nullptr) != (in->sched_queue_bytes == nullptr)))
+    return WVA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  Stage s{ctx};
+  const size_t o_mvo = s.add(in->model_variant_off, (M + 1) * 4), o_vro = s.add(in->variant_replica_off, (V + 1) * 4),
+               o_tk = s.add(in->rep_total_kv_tokens, P * 8), o_tu = s.add(in->rep_tokens_in_use, P * 8),
+               o_ql = s.add(in->rep_queue_length, P * 8), o_ai = s.add(in->rep_avg_input_tokens, P * 8),
+               o_ao = s.add(in->rep_avg_output_tokens, P * 8), o_hr = s.add(in->rep_prefix_hit_rate, P * 8),
+               o_k2 = s.add(in->rep_k2, P * 8), o_so = s.add(in->rep_slice_order, P * 4), o_vc = s.add(in->var_current, V * 4),
+               o_vp = s.add(in->var_pending, V * 4), o_vf = s.add(in->var_fallback_capacity, V * 8),
+               o_kt = s.add(in->cfg_kv_threshold, M * 8), o_su = s.add(in->cfg_scale_up_threshold, M * 8),
+               o_sd = s.add(in->cfg_scale_down_boundary, M * 8), o_qs = s.add(in->sched_queue_size, M * 8),
+               o_qb = s.add(in->sched_queue_bytes, M * 8), o_co = s.add(var_cost, V * 8), o_nr = s.add(var_name_rank, V * 4),
+               o_z = s.add(mod_s2z, M), o_rc = s.add(mod_request_count, M * 8), o_re = s.add(mod_request_error, M);
+  int32_t rc = s.upload();
+  if (rc != WVA_OK) return rc;
+  Layout O;
+  const size_t q_k1 = O.take(P * 8), q_ef = O.take(P * 8), q_de = O.take(P * 8), q_sa = O.take(P), q_vr = O.take(V * 4),
+               q_vcap = O.take(V * 8), q_vt = O.take(V * 8), q_vd = O.take(V * 8), q_vu = O.take(V * 8), q_ms = O.take(M * 8),
+               q_md = O.take(M * 8), q_mu = O.take(M * 8), q_mr = O.take(M * 8), q_mp = O.take(M * 8), q_tg = O.take(V * 4),
+               q_ap = O.take(M);
+  CK(ctx->io_out.reserve(O.off + 256));
+  char* dd = (char*)ctx->io_out.p;
+  const wva_saturation_v2_out none = {};
+  const wva_saturation_v2_out& w = out ? *out : none;
+  SatV2In di;
+  di.n_models = in->n_models; di.n_variants = in->n_variants; di.n_replicas = in->n_replicas;
+  di.model_variant_off = s.at<int>(o_mvo, in->model_variant_off); di.variant_replica_off = s.at<int>(o_vro, in->variant_replica_off);
+  di.rep_total_kv = s.at<long long>(o_tk, in->rep_total_kv_tokens); di.rep_tokens_in_use = s.at<long long>(o_tu, in->rep_tokens_in_use);
+  di.rep_queue_len = s.at<long long>(o_ql, in->rep_queue_length); di.rep_k2 = s.at<long long>(o_k2, in->rep_k2);
+  di.rep_avg_in = s.at<double>(o_ai, in->rep_avg_input_tokens); di.rep_avg_out = s.at<double>(o_ao, in->rep_avg_output_tokens);
+  di.rep_hit = s.at<double>(o_hr, in->rep_prefix_hit_rate); di.rep_slice_order = s.at<int>(o_so, in->rep_slice_order);
+  di.var_current = s.at<int>(o_vc, in->var_current); di.var_pending = s.at<int>(o_vp, in->var_pending);
+  di.var_fallback = s.at<double>(o_vf, in->var_fallback_capacity);
+  di.cfg_kv_threshold = s.at<double>(o_kt, in->cfg_kv_threshold); di.cfg_scale_up = s.at<double>(o_su, in->cfg_scale_up_threshold);
+  di.cfg_scale_down = s.at<double>(o_sd, in->cfg_scale_down_boundary);
+  di.sched_size = s.at<long long>(o_qs, in->sched_queue_size); di.sched_bytes = s.at<long long>(o_qb, in->sched_queue_bytes);
+  SatV2Out dout;
+  dout.rep_k1 = w.rep_k1 ? (long long*)(dd + q_k1) : nullptr; dout.rep_effective = w.rep_effective ? (long long*)(dd + q_ef) : nullptr;
+  dout.rep_demand = w.rep_demand ? (long long*)(dd + q_de) : nullptr; dout.rep_saturated = w.rep_saturated ? (unsigned char*)(dd + q_sa) : nullptr;
+  dout.var_ready = w.var_ready ? (int*)(dd + q_vr) : nullptr;
+  dout.var_cap = (double*)(dd + q_vcap);                                       // always: the optimizer reads it
+  dout.var_total_cap = w.var_total_capacity ? (double*)(dd + q_vt) : nullptr; dout.var_total_demand = w.var_total_demand ? (double*)(dd + q_vd) : nullptr;
+  dout.var_util = w.var_utilization ? (double*)(dd + q_vu) : nullptr;
+  dout.mod_supply = w.mod_total_supply ? (double*)(dd + q_ms) : nullptr; dout.mod_demand = w.mod_total_demand ? (double*)(dd + q_md) : nullptr;
+  dout.mod_util = w.mod_utilization ? (double*)(dd + q_mu) : nullptr;
+  dout.mod_required = (double*)(dd + q_mr); dout.mod_spare = (double*)(dd + q_mp);   // always
+  int* d_t = (int*)(dd + q_tg);
+  unsigned char* d_app = (unsigned char*)(dd + q_ap);
+  const unsigned grid = warp_grid(ctx, in->n_models);
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  saturation_v2_kernel<<<grid, 256, 0, ctx->stream>>>(di, dout);
+  cost_aware_kernel<<<grid, 256, 0, ctx->stream>>>(in->n_models, di.model_variant_off, dout.mod_required, dout.mod_spare, nullptr,
+                                                   di.var_current, s.at<double>(o_co, var_cost), dout.var_cap, d_t);
+  enforce_kernel<<<grid, 256, 0, ctx->stream>>>(in->n_models, di.model_variant_off, s.at<unsigned char>(o_z, mod_s2z),
+                                                s.at<double>(o_rc, mod_request_count), s.at<unsigned char>(o_re, mod_request_error),
+                                                s.at<double>(o_co, var_cost), nullptr, s.at<int>(o_nr, var_name_rank), d_t, d_app);
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  auto back = [&](void* host, size_t off, size_t bytes) -> cudaError_t {
+    return (host && bytes) ? cudaMemcpyAsync(host, dd + off, bytes, cudaMemcpyDeviceToHost, ctx->stream) : cudaSuccess;
+  };
+  CK(back(w.rep_k1, q_k1, P * 8)); CK(back(w.rep_effective, q_ef, P * 8)); CK(back(w.rep_demand, q_de, P * 8));
+  CK(back(w.rep_saturated, q_sa, P)); CK(back(w.var_ready, q_vr, V * 4)); CK(back(w.var_per_replica_capacity, q_vcap, V * 8));
+  CK(back(w.var_total_capacity, q_vt, V * 8)); CK(back(w.var_total_demand, q_vd, V * 8)); CK(back(w.var_utilization, q_vu, V * 8));
+  CK(back(w.mod_total_supply, q_ms, M * 8)); CK(back(w.mod_total_demand, q_md, M * 8)); CK(back(w.mod_utilization, q_mu, M * 8));
+  CK(back(w.mod_required_capacity, q_mr, M * 8)); CK(back(w.mod_spare_capacity, q_mp, M * 8));
+  CK(back(var_target, q_tg, V * 4)); CK(back(mod_applied, q_ap, M));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.saturation_ms = elapsed(ctx, 2, 3);
   return WVA_OK;
 }

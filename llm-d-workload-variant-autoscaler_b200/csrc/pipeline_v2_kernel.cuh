@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) cost_aware_kernel(long long n_models, con
 // ---- Enforcer ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) enforce_kernel(long long n_models, const int* mvo, const unsigned char* s2z, const double* req_count,
                                                       const unsigned char* req_err, const double* cost, const unsigned char* has_cost,
-                                                      int* target, unsigned char* applied) {
+                                                      const int* name_rank, int* target, unsigned char* applied) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -306,17 +306,19 @@ __global__ void __launch_bounds__(256) enforce_kernel(long long n_models, const 
       total = __reduce_add_sync(full, (unsigned)(total > 0 ? 1 : 0));
       if (total == 0) {
         // the reference's running "cheapestCost < 0 || cost < cheapestCost || tie -> smaller name" walk, in index order
-        int cheapest = -1; double cc = -1.0;
+        // (name_rank: the variants' ranks by name when the index order is not the name order — fused pipeline)
+        int cheapest = -1, cheapest_rank = -1; double cc = -1.0;
         for (int c0 = v0; c0 < v1; c0 += 32) {
           const int v = c0 + lane;
           const bool in_map = v < v1 && target[v] >= 0;
           const double c = in_map ? ((has_cost && !has_cost[v]) ? 10.0 : cost[v]) : 0.0;   // saturation.DefaultVariantCost
+          const int rk = in_map ? (name_rank ? name_rank[v] : v) : 0;
           unsigned mask = __ballot_sync(full, in_map);
           for (; mask; mask &= mask - 1) {
             const int src = __ffs(mask) - 1;
             const double sc = shfl_d(full, c, src);
-            const int sv = c0 + src;
-            if (cc < 0 || sc < cc || (sc == cc && sv < cheapest)) { cheapest = sv; cc = sc; }
+            const int sr = __shfl_sync(full, rk, src);
+            if (cc < 0 || sc < cc || (sc == cc && sr < cheapest_rank)) { cheapest = c0 + src; cheapest_rank = sr; cc = sc; }
           }
         }
         if (cheapest >= 0) { if (lane == 0) target[cheapest] = 1; app = true; }

@@ -76,6 +76,7 @@ def load_library():
     L.wva_saturation_v2.argtypes = [ctxp, C.POINTER(abi.SaturationV2In), C.POINTER(abi.SaturationV2Out)]
     L.wva_cost_aware_optimize.argtypes = [ctxp, C.c_int64, C.c_int64] + [C.c_void_p] * 8
     L.wva_enforce.argtypes = [ctxp, C.c_int64, C.c_int64] + [C.c_void_p] * 8
+    L.wva_pipeline_v2.argtypes = [ctxp, C.POINTER(abi.SaturationV2In)] + [C.c_void_p] * 5 + [C.POINTER(abi.SaturationV2Out), C.c_void_p, C.c_void_p]
     L.wva_last_timing.argtypes = [ctxp, C.POINTER(abi.Timing)]
     L.wva_microbench_fp64.argtypes = [ctxp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
@@ -86,7 +87,7 @@ EXPORTS = ["wva_set_option", "wva_create", "wva_destroy", "wva_strerror", "wva_l
            "wva_load_system", "wva_calculate", "wva_solve", "wva_get_candidates", "wva_get_solution",
            "wva_analyze_grid", "wva_grid_run", "wva_grid_fetch", "wva_mm1k_eval", "wva_saturation_v1",
            "wva_saturation_upload", "wva_saturation_run", "wva_saturation_fetch", "wva_limit", "wva_saturation_v2",
-           "wva_cost_aware_optimize", "wva_enforce", "wva_last_timing",
+           "wva_cost_aware_optimize", "wva_enforce", "wva_pipeline_v2", "wva_last_timing",
            "wva_microbench_fp64"]
 
 
@@ -265,6 +266,19 @@ class Engine:
                                          p("mod_request_error"), p("var_cost"), p("var_has_cost"), tgt.ctypes.data, app.ctypes.data),
                     "wva_enforce")
         return tgt[:V], app[:M]
+
+    def pipeline_v2(self, d: dict, var_cost, mod_scale_to_zero_enabled, mod_request_count, mod_request_error=None, var_name_rank=None):
+        """analyzer -> cost-aware optimizer -> enforcer chained on the device; returns (analyzer outputs, targets, applied)."""
+        ist, ost, keep, out = abi.make_saturation_v2(d)
+        V, M = int(d["n_variants"]), int(d["n_models"])
+        arr = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt).reshape(-1)
+        co, rk = arr(var_cost, np.float64), arr(var_name_rank, np.int32)
+        z, rc, re = arr(mod_scale_to_zero_enabled, np.uint8), arr(mod_request_count, np.float64), arr(mod_request_error, np.uint8)
+        tgt, app = np.zeros(max(V, 1), np.int32), np.zeros(max(M, 1), np.uint8)
+        p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+        self._check(self.lib.wva_pipeline_v2(self.ctx, C.byref(ist), p(co), p(rk), p(z), p(rc), p(re), C.byref(ost), tgt.ctypes.data,
+                                             app.ctypes.data), "wva_pipeline_v2")
+        return out, tgt[:V], app[:M]
 
     # ---- observability ------------------------------------------------------------------------
     def timing(self) -> dict:

@@ -258,6 +258,19 @@ int oracle_cost_aware_optimize(int64_t M, int64_t V, const int32_t* mvo, const d
   return 0;
 }
 
+int oracle_enforce_ranked(int64_t M, int64_t V, const int32_t* mvo, const uint8_t* s2z, const double* request_count,
+                          const uint8_t* request_error, const double* cost, const uint8_t* has_cost, const int32_t* name_rank,
+                          int32_t* target, uint8_t* applied) {
+  (void)V;
+  for (int64_t m = 0; m < M; m++) {
+    const int v0 = mvo[m], v1 = mvo[m + 1];
+    const bool app = oracle_v2::enforce_model(v1 - v0, target + v0, cost + v0, has_cost ? has_cost + v0 : nullptr, s2z[m] != 0,
+                                              request_count[m], request_error && request_error[m], name_rank ? name_rank + v0 : nullptr);
+    if (applied) applied[m] = app ? 1 : 0;
+  }
+  return 0;
+}
+
 int oracle_enforce(int64_t M, int64_t V, const int32_t* mvo, const uint8_t* s2z, const double* request_count,
                    const uint8_t* request_error, const double* cost, const uint8_t* has_cost, int32_t* target, uint8_t* applied) {
   (void)V;

@@ -67,7 +67,7 @@ static inline void cost_aware_model(int V, double required, double spare, const 
 
 // One model.  target in/out (-1 = the variant is not in the targets map).  Returns `applied`.  enforcer.go:55-183
 static inline bool enforce_model(int V, int* target, const double* cost, const unsigned char* has_cost, bool s2z_enabled,
-                                 double request_count, bool request_error) {
+                                 double request_count, bool request_error, const int* name_rank = nullptr) {
   if (s2z_enabled) {                                                       // applyScaleToZero :86-127
     if (request_error || request_count > 0) return false;
     for (int v = 0; v < V; v++) if (target[v] >= 0) target[v] = 0;
@@ -76,12 +76,13 @@ static inline bool enforce_model(int V, int* target, const double* cost, const u
   long long total = 0;                                                     // ensureMinimumReplicas :130-183
   for (int v = 0; v < V; v++) if (target[v] >= 0) total += target[v];
   if (total > 0) return false;
-  int cheapest = -1;
+  int cheapest = -1, cheapest_rank = -1;
   double cheapest_cost = -1.0;
   for (int v = 0; v < V; v++) {
     if (target[v] < 0) continue;
     const double c = (has_cost && !has_cost[v]) ? 10.0 : cost[v];          // saturation.DefaultVariantCost
-    if (cheapest_cost < 0 || c < cheapest_cost || (c == cheapest_cost && v < cheapest)) { cheapest = v; cheapest_cost = c; }
+    const int rk = name_rank ? name_rank[v] : v;                           // `variant < cheapestVariant` compares names (:161)
+    if (cheapest_cost < 0 || c < cheapest_cost || (c == cheapest_cost && rk < cheapest_rank)) { cheapest = v; cheapest_rank = rk; cheapest_cost = c; }
   }
   if (cheapest >= 0) { target[cheapest] = 1; return true; }
   return false;

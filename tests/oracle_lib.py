@@ -39,6 +39,7 @@ class Oracle:
         L.oracle_saturation_v2.argtypes = [C.POINTER(abi.SaturationV2In), C.POINTER(abi.SaturationV2Out)]
         L.oracle_cost_aware_optimize.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 8
         L.oracle_enforce.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 8
+        L.oracle_enforce_ranked.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 9
         L.oracle_estimate_capacity_from_params.argtypes = [C.c_longlong, C.c_longlong, C.c_double, C.c_double]
         L.oracle_estimate_capacity_from_params.restype = C.c_longlong
         for fn in ("oracle_prefill_time", "oracle_decode_time", "oracle_iteration_time"):
@@ -157,6 +158,21 @@ class Oracle:
         p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
         self.lib.oracle_enforce(len(rc), V, p(mvo), p(z), p(rc), p(re), p(co), p(hc), tgt.ctypes.data, app.ctypes.data)
         return tgt[:V], app[:len(rc)]
+
+    def pipeline_v2(self, d, var_cost, s2z, request_count, request_error=None, var_name_rank=None):
+        """the composition wva_pipeline_v2 must equal: analyzer -> optimizer (every model has a result) -> enforcer"""
+        out = self.saturation_v2(d)
+        tgt = self.cost_aware_optimize(dict(model_variant_off=d["model_variant_off"], mod_required_capacity=out["mod_required_capacity"],
+                                            mod_spare_capacity=out["mod_spare_capacity"], var_current=d["var_current"], var_cost=var_cost,
+                                            var_per_replica_capacity=out["var_per_replica_capacity"])).copy()
+        g = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt).reshape(-1)
+        mvo, z, rc, re, co, rk = g(d["model_variant_off"], np.int32), g(s2z, np.uint8), g(request_count, np.float64), g(request_error, np.uint8), g(var_cost, np.float64), g(var_name_rank, np.int32)
+        V = tgt.size
+        t = tgt if V else np.zeros(1, np.int32)
+        app = np.zeros(max(len(rc), 1), np.uint8)
+        p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+        self.lib.oracle_enforce_ranked(len(rc), V, p(mvo), p(z), p(rc), p(re), p(co), None, p(rk), t.ctypes.data, app.ctypes.data)
+        return out, t[:V], app[:len(rc)]
 
     def estimate_capacity_from_params(self, max_batched_tokens, max_num_seqs, avg_in, avg_out):
         return int(self.lib.oracle_estimate_capacity_from_params(int(max_batched_tokens), int(max_num_seqs), float(avg_in), float(avg_out)))

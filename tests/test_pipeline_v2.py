@@ -348,3 +348,35 @@ def test_v2_pipeline_end_to_end_device(pkg, engine, oracle):
     r2, d2, t2 = run(OracleEngine(oracle))
     assert r1 == r2 and d1 == d2 and t1 == t2
     assert r1["RequiredCapacity"] > 0 and t1["a-cheap"] >= 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,seed", [(1, 21), (700, 22), (15000, 23)])
+def test_fused_pipeline_equals_the_three_stages(engine, oracle, M, seed):
+    """wva_pipeline_v2 (one upload, three chained launches, one download) == the composition of the three stage calls,
+    on the device and on the oracle; variant names are NOT in index order (random name ranks)."""
+    d = random_v2_batch(M, seed)
+    g = np.random.default_rng(seed + 1000)
+    V = int(d["n_variants"])
+    cost = g.choice([1.0, 2.0, 2.0, 5.0, 10.0], V)
+    rank = np.zeros(V, np.int32)
+    mvo = d["model_variant_off"]
+    for m in range(M):
+        rank[mvo[m]:mvo[m + 1]] = g.permutation(mvo[m + 1] - mvo[m])
+    s2z = (g.random(M) < 0.4).astype(np.uint8)
+    cnt = np.where(g.random(M) < 0.5, 0.0, 3.0)
+    err = (g.random(M) < 0.1).astype(np.uint8)
+    go, gt, ga = engine.pipeline_v2(d, cost, s2z, cnt, err, rank)
+    oo, ot, oa = oracle.pipeline_v2(d, cost, s2z, cnt, err, rank)
+    assert np.array_equal(gt, ot) and np.array_equal(ga, oa)
+    for k in oo:
+        assert np.array_equal(_bits(go[k]), _bits(oo[k])), k
+    # and against the separate device calls (name order == index order when no ranks are given)
+    out = engine.saturation_v2(d)
+    t = engine.cost_aware_optimize(dict(model_variant_off=mvo, mod_required_capacity=out["mod_required_capacity"],
+                                        mod_spare_capacity=out["mod_spare_capacity"], var_current=d["var_current"], var_cost=cost,
+                                        var_per_replica_capacity=out["var_per_replica_capacity"]))
+    t2, a2 = engine.enforce(dict(model_variant_off=mvo, mod_scale_to_zero_enabled=s2z, mod_request_count=cnt, mod_request_error=err,
+                                 var_cost=cost, var_has_cost=None, var_target=t))
+    _, ft, fa = engine.pipeline_v2(d, cost, s2z, cnt, err, None)
+    assert np.array_equal(ft, t2) and np.array_equal(fa, a2)

@@ -256,7 +256,7 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        sizer_name = "sizer_warp_kernel" if S * A <= 148 * 80 else "sizer_lane_kernel"   # capi.cu wva_calculate
+        sizer_name = "sizer_warp_kernel" if S * A <= 148 * 32 else "sizer_lane_kernel"   # capi.cu wva_calculate
         if grid_ms >= calc_ms:
             dominant, dom_ms, alg_bytes, dom_states = "grid_kernel", grid_ms, S * A * R * ALG_BYTES_PER_EVAL, last["grid_states"]
         else:
@@ -281,8 +281,11 @@ def main():
                                  "(arithmetic intensity 1e3-1e5 flop/B, SURVEY 0.4): the meaningful bound is `fp64`"},
             "fp64": {"kernel": dominant, "achieved_ops_per_s": fp64_rate, "peak_dfma_per_s": dfma,
                      "peak_ddiv_per_s": ddiv, "frac_of_dfma_peak": fp64_rate / dfma,
-                     "note": "FP64-pipe ops = 9 x states visited (5 per pass-1 state, 13 per pass-2 state); "
-                             "DFMA / div.rn.f64 peaks measured in this run by wva_microbench_fp64"},
+                     "pipe_active_pct_ncu": (traffic.get("fp64_pipe_active_pct") or {}).get(dominant),
+                     "note": "achieved = ALGORITHMIC FP64-pipe ops (9 x live states: 5 per pass-1 state, 13-14 per pass-2 "
+                             "state) / kernel time; DFMA / div.rn.f64 peaks measured in this run by wva_microbench_fp64; "
+                             "pipe_active_pct_ncu = executed share from the ncu capture in profiles/ (lock-step lanes "
+                             "riding along execute ~2.5x the live states, DESIGN.md section 4)"},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ms2.item()) / args.steps},
             "gpu_launches": int(launches),

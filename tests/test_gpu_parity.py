@@ -65,6 +65,26 @@ def test_calculate_lane_kernel_matches_oracle(pkg, engine, oracle, S, A, N, stre
         assert _bit_equal(g[k], o[k]), k
 
 
+@pytest.mark.parametrize("mode", [2, 4, 5])
+@pytest.mark.parametrize("sort,gang", [(1, 0), (1, 1), (0, 1)])
+def test_queue_order_options_do_not_change_results(pkg, engine, oracle, mode, sort, gang):
+    """The probe-sorted queue (WVA_OPT_LENGTH_SORT) and gang refill (WVA_OPT_GANG_REFILL) only change the ORDER in which
+    the exact sizer visits the work items: every candidate stays bit-identical to the oracle."""
+    sysd = pkg.synth.queue_system(150, 8, 32, stream=81)
+    sysd["srv_max_batch"][::4] = 24              # two batch sizes: the sort key groups equal N
+    engine.set_option(1, mode); engine.set_option(2, sort); engine.set_option(3, gang)
+    try:
+        engine.load_system(sysd)
+        engine.calculate()
+        g = engine.candidates()
+    finally:
+        engine.set_option(1, 0); engine.set_option(2, 0); engine.set_option(3, 0)
+    o = oracle.calculate(sysd)
+    _cmp_candidates(g, o)
+    for k in F32_FIELDS:
+        assert _bit_equal(g[k], o[k]), k
+
+
 def test_baseline_config1_full_path(pkg, engine, oracle):
     """BASELINE config 1: 10 models x 4 variants x 32 levels, single class, unlimited."""
     sysd = pkg.synth.baseline_config(1)

@@ -91,8 +91,8 @@ struct wva_ctx {
   // queueing system
   bool loaded = false, calculated = false, solved = false;
   bool force_lane_sizer = false;
-  bool gang_refill = false;         // lock-step lane sizer: a warp refills only when all its lanes are idle (opt-in)
-  bool length_sort = false;         // lane sizer pulls items through the probe-sorted permutation (sizer_probe.cuh; opt-in)
+  int gang_refill = -1;             // lock-step lane sizer: a warp refills only when all its lanes are idle; -1 = by size
+  int length_sort = -1;             // lane sizer pulls items through the probe-sorted permutation (sizer_probe.cuh); -1 = by size
   int lane_sizer_mode = 2;   // 1 flattened, 2 lock-step (default), 3 lock-step with two chains per lane (slower: measured)
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
@@ -303,7 +303,13 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
     // length-sorted queue: float32 probe -> (N, expected chain length) keys -> descending radix sort of the item ids
     const unsigned* order = nullptr;
     const unsigned long long n_items = split ? 2 * n_pairs : n_pairs;
-    if (ctx->length_sort && n_items >= 64 && n_items < (1ull << 31)) {
+    // measured (r1, B200): the sorted queue + gang refill pays between ~130 and ~400 pairs per SM (the items then fill
+    // 1.5-5 waves and longest-first ordering shortens the tail: -18 % at 24 k pairs, -30 % at 48 k, -14 % at 56 k); below,
+    // every lane holds one item and the probe is pure overhead; above, the whole-pair kernel gains ~6 % before the probe
+    const bool by_size = n_pairs > (unsigned long long)ctx->sm_count * 130 && n_pairs <= (unsigned long long)ctx->sm_count * 400;
+    const bool do_sort = ctx->length_sort < 0 ? by_size : ctx->length_sort != 0;
+    const bool do_gang = ctx->gang_refill < 0 ? by_size : ctx->gang_refill != 0;
+    if (do_sort && n_items >= 64 && n_items < (1ull << 31)) {
       size_t tmp = 0;
       cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr,
                                                 (unsigned*)nullptr, (int)n_items, 0, 32, ctx->stream);
@@ -329,7 +335,7 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
                                          : sizer_lane_kernel<THREADS, SMEM, false, false>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list, sw, order, ctx->gang_refill ? 1 : 0);
+    k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list, sw, order, do_gang ? 1 : 0);
   }
   ctx->launches++;
   return cudaGetLastError();
@@ -354,8 +360,8 @@ int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
     if (value >= 1 && value <= 5) ctx->lane_sizer_mode = value;
     return WVA_OK;
   }
-  if (option == WVA_OPT_LENGTH_SORT) { ctx->length_sort = value != 0; return WVA_OK; }
-  if (option == WVA_OPT_GANG_REFILL) { ctx->gang_refill = value != 0; return WVA_OK; }
+  if (option == WVA_OPT_LENGTH_SORT) { ctx->length_sort = value < 0 ? -1 : (value != 0); return WVA_OK; }
+  if (option == WVA_OPT_GANG_REFILL) { ctx->gang_refill = value < 0 ? -1 : (value != 0); return WVA_OK; }
   return WVA_ERR_ARG;
 }
 

@@ -57,7 +57,7 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
   SizerLane z;
   z.m.N = 1; z.m.K = 11; z.m.mono = 0; z.m.mu_last = 1.0; z.m.r_last = 1.0;
   SolveStats st;
-  bool live = false, exhausted = false, first_wave = true;
+  bool live = false, exhausted = false;
   unsigned long long my_solves = 0, my_states = 0, my_slots = 0;
 
   while (true) {
@@ -69,16 +69,7 @@ sizer_lane_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
     const bool may_refill = !gang || !__any_sync(full, live);
     if (!live && !exhausted && may_refill) {
       while (true) {
-        // queue position: with a sorted queue the first wave is dealt statically, consecutive groups of 32 to
-        // DIFFERENT SMs (warp w of block b takes group w * gridDim + b), so the longest items do not share an SM;
-        // later positions come from the global counter
-        unsigned long long item;
-        if (order && first_wave) {
-          item = ((unsigned long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32ull + (unsigned)lane;
-          first_wave = false;
-        } else {
-          item = atomicAdd(&ctr->next_pair, 1ull) + (order ? (unsigned long long)gridDim.x * THREADS : 0ull);
-        }
+        unsigned long long item = atomicAdd(&ctr->next_pair, 1ull);
         if (item >= (SPLIT ? 2 * n_pairs : n_pairs)) { exhausted = true; break; }
         if (order) item = order[item];                 // length-sorted queue (sizer_probe.cuh)
         const unsigned long long pair = SPLIT ? (item >> 1) : item;

@@ -78,7 +78,7 @@ def test_queue_order_options_do_not_change_results(pkg, engine, oracle, mode, so
         engine.calculate()
         g = engine.candidates()
     finally:
-        engine.set_option(1, 0); engine.set_option(2, 0); engine.set_option(3, 0)
+        engine.set_option(1, 0); engine.set_option(2, -1); engine.set_option(3, -1)
     o = oracle.calculate(sysd)
     _cmp_candidates(g, o)
     for k in F32_FIELDS:

@@ -12,9 +12,9 @@ with pkg.Engine(0) as e:
     e.load_system(d)
     ref = None
     for mode in modes:
-        e.set_option(2, 0 if mode < 0 else 1)      # negative mode: natural order (length sort off)
+        e.set_option(2, 0 if mode < 0 else (1 if gang >= 0 else -1))      # negative mode: natural order; gang -1: library default
         mode = abs(mode)
-        e.set_option(3, gang)
+        e.set_option(3, gang if mode >= 0 else 0)
         e.set_option(1, mode)
         for rep in range(2):
             e.calculate()

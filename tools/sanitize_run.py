@@ -12,7 +12,7 @@ with pkg.Engine(0) as e:
     for mode in (2, 4, 5):
         e.set_option(1, mode)
         e.load_system(pkg.synth.queue_system(40, 6, 32, stream=6)); e.calculate()
-    e.set_option(2, 0); e.set_option(3, 0)
+    e.set_option(2, -1); e.set_option(3, -1)
     e.set_option(1, 0)
     e.solve(); un = e.solution()
     e.analyze_grid(40)

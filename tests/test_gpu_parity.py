@@ -85,6 +85,24 @@ def test_queue_order_options_do_not_change_results(pkg, engine, oracle, mode, so
         assert _bit_equal(g[k], o[k]), k
 
 
+@pytest.mark.parametrize("mode", [1, 2, 4, 5])
+def test_lane_kernels_with_the_table_in_global_memory(pkg, engine, oracle, mode):
+    """N = 1200: 64 lanes x 4.8 KB of head table do not fit in shared memory, the lane kernels keep their float32 table
+    columns in global memory (launch_sizer<256, false>); same bar."""
+    sysd = pkg.synth.queue_system(6, 3, 1200, stream=83)
+    engine.set_option(1, mode)
+    try:
+        engine.load_system(sysd)
+        engine.calculate()
+        g = engine.candidates()
+    finally:
+        engine.set_option(1, 0)
+    o = oracle.calculate(sysd)
+    _cmp_candidates(g, o)
+    for k in F32_FIELDS:
+        assert _bit_equal(g[k], o[k]), k
+
+
 def test_baseline_config1_full_path(pkg, engine, oracle):
     """BASELINE config 1: 10 models x 4 variants x 32 levels, single class, unlimited."""
     sysd = pkg.synth.baseline_config(1)

@@ -16,6 +16,15 @@ static cudaError_t launch_grid(wva_ctx* ctx, int blocks, size_t smem, int R, con
 
 // Runs the grid on the resident system and keeps the results in HBM.
 // full != 0 materialises ok/ttft/itl/rho/tput [S*A*R]; the frontier [S*A] is always produced.
+namespace {
+// CSR offsets as every batched entry point takes them: off[0] == 0, non-decreasing, off[n] == total
+inline bool valid_offsets(const int32_t* off, size_t n, size_t total) {
+  if (!off || off[0] != 0 || (size_t)off[n] != total) return false;
+  for (size_t i = 0; i < n; i++) if (off[i + 1] < off[i]) return false;
+  return true;
+}
+}  // namespace
+
 extern "C" int32_t wva_grid_run(wva_ctx* ctx, int32_t R, int32_t full) {
   if (!ctx || R < 1) return WVA_ERR_ARG;
   if (!ctx->loaded) { ctx->last_error = "wva_grid_run before wva_load_system"; return WVA_ERR_STATE; }
@@ -141,9 +150,10 @@ extern "C" int32_t wva_saturation_upload(wva_ctx* ctx, const wva_saturation_in* 
   const long long M = in->n_models, V = in->n_variants, P = in->n_replicas;
   if (M < 0 || V < 0 || P < 0 || P > 0x7fffffffLL || V > 0x7fffffffLL) return WVA_ERR_ARG;
   if (!in->model_variant_off || !in->variant_replica_off) return WVA_ERR_ARG;
-  if (in->model_variant_off[0] != 0 || in->model_variant_off[M] != V || in->variant_replica_off[0] != 0 ||
-      in->variant_replica_off[V] != P)
+  if (!valid_offsets(in->model_variant_off, (size_t)M, (size_t)V) || !valid_offsets(in->variant_replica_off, (size_t)V, (size_t)P)) {
+    ctx->last_error = "model_variant_off / variant_replica_off are not CSR offsets of the given sizes";
     return WVA_ERR_ARG;
+  }
   CK(cudaSetDevice(ctx->device));
   SatState& st = ctx->sat;
   Layout L;
@@ -446,6 +456,16 @@ extern "C" int32_t wva_saturation_v2(wva_ctx* ctx, const wva_saturation_v2_in* i
              !in->rep_avg_output_tokens || !in->rep_prefix_hit_rate || !in->rep_k2)) ||
       ((in->sched_queue_size == nullptr) != (in->sched_queue_bytes == nullptr)))
     return WVA_ERR_ARG;
+  if (!valid_offsets(in->model_variant_off, M, V) || !valid_offsets(in->variant_replica_off, V, P)) {
+    ctx->last_error = "model_variant_off / variant_replica_off are not CSR offsets of the given sizes";
+    return WVA_ERR_ARG;
+  }
+  if (in->rep_slice_order)
+    for (size_t m = 0; m < M; m++) {
+      const int32_t a = in->variant_replica_off[in->model_variant_off[m]], b = in->variant_replica_off[in->model_variant_off[m + 1]];
+      for (int32_t k = a; k < b; k++)
+        if (in->rep_slice_order[k] < a || in->rep_slice_order[k] >= b) { ctx->last_error = "rep_slice_order leaves its model"; return WVA_ERR_ARG; }
+    }
   CK(cudaSetDevice(ctx->device));
   Stage s{ctx};
   const size_t o_mvo = s.add(in->model_variant_off, (M + 1) * 4), o_vro = s.add(in->variant_replica_off, (V + 1) * 4),
@@ -513,6 +533,7 @@ extern "C" int32_t wva_cost_aware_optimize(wva_ctx* ctx, int64_t n_models, int64
   if (n_variants > 0x7fffffffLL) return WVA_ERR_LIMIT;
   if (!model_variant_off || !mod_required || !mod_spare || (n_variants && (!var_current || !var_cost || !var_cap || !var_target)))
     return WVA_ERR_ARG;
+  if (!valid_offsets(model_variant_off, (size_t)n_models, (size_t)n_variants)) { ctx->last_error = "model_variant_off is not a CSR offset array"; return WVA_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   const size_t M = (size_t)n_models, V = (size_t)n_variants;
   Stage s{ctx};
@@ -542,6 +563,7 @@ extern "C" int32_t wva_enforce(wva_ctx* ctx, int64_t n_models, int64_t n_variant
   if (n_models == 0) return WVA_OK;
   if (n_variants > 0x7fffffffLL) return WVA_ERR_LIMIT;
   if (!model_variant_off || !mod_s2z || !mod_request_count || (n_variants && (!var_cost || !var_target))) return WVA_ERR_ARG;
+  if (!valid_offsets(model_variant_off, (size_t)n_models, (size_t)n_variants)) { ctx->last_error = "model_variant_off is not a CSR offset array"; return WVA_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   const size_t M = (size_t)n_models, V = (size_t)n_variants;
   Stage s{ctx};
@@ -582,6 +604,16 @@ extern "C" int32_t wva_pipeline_v2(wva_ctx* ctx, const wva_saturation_v2_in* in,
              !in->rep_avg_output_tokens || !in->rep_prefix_hit_rate || !in->rep_k2)) ||
       ((in->sched_queue_size == nullptr) != (in->sched_queue_bytes == nullptr)))
     return WVA_ERR_ARG;
+  if (!valid_offsets(in->model_variant_off, M, V) || !valid_offsets(in->variant_replica_off, V, P)) {
+    ctx->last_error = "model_variant_off / variant_replica_off are not CSR offsets of the given sizes";
+    return WVA_ERR_ARG;
+  }
+  if (in->rep_slice_order)
+    for (size_t m = 0; m < M; m++) {
+      const int32_t a = in->variant_replica_off[in->model_variant_off[m]], b = in->variant_replica_off[in->model_variant_off[m + 1]];
+      for (int32_t k = a; k < b; k++)
+        if (in->rep_slice_order[k] < a || in->rep_slice_order[k] >= b) { ctx->last_error = "rep_slice_order leaves its model"; return WVA_ERR_ARG; }
+    }
   CK(cudaSetDevice(ctx->device));
   Stage s{ctx};
   const size_t o_mvo = s.add(in->model_variant_off, (M + 1) * 4), o_vro = s.add(in->variant_replica_off, (V + 1) * 4),

@@ -380,3 +380,21 @@ def test_fused_pipeline_equals_the_three_stages(engine, oracle, M, seed):
                                  var_cost=cost, var_has_cost=None, var_target=t))
     _, ft, fa = engine.pipeline_v2(d, cost, s2z, cnt, err, None)
     assert np.array_equal(ft, t2) and np.array_equal(fa, a2)
+
+
+@pytest.mark.gpu
+def test_v2_entry_points_reject_malformed_offsets(pkg, engine):
+    d = random_v2_batch(20, 31)
+    bad = dict(d); bad["variant_replica_off"] = d["variant_replica_off"].copy(); bad["variant_replica_off"][3] = 10**6
+    with pytest.raises(pkg.WvaError):
+        engine.saturation_v2(bad)
+    bad = dict(d); bad["rep_slice_order"] = d["rep_slice_order"].copy()
+    if bad["rep_slice_order"].size:
+        bad["rep_slice_order"][0] = int(d["n_replicas"]) - 1 if d["variant_replica_off"][d["model_variant_off"][1]] < d["n_replicas"] - 1 else 0
+        bad["rep_slice_order"][0] = int(d["n_replicas"]) + 5
+        with pytest.raises(pkg.WvaError):
+            engine.saturation_v2(bad)
+    o = random_optimizer_batch(10, 32)
+    o["model_variant_off"] = o["model_variant_off"].copy(); o["model_variant_off"][-1] += 1
+    with pytest.raises(pkg.WvaError):
+        engine.cost_aware_optimize(o)

@@ -1,14 +1,15 @@
 // sizer_probe.cuh — length-sorted work queue for the lock-step lane sizer.
 //
-// The lanes of a warp solve their chains in lock step, so a round costs the LONGEST chain among the 32 work
-// items of the warp; with the items in natural (server, accelerator) order the early-exit lengths (E4) inside
-// a warp differ by 2-10x and about half of the FP64 issue slots were spent on lanes riding along (r1 profile:
-// 9.2e9 FP64 warp instructions for 4.3e9 worth of live states).  This pass makes the queue order a function of
-// the expected chain length: a throw-away float32 PROBE sizes every item (6 bisection steps on a float32 birth-death
-// chain whose constant-rate tail is summed in closed form, < 0.1 % of the real work), estimates where the exact
-// chain's 2^-54 early exit fires at the probed rate, and the item ids are radix-sorted by (N, length) descending — longest first,
-// equal N together (mixed N in a warp forces the slow per-lane path).  The exact kernels then pull items
-// through this permutation.
+// The lanes of a warp solve their chains in lock step, so a round costs the LONGEST chain among the 32 work items of
+// the warp.  Chain length (early exit E4) varies 10x between the bisection steps of an item and between items, and in
+// natural (server, accelerator) order only 40-52 % of the executed lane-steps did live work
+// (SizerCounters.lockstep_slots).  This pass makes the queue order a function of the expected work: a throw-away
+// float32 PROBE sizes every item (6 bisection steps on a float32 birth-death chain whose constant-rate tail is summed in
+// closed form, < 5 % of the real work), estimates where the exact chain's 2^-54 early exit fires at the probed rate,
+// and the item ids are radix-sorted by (N, bisects?, length) descending — longest first, equal N together (mixed N in a
+// warp forces the slow per-lane path), items whose search ends at an end point (2 solves instead of ~22) last.  With gang
+// refill (a warp takes 32 new items only when all its lanes are idle) 81-83 % of the lane-steps are live.
+// wva_calculate uses it where it was measured to pay (130-400 pairs per SM, capi.cu launch_sizer); see DESIGN.md §4.
 //
 // NOTHING computed here reaches a result: the probe only chooses the ORDER in which the exact, bit-reproducible
 // sizer visits the items (each item's arithmetic is independent of every other item's), so a bad probe can

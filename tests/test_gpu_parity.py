@@ -382,6 +382,13 @@ def test_limiter_reference_vectors(engine):
     assert g["target"].tolist() == [3] and g["gpus_allocated"].tolist() == [2]
 
 
+def test_type_allocator_sequences_device(engine):
+    """type_inventory_test.go:156-432 through wva_limit (same table as tests/test_oracle_kat.py)."""
+    from tests.test_oracle_kat import TYPE_ALLOCATOR_CASES, limiter_case
+    for limits, decisions, want in TYPE_ALLOCATOR_CASES:
+        assert engine.limit(limiter_case(limits, decisions))["gpus_allocated"].tolist() == want
+
+
 # ---- boundary behaviour ----------------------------------------------------------------------------------------
 def test_call_order_and_errors(pkg):
     with pkg.Engine(0) as e:

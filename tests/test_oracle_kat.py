@@ -313,3 +313,26 @@ def test_limiter_reference_vectors(oracle):
     g = oracle.limit(dict(n_types=1, acc_type=[0, -1], current=[2, 1], target=[1, 2], gpus_per_replica=[1, 1],
                           spare=[0.1, 0.1], cost=[5., 5.], type_limit=[10]))
     assert g["target"].tolist() == [1, 1] and g["was_limited"].tolist() == [0, 1]
+
+
+# ---- internal/engines/pipeline/type_inventory_test.go:227-300,387-432 (typeAllocator.TryAllocate sequences) -------------------------------------------
+TYPE_ALLOCATOR_CASES = [
+    # limits by type, decisions (type, current, target, gpus/replica, spare), expected gpus allocated
+    ({"A100": 8, "H100": 16}, [("H100", 0, 4, 1, .1), ("A100", 0, 6, 1, .2), ("H100", 0, 20, 1, .3)], [4, 6, 12]),   # :387-432
+    ({"H100": 8}, [("H100", 6, 6, 1, .5), ("H100", 0, 4, 1, .1)], [0, 2]),                                          # :268-298 partial
+    ({"A100": 8, "H100": 16}, [("H100", 4, 4, 1, .9), ("A100", 4, 4, 1, .9), ("H100", 0, 4, 1, .1)], [0, 0, 4]),    # :227-266 available = limit - used
+    ({"H100": 8}, [("H100", 12, 12, 1, .9), ("H100", 0, 1, 1, .1)], [0, 0]),                                        # :156-177 usage above the limit: available 0
+]
+
+
+def limiter_case(limits, decisions):
+    types = sorted(limits)
+    return dict(n_types=len(types), acc_type=[types.index(t) for t, *_ in decisions], current=[d[1] for d in decisions],
+                target=[d[2] for d in decisions], gpus_per_replica=[d[3] for d in decisions], spare=[d[4] for d in decisions],
+                cost=[1.0] * len(decisions), type_limit=[limits[t] for t in types])
+
+
+@pytest.mark.parametrize("limits,decisions,want", TYPE_ALLOCATOR_CASES)
+def test_type_allocator_sequences(oracle, limits, decisions, want):
+    g = oracle.limit(limiter_case(limits, decisions))
+    assert g["gpus_allocated"].tolist() == want

@@ -213,7 +213,7 @@ def make_saturation_in(d: dict):
     return st, keep
 
 
-def alloc_saturation_out(M: int, V: int, P: int):
+def alloc_saturation_out(M: int, V: int, P: int, only=None):
     spec = {"var_target": (np.int32, V), "var_replica_count": (np.int32, V), "var_non_saturated": (np.int32, V),
             "var_max_kv": (np.float64, V), "var_max_queue": (np.int64, V), "var_avg_spare_kv": (np.float64, V),
             "var_avg_spare_queue": (np.float64, V), "rep_saturated": (np.uint8, P),
@@ -223,6 +223,9 @@ def alloc_saturation_out(M: int, V: int, P: int):
     st = SaturationOut()
     out = {}
     for name, (dt, n) in spec.items():
+        if only is not None and name not in only:
+            setattr(st, name, None)
+            continue
         a = np.zeros(max(n, 1), dtype=dt)
         setattr(st, name, ptr(a))
         out[name] = a[:n]

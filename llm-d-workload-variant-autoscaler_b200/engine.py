@@ -203,14 +203,17 @@ class Engine:
     def saturation_run(self, detail: bool = False):
         self._check(self.lib.wva_saturation_run(self.ctx, 1 if detail else 0), "wva_saturation_run")
 
-    def saturation_fetch(self, detail: bool = False):
+    def saturation_fetch(self, detail: bool = False, fields=None):
+        """Results of the last saturation_run.  detail=False: targets, flags and partials only; `fields`: exactly these
+        arrays (names of wva_saturation_out) — nothing else is allocated or copied back."""
         M, V, P = self._sat_dims
-        ost, out = abi.alloc_saturation_out(M, V, P)
-        if not detail:
+        ost, out = abi.alloc_saturation_out(M, V, P, only=fields)
+        if fields is None and not detail:
             for k in ("var_replica_count", "var_non_saturated", "var_max_kv", "var_max_queue", "var_avg_spare_kv",
                       "var_avg_spare_queue", "rep_saturated", "mod_total_replicas", "mod_non_saturated",
                       "mod_avg_spare_kv", "mod_avg_spare_queue"):
                 setattr(ost, k, None)
+                out.pop(k, None)
         self._check(self.lib.wva_saturation_fetch(self.ctx, C.byref(ost)), "wva_saturation_fetch")
         return out
 

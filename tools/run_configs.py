@@ -110,11 +110,12 @@ with pkg.Engine(0) as e:
             for b in range(60):
                 d = pkg.synth.saturation_batch(10_000, 32, stream=500 + b)
                 t0 = time.perf_counter()
-                r = e.saturation_v1(d)                       # upload + analysis + targets + fetch of everything
+                e.saturation_upload(d); e.saturation_run(True)       # upload + analysis + targets
+                r = e.saturation_fetch(fields=("var_target", "var_avg_spare_kv", "mod_flags"))   # what a decision needs
                 lim_in = {"n_types": 8, "acc_type": (np.arange(d["n_variants"]) % 8).astype(np.int32),
                           "current": d["var_current"], "target": np.maximum(r["var_target"], 0).astype(np.int32),
                           "gpus_per_replica": np.ones(d["n_variants"], np.int32),
-                          "spare": np.repeat(r["mod_avg_spare_kv"], 32), "cost": d["var_cost"],
+                          "spare": r["var_avg_spare_kv"], "cost": d["var_cost"],   # engine.go:650-651
                           "type_limit": np.full(8, int(d["var_current"].sum() // 8 + 500), np.int32)}
                 e.limit(lim_in)
                 lat.append((time.perf_counter() - t0) * 1e3)
@@ -122,7 +123,7 @@ with pkg.Engine(0) as e:
             out["cfg5"] = {"models_per_batch": 10_000, "variants": 320_000, "replicas": int(d["n_replicas"]),
                            "decision_latency_ms_p50": float(np.percentile(lat, 50)),
                            "decision_latency_ms_p99": float(np.percentile(lat, 99)),
-                           "note": "host SoA batch -> upload -> saturation analysis + targets -> limiter -> host decisions"}
+                           "note": "host SoA batch -> upload -> saturation analysis + targets -> fetch of targets / spare / flags -> limiter -> host decisions"}
 print(json.dumps(out, indent=1))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_r1.json"), "w"), indent=1)

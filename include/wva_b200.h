@@ -180,7 +180,7 @@ int64_t wva_launch_count(const wva_ctx* ctx);
                                       predicted next bisection point */
 #define WVA_OPT_LENGTH_SORT 2      /* 1: the lane sizer visits the work items in probe-sorted order
                                       (csrc/sizer_probe.cuh); 0: natural (server, accelerator) order; -1 (default):
-                                      sorted where it was measured to pay (130-400 pairs per SM).  Order
+                                      sorted where it was measured to pay (130-1500 pairs per SM).  Order
                                       only — results are identical either way */
 #define WVA_OPT_GANG_REFILL 3      /* 1: a warp of the lane sizer takes 32 new items only when all its
                                       lanes are idle (lanes stay in the same bisection step); 0: lanes refill

@@ -303,10 +303,11 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
     // length-sorted queue: float32 probe -> (N, expected chain length) keys -> descending radix sort of the item ids
     const unsigned* order = nullptr;
     const unsigned long long n_items = split ? 2 * n_pairs : n_pairs;
-    // measured (r1, B200): the sorted queue + gang refill pays between ~130 and ~400 pairs per SM (the items then fill
-    // 1.5-5 waves and longest-first ordering shortens the tail: -18 % at 24 k pairs, -30 % at 48 k, -14 % at 56 k); below,
-    // every lane holds one item and the probe is pure overhead; above, the whole-pair kernel gains ~6 % before the probe
-    const bool by_size = n_pairs > (unsigned long long)ctx->sm_count * 130 && n_pairs <= (unsigned long long)ctx->sm_count * 400;
+    // measured (r1, B200): the sorted queue + gang refill pays between ~130 and ~1500 pairs per SM (the items then fill
+    // 1.5-15 waves and longest-first ordering shortens the tail: -18 % at 24 k pairs, -30 % at 48 k, -15 % at 100-130 k);
+    // below, every lane holds one item and the probe is pure overhead; far above, the gain (6 % at 320 k pairs, 2 % at
+    // N = 256) no longer covers the probe's variance
+    const bool by_size = n_pairs > (unsigned long long)ctx->sm_count * 130 && n_pairs <= (unsigned long long)ctx->sm_count * 1500;
     const bool do_sort = ctx->length_sort < 0 ? by_size : ctx->length_sort != 0;
     const bool do_gang = ctx->gang_refill < 0 ? by_size : ctx->gang_refill != 0;
     if (do_sort && n_items >= 64 && n_items < (1ull << 31)) {

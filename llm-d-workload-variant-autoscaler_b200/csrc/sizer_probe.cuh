@@ -9,7 +9,7 @@
 // and the item ids are radix-sorted by (N, bisects?, length) descending — longest first, equal N together (mixed N in a
 // warp forces the slow per-lane path), items whose search ends at an end point (2 solves instead of ~22) last.  With gang
 // refill (a warp takes 32 new items only when all its lanes are idle) 81-83 % of the lane-steps are live.
-// wva_calculate uses it where it was measured to pay (130-400 pairs per SM, capi.cu launch_sizer); see DESIGN.md §4.
+// wva_calculate uses it where it was measured to pay (130-1500 pairs per SM, capi.cu launch_sizer); see DESIGN.md §4.
 //
 // NOTHING computed here reaches a result: the probe only chooses the ORDER in which the exact, bit-reproducible
 // sizer visits the items (each item's arithmetic is independent of every other item's), so a bad probe can

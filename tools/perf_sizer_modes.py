@@ -12,9 +12,10 @@ with pkg.Engine(0) as e:
     e.load_system(d)
     ref = None
     for mode in modes:
-        e.set_option(2, 0 if mode < 0 else (1 if gang >= 0 else -1))      # negative mode: natural order; gang -1: library default
+        natural = mode < 0                                                # negative mode: natural order, lanes refill one by one
+        e.set_option(2, 0 if natural else (1 if gang >= 0 else -1))      # gang -1: library default for both options
+        e.set_option(3, 0 if natural else gang)
         mode = abs(mode)
-        e.set_option(3, gang if mode >= 0 else 0)
         e.set_option(1, mode)
         for rep in range(2):
             e.calculate()

@@ -103,6 +103,21 @@ def test_lane_kernels_with_the_table_in_global_memory(pkg, engine, oracle, mode)
         assert _bit_equal(g[k], o[k]), k
 
 
+@pytest.mark.parametrize("S", [1400, 2000, 5000])
+def test_default_policy_windows_match_oracle(pkg, engine, oracle, S):
+    """wva_calculate picks the kernel and the queue order by system size (capi.cu): 1 400 servers x 16 = 151 pairs/SM ->
+    split items on the probe-sorted queue; 2 000 -> speculative split items, sorted; 5 000 -> whole pairs, sorted.  Every
+    window at its real size against the oracle, all fields bit for bit."""
+    sysd = pkg.synth.queue_system(S, 16, 32, stream=90 + S % 7)
+    engine.load_system(sysd)
+    engine.calculate()
+    g = engine.candidates()
+    o = oracle.calculate(sysd)
+    _cmp_candidates(g, o)
+    for k in F32_FIELDS:
+        assert _bit_equal(g[k], o[k]), k
+
+
 def test_baseline_config1_full_path(pkg, engine, oracle):
     """BASELINE config 1: 10 models x 4 variants x 32 levels, single class, unlimited."""
     sysd = pkg.synth.baseline_config(1)

@@ -88,6 +88,34 @@ def _analyzer_cases(pkg, eng):
     r = a.analyze(inp([rm("pod-1", "variant-a", "H100", 10.0, 5000, 16000, 0, 100, 50)], [st("variant-a", 1), st("variant-b", 0)]))
     vb = [v for v in r["VariantCapacities"] if v["VariantName"] == "variant-b"][0]
     assert vb["PerReplicaCapacity"] == 9000.0 and vb["TotalCapacity"] == 0.0 and vb["ReplicaCount"] == 0
+    # zero-replica variants (:266-442): live record, deployment-derived record + workload, bounds, fallback
+    a = A()
+    a.store.update("test-ns", "test-model", "variant-a", {"AcceleratorName": "H100", "GpuCount": 1, "EffectiveCapacity": 12000, "LearnedFrom": "live"})
+    r = a.analyze(inp([], [st("variant-a", 0)]))
+    assert len(r["VariantCapacities"]) == 1 and r["VariantCapacities"][0]["PerReplicaCapacity"] == 12000.0
+    a = A()
+    a.store.update("test-ns", "test-model", "variant-b", {"AcceleratorName": "A100", "GpuCount": 1, "EffectiveCapacity": 8192, "LearnedFrom": "deployment",
+                                                          "VLLMParams": {"EffectiveMaxBatchedTokens": 8192, "MaxNumSeqs": 256}})
+    r = a.analyze(inp([rm("pod-1", "variant-a", "H100", 10.0, 5000, 16000, 0, 500, 100)], [st("variant-a", 1), st("variant-b", 0)]))
+    assert r["VariantCapacities"][1]["VariantName"] == "variant-b" and r["VariantCapacities"][1]["PerReplicaCapacity"] == 140800.0
+    a = A()
+    dp = {"GpuMemoryUtilization": 0.9, "BlockSize": 16, "KvCacheDtype": "auto", "TensorParallelSize": 1, "MaxNumSeqs": 256, "EffectiveMaxBatchedTokens": 8192}
+    a.store.update("test-ns", "test-model", "variant-b", {"AcceleratorName": "H100", "GpuCount": 1, "EffectiveCapacity": 8192, "VLLMParams": dict(dp), "LearnedFrom": "deployment"})
+    a.store.update("test-ns", "test-model", "variant-a", {"AcceleratorName": "H100", "GpuCount": 1, "TotalKvCapacityTokens": 50000, "EffectiveCapacity": 40000,
+                                                          "VLLMParams": dict(dp), "LearnedFrom": "live"})
+    r = a.analyze(inp([rm("pod-1", "variant-a", "H100", 10.0, 5000, 50000, 0, 500, 100)], [st("variant-a", 1), st("variant-b", 0)]))
+    assert r["VariantCapacities"][1]["VariantName"] == "variant-b" and r["VariantCapacities"][1]["PerReplicaCapacity"] == 40000.0
+    a = A()
+    a.store.update("test-ns", "test-model", "variant-a", {"AcceleratorName": "A100", "GpuCount": 1, "EffectiveCapacity": 8192, "TotalKvCapacityTokens": 30000,
+                                                          "VLLMParams": {"EffectiveMaxBatchedTokens": 8192, "MaxNumSeqs": 256, "NumGpuBlocksOverride": 1875, "BlockSize": 16},
+                                                          "LearnedFrom": "deployment"})
+    r = a.analyze(inp([rm("pod-1", "variant-x", "L40S", 5.0, 5000, 16000, 0, 500, 100)], [st("variant-x", 1), st("variant-a", 0)]))
+    assert r["VariantCapacities"][1]["VariantName"] == "variant-a" and r["VariantCapacities"][1]["PerReplicaCapacity"] == 24000.0
+    a = A()
+    a.store.update("test-ns", "test-model", "variant-a", {"AcceleratorName": "H100", "GpuCount": 1, "EffectiveCapacity": 8192, "LearnedFrom": "deployment",
+                                                          "VLLMParams": {"EffectiveMaxBatchedTokens": 8192, "MaxNumSeqs": 256}})
+    r = a.analyze(inp([], [st("variant-a", 0)]))
+    assert len(r["VariantCapacities"]) == 1 and r["VariantCapacities"][0]["PerReplicaCapacity"] == 8192.0
     # scaling signals (:480-536)
     r = A().analyze(inp([rm("pod-1", "variant-a", "H100", 10.0, 11000, 16000, 3, 100, 50)], one))
     assert r["RequiredCapacity"] > 0 and r["TotalDemand"] == 11000.0 + 3 * 100
@@ -398,3 +426,34 @@ def test_v2_entry_points_reject_malformed_offsets(pkg, engine):
     o["model_variant_off"] = o["model_variant_off"].copy(); o["model_variant_off"][-1] += 1
     with pytest.raises(pkg.WvaError):
         engine.cost_aware_optimize(o)
+
+
+def test_v2_analyzer_batch_equals_single_calls(pkg, oracle):
+    """Every model of a cycle in one batched call == one Analyze per model (the k2 history and the store are keyed by
+    model, so models do not interact); a second cycle sees the history of the first."""
+    eng = OracleEngine(oracle)
+    g = np.random.default_rng(17)
+
+    def model(i, sat_queue):
+        ms, sts = [], []
+        for v in range(int(g.integers(1, 4))):
+            n = int(g.integers(0, 4))
+            for k in range(n):
+                cap = int(g.choice([16000, 32000]))
+                ms.append(rm(f"m{i}-v{v}-p{k}", f"v{v}", g.choice(["A100", "H100"]), float(g.choice([5.0, 10.0])), int(cap * g.uniform(0.1, 0.9)), cap,
+                             int(g.integers(5, 9)) if sat_queue else int(g.integers(0, 4)), float(g.uniform(50, 900)), float(g.choice([40.0, 300.0, 700.0]))))
+            sts.append(st(f"v{v}", n + int(g.integers(0, 2)), int(g.integers(0, 2))))
+        d = inp(ms, sts, {"QueueSize": int(g.integers(0, 9)), "QueueBytes": int(g.integers(0, 9000))} if i % 2 else None)
+        d["ModelID"] = f"model-{i}"
+        return d
+
+    cycle1 = [model(i, True) for i in range(12)]
+    cycle2 = [dict(m, ReplicaMetrics=[dict(r, QueueLength=1) for r in m["ReplicaMetrics"]]) for m in cycle1]   # queues drained
+    batch = pkg.pipeline.SaturationAnalyzerV2(eng)
+    singles = pkg.pipeline.SaturationAnalyzerV2(eng)
+    for cyc in (cycle1, cycle2):
+        rb = batch.analyze_batch(cyc)
+        rs = [singles.analyze(m) for m in cyc]
+        assert rb == rs
+    assert batch.history == singles.history and batch.history       # cycle 1 observed k2 values, cycle 2 used them
+    assert batch.store.records == singles.store.records

@@ -164,6 +164,33 @@ class Manager:
         servers = {s["name"]: s for s in _get(self.spec, "serverData", "servers", default=[]) or []}
         return solution_to_spec(sol, self.index, servers)
 
+    def analyze_model(self, server_name: str) -> dict:
+        """interfaces.ModelAnalyzer.AnalyzeModel as internal/modelanalyzer implements it (analyzer.go:24-33, utils.go:9-25):
+        Server.Calculate for one variant server -> {"Allocations": {accelerator: ModelAcceleratorAllocation}}; an unknown
+        server gives the empty response.  The device sizes every server of the spec in the same launch; the required-QPS
+        fields are the adapter's float32 product MaxArrvRatePerReplica * 1000, widened."""
+        i = self.index.server_of.get(server_name)
+        if i is None:
+            return {"Allocations": {}}
+        if getattr(self, "_cand", None) is None:
+            self.engine.load_system(self.sysd)
+            self.engine.calculate()
+            self._cand = self.engine.candidates()
+        c = self._cand
+        out = {}
+        for a, acc in enumerate(self.index.acc):
+            st = int(c["state"][i, a])
+            if st == 0:
+                continue                                         # nil allocation: not in Server.AllAllocations()
+            qps = float(np.float32(c["max_arrv_rate"][i, a]) * np.float32(1000.0))
+            out[acc] = {"Allocation": {"accelerator": acc if st == 1 else "", "numReplicas": int(c["num_replicas"][i, a]),
+                                       "maxBatch": int(c["batch_size"][i, a]), "cost": float(c["cost"][i, a]),
+                                       "value": float(c["value"][i, a]), "itlAverage": float(c["itl"][i, a]),
+                                       "ttftAverage": float(c["ttft"][i, a]), "rho": float(c["rho"][i, a]),
+                                       "maxArrvRatePerReplica": float(c["max_arrv_rate"][i, a])},
+                        "RequiredPrefillQPS": qps, "RequiredDecodeQPS": qps, "Reason": "markovian analysis"}
+        return {"Allocations": out}
+
     def allocation_by_type(self) -> dict:
         """System.AllocateByType (system.go:271-300): accelerator type -> (count, limit, cost) of the last solution."""
         sol = self.last_solution

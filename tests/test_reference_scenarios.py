@@ -111,6 +111,38 @@ def test_solve_unlimited_on_greedy_base_oracle(pkg, oracle):
         assert sol["value"][i] == np.where(feas, cand["value"][i], np.inf).min()
 
 
+class _OracleSizer:
+    """engine stand-in for the CPU test of Manager.analyze_model: load/calculate/candidates answered by the oracle"""
+
+    def __init__(self, oracle):
+        self.o = oracle
+
+    def load_system(self, d):
+        self.d = d
+
+    def calculate(self):
+        self.c = self.o.calculate(self.d)
+
+    def candidates(self):
+        return self.c
+
+
+def test_model_analyzer_adapter(pkg, oracle):
+    """internal/modelanalyzer: one entry per accelerator with a non-nil allocation, QPS = float32(maxArrv * 1000),
+    unknown server -> empty response (analyzer.go:24-33)."""
+    m = pkg.manager.Manager(_OracleSizer(oracle), rs.greedy_base())
+    r = m.analyze_model("server1")["Allocations"]
+    assert set(r) == {"A100", "H100"}
+    for acc, e in r.items():
+        assert e["Reason"] == "markovian analysis" and e["RequiredPrefillQPS"] == e["RequiredDecodeQPS"]
+        assert e["RequiredPrefillQPS"] == float(np.float32(e["Allocation"]["maxArrvRatePerReplica"]) * np.float32(1000))
+        assert e["Allocation"]["accelerator"] == acc and e["Allocation"]["numReplicas"] >= 1
+    assert m.analyze_model("nope") == {"Allocations": {}}
+    s = rs.greedy_base()
+    s["serverData"]["servers"].append(rs._server("lonely", "llama-13b", "low-priority", 5, 10, 10))   # no target for the class
+    assert pkg.manager.Manager(_OracleSizer(oracle), s).analyze_model("lonely") == {"Allocations": {}}
+
+
 # ---- the same systems through Manager -> C-ABI (GPU) ---------------------------------------------------------------------------
 def _device_vs_oracle(pkg, engine, oracle, spec):
     d, idx, cand, want = _oracle_optimize(pkg, oracle, spec)
@@ -130,6 +162,13 @@ def _device_vs_oracle(pkg, engine, oracle, spec):
     servers = {s["name"]: s for s in m.spec["serverData"]["servers"]}
     assert got_spec == pkg.manager.solution_to_spec(want, idx, servers)
     return m, got_spec, idx
+
+
+@pytest.mark.gpu
+def test_model_analyzer_adapter_device(pkg, engine, oracle):
+    a = pkg.manager.Manager(engine, rs.greedy_base()).analyze_model("server2")
+    b = pkg.manager.Manager(_OracleSizer(oracle), rs.greedy_base()).analyze_model("server2")
+    assert a == b and set(a["Allocations"]) == {"A100", "H100"}
 
 
 @pytest.mark.gpu

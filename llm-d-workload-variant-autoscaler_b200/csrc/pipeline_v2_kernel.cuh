@@ -42,46 +42,102 @@ __device__ __forceinline__ double shfl_d(unsigned mask, double v, int src) {
   return __hiloint2double(hi, lo);
 }
 
-// effective capacity of replica r (0 when it has no capacity data); also its demand
-__device__ __forceinline__ bool v2_replica(const SatV2In& in, int r, double kv_thr, long long& k1, long long& eff, long long& demand) {
+// the five input streams of one replica
+struct V2Rep { long long cap, in_use, queue, k2; double avg_in; };
+__device__ __forceinline__ V2Rep v2_load(const SatV2In& in, int r) {
+  V2Rep x;
+  x.cap = in.rep_total_kv[r]; x.in_use = in.rep_tokens_in_use[r]; x.queue = in.rep_queue_len[r]; x.k2 = in.rep_k2[r];
+  x.avg_in = in.rep_avg_in[r];
+  return x;
+}
+// effective capacity of a replica (0 when it has no capacity data); also its demand
+__device__ __forceinline__ bool v2_eval(const V2Rep& x, double kv_thr, long long& k1, long long& eff, long long& demand) {
   k1 = 0; eff = 0; demand = 0;
-  const long long cap = in.rep_total_kv[r];
-  if (cap <= 0) return false;                                                          // analyzer.go:148-150
-  demand = in.rep_tokens_in_use[r];
-  const double ai = in.rep_avg_in[r];
-  if (ai > 0) demand += in.rep_queue_len[r] * go_int64(ai);                            // :153-156
-  k1 = go_int64(d_mul((double)cap, kv_thr));                                           // :159
-  const long long k2r = in.rep_k2[r];
-  const long long k2 = k2r < 0 ? k1 : k2r;                                             // computeK2 priority 4
+  if (x.cap <= 0) return false;                                                        // analyzer.go:148-150
+  demand = x.in_use;
+  if (x.avg_in > 0) demand += x.queue * go_int64(x.avg_in);                            // :153-156
+  k1 = go_int64(d_mul((double)x.cap, kv_thr));                                         // :159
+  const long long k2 = x.k2 < 0 ? k1 : x.k2;                                           // computeK2 priority 4
   eff = k2 < k1 ? k2 : k1;                                                             // :175-178
   return true;
 }
+__device__ __forceinline__ bool v2_replica(const SatV2In& in, int r, double kv_thr, long long& k1, long long& eff, long long& demand) {
+  if (in.rep_total_kv[r] <= 0) { k1 = 0; eff = 0; demand = 0; return false; }          // the other streams are not read
+  return v2_eval(v2_load(in, r), kv_thr, k1, eff, demand);
+}
 
-// Three ordered float64 sums over 32 slots at once: the slots go through shared memory ([3][32] per warp) and lane c
+// Three ordered float64 sums over 32 slots at once: the slots go through shared memory ([3][V2_COL] per warp) and lane c
 // (c = 0, 1, 2; the other lanes shadow c % 3) runs chain c as 32 dependent adds fed by LDS — 2 instructions per
 // element for the warp instead of the 14 of a shuffle-fed walk.  A slot that must not count holds +0.0 (x + 0.0 == x).
+// V2_COL = 34 doubles puts the three columns 4 banks apart: with 32 (same banks) every read was a 3-way conflict, and
+// those reads were most of the kernel's L1TEX time (ncu: 1.6e8 conflict cycles per launch at 200 000 models).
+#define V2_COL 34
 __device__ __forceinline__ void ordered_sums3(double* buf, int lane, double a, double b, double c, double& sa, double& sb, double& sc) {
   const unsigned full = 0xffffffffu;
   __syncwarp();
-  buf[lane] = a; buf[32 + lane] = b; buf[64 + lane] = c;
+  buf[lane] = a; buf[V2_COL + lane] = b; buf[2 * V2_COL + lane] = c;
   __syncwarp();
-  const double* col = buf + 32 * (lane % 3);
+  const double2* col = reinterpret_cast<const double2*>(buf + V2_COL * (lane % 3));   // 16-byte aligned: V2_COL is even
   double acc = (lane % 3 == 0) ? sa : ((lane % 3 == 1) ? sb : sc);
 #pragma unroll
-  for (int l = 0; l < 32; l++) acc = d_add(acc, col[l]);
+  for (int l = 0; l < 16; l++) { const double2 t = col[l]; acc = d_add(d_add(acc, t.x), t.y); }
   sa = shfl_d(full, acc, 0); sb = shfl_d(full, acc, 1); sc = shfl_d(full, acc, 2);
 }
 
-__global__ void __launch_bounds__(256) saturation_v2_kernel(SatV2In in, SatV2Out out) {
+// Replicas of one model staged per warp: a model's replicas are one contiguous range of the replica arrays, so the
+// warp reads them COALESCED (lane = replica, 5 input streams, 4 output streams), leaves (effective, demand) in shared
+// memory, and the per-variant parts — ordered demand sum, median — run lane-per-variant on shared memory.  Reading the
+// replica arrays lane-per-variant straight from global memory (12 sectors per request) kept L1TEX 93 % busy and the
+// kernel at 2.0 TB/s; staged, with conflict-free ordered sums and two rounds of loads in flight, it runs at 4.0 TB/s
+// (profiles/r1_v2_pipeline.json).  Models with more than V2_STAGE replicas still take the lane-per-variant path.
+#define V2_STAGE 256
+#define V2_NO_DATA 0x7fffffffffffffffLL   // never a real effective capacity: go_int64 < 2^63 - 1, and eff <= k1
+
+// 4 blocks per SM = 64 registers: measured 0.68 ms at 200 000 models x 32 variants against 0.98 / 0.77 / 0.80 ms for
+// 1 / 3 / 5 blocks (88 / 72 / 48 registers) — occupancy against spills.
+#ifndef V2_MINB
+#define V2_MINB 4
+#endif
+#ifndef V2_ROUNDS
+#define V2_ROUNDS 2   // rounds of replica loads in flight per lane in the staging phase (1: 0.85 ms, 2: 0.68, 3: 0.67)
+#endif
+__global__ void __launch_bounds__(256, V2_MINB) saturation_v2_kernel(SatV2In in, SatV2Out out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  __shared__ double sums_buf[8][96];
+  __shared__ __align__(16) double sums_buf[8][3 * V2_COL];
+  __shared__ long long stage_eff[8][V2_STAGE], stage_dem[8][V2_STAGE];
   double* buf = sums_buf[threadIdx.x >> 5];
+  long long* s_eff = stage_eff[threadIdx.x >> 5];
+  long long* s_dem = stage_dem[threadIdx.x >> 5];
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long m = warp0; m < in.n_models; m += nwarps) {
     const int v0 = in.model_variant_off[m], v1 = in.model_variant_off[m + 1];
     const double kv_thr = in.cfg_kv_threshold[m];
+    const int R0 = in.variant_replica_off[v0], R1 = in.variant_replica_off[v1];
+    const bool staged = R1 - R0 <= V2_STAGE;
+    if (staged) {                                                                      // computeReplicaCapacity, lane = replica
+      __syncwarp();
+      for (int r0 = R0 + lane; r0 < R1; r0 += 32 * V2_ROUNDS) {                         // V2_ROUNDS rounds of loads in flight
+        V2Rep x[V2_ROUNDS];
+#pragma unroll
+        for (int h = 0; h < V2_ROUNDS; h++) x[h] = v2_load(in, r0 + 32 * h < R1 ? r0 + 32 * h : r0);
+#pragma unroll
+        for (int h = 0; h < V2_ROUNDS; h++) {
+          const int r = r0 + 32 * h;
+          if (r >= R1) break;
+          long long k1, eff, demand;
+          const bool has = v2_eval(x[h], kv_thr, k1, eff, demand);
+          s_eff[r - R0] = has ? eff : V2_NO_DATA;
+          s_dem[r - R0] = demand;
+          if (out.rep_k1) out.rep_k1[r] = k1;
+          if (out.rep_effective) out.rep_effective[r] = eff;
+          if (out.rep_demand) out.rep_demand[r] = demand;
+          if (out.rep_saturated) out.rep_saturated[r] = (has && demand >= eff) ? 1 : 0;  // :180
+        }
+      }
+      __syncwarp();
+    }
     double total_supply = 0.0, total_anticipated = 0.0, total_demand = 0.0;
     for (int c0 = v0; c0 < v1; c0 += 32) {
       const int v = c0 + lane;
@@ -93,25 +149,37 @@ __global__ void __launch_bounds__(256) saturation_v2_kernel(SatV2In in, SatV2Out
         long long e8[8];                                                               // effective capacities of a small variant
         const bool small = hi - lo <= 8;
 #pragma unroll
-        for (int j = 0; j < 8; j++) e8[j] = 0x7fffffffffffffffLL;
-        for (int r0 = lo; r0 < hi; r0 += 8) {                                          // computeReplicaCapacity, slice order
+        for (int j = 0; j < 8; j++) e8[j] = V2_NO_DATA;
+        if (staged) {
+          for (int r0 = lo; r0 < hi; r0 += 8) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const int r = r0 + j;
-            if (r >= hi) break;
-            long long k1, eff, demand;
-            const bool has = v2_replica(in, r, kv_thr, k1, eff, demand);
-            if (has) { n_data++; demand_sum = d_add(demand_sum, (double)demand); if (small) e8[j] = eff; }   // :309-312
-            if (out.rep_k1) out.rep_k1[r] = k1;
-            if (out.rep_effective) out.rep_effective[r] = eff;
-            if (out.rep_demand) out.rep_demand[r] = demand;
-            if (out.rep_saturated) out.rep_saturated[r] = (has && demand >= eff) ? 1 : 0;   // :180
+            for (int j = 0; j < 8; j++) {
+              const int r = r0 + j;
+              if (r >= hi) break;
+              const long long eff = s_eff[r - R0];
+              if (eff != V2_NO_DATA) { n_data++; demand_sum = d_add(demand_sum, (double)s_dem[r - R0]); if (small) e8[j] = eff; }   // :309-312
+            }
+          }
+        } else {
+          for (int r0 = lo; r0 < hi; r0 += 8) {                                        // slice order, straight from global memory
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int r = r0 + j;
+              if (r >= hi) break;
+              long long k1, eff, demand;
+              const bool has = v2_replica(in, r, kv_thr, k1, eff, demand);
+              if (has) { n_data++; demand_sum = d_add(demand_sum, (double)demand); if (small) e8[j] = eff; }
+              if (out.rep_k1) out.rep_k1[r] = k1;
+              if (out.rep_effective) out.rep_effective[r] = eff;
+              if (out.rep_demand) out.rep_demand[r] = demand;
+              if (out.rep_saturated) out.rep_saturated[r] = (has && demand >= eff) ? 1 : 0;
+            }
           }
         }
         if (n_data > 0) {
           // median (analyzer.go:505-519) by rank counting: the element of rank k has exactly k elements before it in
           // (value, index) order.  Up to 8 replicas: on the registers just filled (absent slots hold +inf and rank last);
-          // more: re-evaluating the replicas, no scratch.
+          // more: over the staged values, or re-evaluating the replicas — no scratch.
           const int k_hi = n_data / 2, k_lo = (n_data % 2 == 0) ? k_hi - 1 : k_hi;
           long long m_lo = 0, m_hi = 0;
           if (small) {
@@ -122,6 +190,18 @@ __global__ void __launch_bounds__(256) saturation_v2_kernel(SatV2In in, SatV2Out
               for (int b = 0; b < 8; b++) rank += (e8[b] < e8[a] || (e8[b] == e8[a] && b < a)) ? 1 : 0;
               if (rank == k_lo) m_lo = e8[a];
               if (rank == k_hi) m_hi = e8[a];
+            }
+          } else if (staged) {
+            for (int r = lo; r < hi; r++) {
+              const long long e = s_eff[r - R0];
+              if (e == V2_NO_DATA) continue;
+              int rank = 0;
+              for (int q = lo; q < hi; q++) {
+                const long long eq = s_eff[q - R0];                                    // the sentinel never ranks before a value
+                if (eq < e || (eq == e && q < r)) rank++;
+              }
+              if (rank == k_lo) m_lo = e;
+              if (rank == k_hi) m_hi = e;
             }
           } else {
             for (int r = lo; r < hi; r++) {
@@ -162,7 +242,7 @@ __global__ void __launch_bounds__(256) saturation_v2_kernel(SatV2In in, SatV2Out
     if (in.sched_size && !(qs == 0 && qb == 0)) {
       // computeModelWorkloadAverages (:438-455): float64 sums over the model's replicas in SLICE order; the lanes
       // fetch 32 replicas per round trip, the adds run in order through shuffles
-      const int r0 = in.variant_replica_off[v0], r1 = in.variant_replica_off[v1];
+      const int r0 = R0, r1 = R1;
       double ai = 0.0, ao = 0.0, ah = 0.0;
       int cnt = 0;
       for (int b = r0; b < r1; b += 32) {

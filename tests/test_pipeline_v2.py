@@ -342,6 +342,20 @@ def test_saturation_v2_matches_oracle(engine, oracle, M, seed):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("max_variants,max_replicas,seed", [(40, 16, 11), (6, 120, 12), (70, 30, 13)])
+def test_saturation_v2_staged_and_unstaged_models(engine, oracle, max_variants, max_replicas, seed):
+    """Models of up to 256 replicas are staged through shared memory, larger ones read lane-per-variant from global
+    memory (pipeline_v2_kernel.cuh V2_STAGE); both sides of the limit, variants above 8 replicas (the general median)
+    and models wider than a warp in one batch."""
+    d = random_v2_batch(300, seed, max_variants=max_variants, max_replicas=max_replicas)
+    sizes = np.diff(d["variant_replica_off"][d["model_variant_off"]])
+    assert (sizes <= 256).any() and (sizes > 256).any()
+    g, o = engine.saturation_v2(d), oracle.saturation_v2(d)
+    for k in o:
+        assert np.array_equal(_bits(g[k]), _bits(o[k])), k
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("M,seed", [(1, 5), (400, 6), (30000, 7)])
 def test_cost_aware_and_enforcer_match_oracle(engine, oracle, M, seed):
     d = random_optimizer_batch(M, seed)

@@ -43,4 +43,22 @@ with pkg.Engine(0) as e:
     for _ in range(3):
         e.enforce(enf); ts.append(e.timing()["limit_ms"])
     out["enforce_ms"] = min(ts); out["enforce_alg_GBs"] = (V * 16 + M * 14) / (min(ts) * 1e-3) / 1e9
+    # the fused call: analyzer (without the per-replica outputs nobody downstream reads) -> optimizer -> enforcer on the device
+    import ctypes as C
+    abi = pkg._abi
+    ist, ost, keep, _o = abi.make_saturation_v2(d)
+    for k in ("rep_k1", "rep_effective", "rep_demand", "rep_saturated", "var_ready", "var_total_capacity", "var_total_demand", "var_utilization",
+              "mod_total_supply", "mod_total_demand", "mod_utilization"):
+        setattr(ost, k, None)
+    tgt, app = np.zeros(V, np.int32), np.zeros(M, np.uint8)
+    cost = np.ascontiguousarray(opt["var_cost"], np.float64); z = np.ascontiguousarray(enf["mod_scale_to_zero_enabled"], np.uint8)
+    rc_ = np.ascontiguousarray(enf["mod_request_count"], np.float64)
+    ts = []
+    with pkg.Engine(0) as e2:
+        for _ in range(3):
+            r = e2.lib.wva_pipeline_v2(e2.ctx, C.byref(ist), cost.ctypes.data, None, z.ctypes.data, rc_.ctypes.data, None, C.byref(ost), tgt.ctypes.data, app.ctypes.data)
+            assert r == 0
+            ts.append(e2.timing()["saturation_ms"])
+    out["pipeline_v2_three_kernels_ms"] = min(ts)
+    out["pipeline_v2_alg_GBs"] = (P * 56 + V * 44 + M * 60) / (min(ts) * 1e-3) / 1e9
 print(json.dumps(out, indent=1))

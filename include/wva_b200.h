@@ -199,6 +199,13 @@ int32_t wva_calculate(wva_ctx* ctx);
 int32_t wva_solve(wva_ctx* ctx);
 /* Server.AllAllocations() of every server (server.go:138-140). */
 int32_t wva_get_candidates(wva_ctx* ctx, wva_candidates* out);
+/* Install candidates computed elsewhere — on another GPU, for another shard of the servers — in place of a
+ * wva_calculate on this context: Server.allAllocations (pkg/core/server.go:21,55-67) is plain per-server data, and
+ * Solver.Solve (pkg/solver/solver.go:32-60) reads nothing else of the sizing.  This is the exchange step of the
+ * model-sharded limited-capacity solve: every rank sizes its shard, the candidate arrays are all-gathered, and the
+ * greedy sweep — which needs all servers — runs on the merged set.  All arrays are [S*A] for the LOADED system and
+ * required except n_solves; state must be a WVA_ALLOC_* value and num_replicas >= 0 (else WVA_ERR_ARG). */
+int32_t wva_set_candidates(wva_ctx* ctx, const wva_candidates* in);
 /* System.GenerateSolution (system.go:303-319) + allocationByType. */
 int32_t wva_get_solution(wva_ctx* ctx, wva_solution* out);
 

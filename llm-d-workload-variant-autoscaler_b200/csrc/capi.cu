@@ -517,6 +517,40 @@ int32_t wva_solve(wva_ctx* ctx) {
   return WVA_OK;
 }
 
+// ------------------------------------------------------------------ candidates from outside
+int32_t wva_set_candidates(wva_ctx* ctx, const wva_candidates* in) {
+  if (!ctx || !in) return WVA_ERR_ARG;
+  if (!ctx->loaded) { ctx->last_error = "wva_set_candidates before wva_load_system"; return WVA_ERR_STATE; }
+  const size_t P = (size_t)ctx->S * ctx->A;
+  if (P > 0 && (!in->state || !in->num_replicas || !in->batch_size || !in->cost || !in->value || !in->itl || !in->ttft ||
+                !in->rho || !in->max_arrv_rate)) {
+    ctx->last_error = "wva_set_candidates: a required array is NULL";
+    return WVA_ERR_ARG;
+  }
+  for (size_t i = 0; i < P; i++)
+    if (in->state[i] > WVA_ALLOC_EMPTY || in->num_replicas[i] < 0) {
+      ctx->last_error = "wva_set_candidates: state / num_replicas out of range";
+      return WVA_ERR_ARG;
+    }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  const CandView& c = ctx->cand;
+  struct { void* dst; const void* src; size_t b; } cp[] = {
+      {c.state, in->state, P}, {c.num_replicas, in->num_replicas, P * 4}, {c.batch_size, in->batch_size, P * 4},
+      {c.cost, in->cost, P * 4}, {c.value, in->value, P * 4}, {c.itl, in->itl, P * 4}, {c.ttft, in->ttft, P * 4},
+      {c.rho, in->rho, P * 4}, {c.max_arrv_rate, in->max_arrv_rate, P * 4}};
+  if (P > 0) {
+    for (auto& x : cp) CK(cudaMemcpyAsync(x.dst, x.src, x.b, cudaMemcpyHostToDevice, ctx->stream));
+    if (in->n_solves) CK(cudaMemcpyAsync(c.n_solves, in->n_solves, P * 4, cudaMemcpyHostToDevice, ctx->stream));
+    else CK(cudaMemsetAsync(c.n_solves, 0, P * 4, ctx->stream));
+  }
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));               // the caller's buffers are free again on return (cgo pointer rule)
+  ctx->timing.h2d_ms = elapsed(ctx, 0, 1);
+  ctx->calculated = true; ctx->solved = false;
+  return WVA_OK;
+}
+
 // ------------------------------------------------------------------ readback
 int32_t wva_get_candidates(wva_ctx* ctx, wva_candidates* out) {
   if (!ctx || !out) return WVA_ERR_ARG;

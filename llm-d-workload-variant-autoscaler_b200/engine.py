@@ -63,6 +63,7 @@ def load_library():
     L.wva_calculate.argtypes = [ctxp]
     L.wva_solve.argtypes = [ctxp]
     L.wva_get_candidates.argtypes = [ctxp, C.POINTER(abi.Candidates)]
+    L.wva_set_candidates.argtypes = [ctxp, C.POINTER(abi.Candidates)]
     L.wva_get_solution.argtypes = [ctxp, C.POINTER(abi.Solution)]
     L.wva_analyze_grid.argtypes = [ctxp, C.c_int32] + [C.c_void_p] * 6
     L.wva_grid_run.argtypes = [ctxp, C.c_int32, C.c_int32]
@@ -84,7 +85,7 @@ def load_library():
 
 
 EXPORTS = ["wva_set_option", "wva_create", "wva_destroy", "wva_strerror", "wva_last_error", "wva_launch_count",
-           "wva_load_system", "wva_calculate", "wva_solve", "wva_get_candidates", "wva_get_solution",
+           "wva_load_system", "wva_calculate", "wva_solve", "wva_get_candidates", "wva_set_candidates", "wva_get_solution",
            "wva_analyze_grid", "wva_grid_run", "wva_grid_fetch", "wva_mm1k_eval", "wva_saturation_v1",
            "wva_saturation_upload", "wva_saturation_run", "wva_saturation_fetch", "wva_limit", "wva_saturation_v2",
            "wva_cost_aware_optimize", "wva_enforce", "wva_pipeline_v2", "wva_last_timing",
@@ -136,6 +137,14 @@ class Engine:
         cst, cand = abi.alloc_candidates(self.S, self.A)
         self._check(self.lib.wva_get_candidates(self.ctx, C.byref(cst)), "wva_get_candidates")
         return cand
+
+    def set_candidates(self, cand: dict):
+        """Candidates sized elsewhere (another rank's shard, all-gathered) in place of calculate(); [S, A] arrays."""
+        for k in abi.CAND_ARRAYS:
+            if np.asarray(cand[k]).size != self.S * self.A:
+                raise WvaError(f"set_candidates: {k} has {np.asarray(cand[k]).size} elements, the loaded system needs {self.S * self.A}")
+        cst, keep = abi.candidates_struct(cand)
+        self._check(self.lib.wva_set_candidates(self.ctx, C.byref(cst)), "wva_set_candidates")
 
     def solution(self):
         sst, sol = abi.alloc_solution(self.S, self.T)

@@ -1,10 +1,17 @@
 """Model-sharded multi-GPU plumbing.
 
 The hot path shards by server: rank r owns servers ``s % world == r`` (or, in the weak-scaling
-bench, its own 1k models); the small accelerator / capacity tables are replicated and **no data-path
-collective exists**.  What crosses ranks is one all-reduce(sum) of per-shard partials — the by-type
-GPU counts and costs of System.AllocateByType (pkg/core/system.go:271-299) plus a few counters — over
-NCCL (NVLink/NVSwitch) through torch.distributed; on CPU the same code runs over gloo in the tests.
+bench, its own 1k models); the small accelerator / capacity tables are replicated and the sizing has
+**no data-path collective**.  What crosses ranks:
+
+* unlimited capacity (SolveUnlimited is per server): one all-reduce(sum) of per-shard partials — the by-type GPU
+  counts and costs of System.AllocateByType (pkg/core/system.go:271-299) plus a few counters;
+* limited capacity (SolveGreedy, pkg/solver/greedy.go:35-105, orders ALL servers against shared per-type pools): one
+  all-gather of the candidate allocations (37 B per (server, accelerator) pair), after which every rank runs the same
+  sweep on the merged set (wva_set_candidates + wva_solve) and holds the same global solution — the sizing, >99 % of
+  the time, stays sharded.
+
+Both go over NCCL (NVLink/NVSwitch) through torch.distributed; on CPU the same code runs over gloo in the tests.
 torch is plumbing here (process group + device buffer), not compute.
 """
 from __future__ import annotations
@@ -50,3 +57,91 @@ def all_reduce_partials(vec: np.ndarray, device=None) -> np.ndarray:
 def shard_indices(n_servers: int, rank: int, world: int) -> np.ndarray:
     """servers owned by `rank` under the canonical round-robin partition"""
     return np.arange(rank, n_servers, world)
+
+
+# ---- limited-capacity solve over model shards ---------------------------------------------------------------------------
+_CAND_FIELDS = (("state", np.uint8), ("num_replicas", np.int32), ("batch_size", np.int32), ("cost", np.float32),
+                ("value", np.float32), ("itl", np.float32), ("ttft", np.float32), ("rho", np.float32),
+                ("max_arrv_rate", np.float32), ("n_solves", np.int32))
+
+
+def pack_candidates(cand: dict, rows: int, n_acc: int) -> np.ndarray:
+    """field-major byte image of a shard's candidate arrays, padded to `rows` servers"""
+    parts = []
+    for k, dt in _CAND_FIELDS:
+        a = np.zeros((rows, n_acc), dtype=dt)
+        src = np.asarray(cand[k], dtype=dt).reshape(-1, n_acc)
+        a[: src.shape[0]] = src
+        parts.append(a.reshape(-1).view(np.uint8))
+    return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+
+
+def unpack_candidates(buf: np.ndarray, rows: int, n_acc: int) -> dict:
+    out, off = {}, 0
+    for k, dt in _CAND_FIELDS:
+        nb = rows * n_acc * np.dtype(dt).itemsize
+        out[k] = np.ascontiguousarray(buf[off:off + nb]).view(dt).reshape(rows, n_acc)
+        off += nb
+    return out
+
+
+def gather_candidates(cand: dict, n_servers: int, n_acc: int, rank: int, world: int, device=None) -> dict:
+    """All-gather the shards' candidate arrays into [n_servers, n_acc] arrays in the server order of the full system
+    (shard r holds servers r, r + world, ...: server j * world + r is row j of shard r, so the merge is one transpose
+    per field).  One collective of ceil(S / world) * A * 37 bytes per rank."""
+    import torch
+    import torch.distributed as dist
+    rows = (n_servers + world - 1) // world
+    mine = pack_candidates(cand, rows, n_acc)
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        allb = mine.reshape(1, -1)
+    else:
+        t = torch.from_numpy(mine)
+        if device is not None:
+            t = t.to(device)
+        out = torch.empty(world * t.numel(), dtype=torch.uint8, device=t.device)     # flat: gloo accepts no other shape
+        dist.all_gather_into_tensor(out, t)
+        allb = out.cpu().numpy().reshape(world, -1)
+    full, off = {}, 0
+    for k, dt in _CAND_FIELDS:
+        nb = rows * n_acc * np.dtype(dt).itemsize
+        g = np.ascontiguousarray(allb[:, off:off + nb]).view(dt).reshape(world, rows, n_acc)      # [rank][row][acc]
+        full[k] = np.ascontiguousarray(g.transpose(1, 0, 2)).reshape(rows * world, n_acc)[:n_servers]
+        off += nb
+    return full
+
+
+def solve_sharded(engine, sysd: dict, rank: int, world: int, device=None, shard_fn=None, timings: dict | None = None):
+    """Manager.Optimize (pkg/manager/manager.go:21-27) over `world` ranks for either capacity mode: size the rank's
+    shard, all-gather the candidates, run the allocator on the merged set.  Every rank returns the global solution.
+    `engine` is an Engine (or, in the CPU tests, a stand-in with the same six methods); `timings` collects host
+    wall-clock milliseconds per step."""
+    import time
+    if shard_fn is None:
+        from .synth import shard_system as shard_fn
+    S, A = int(sysd["n_servers"]), int(sysd["n_acc"])
+    t = [time.perf_counter()]
+
+    def lap(name):
+        t.append(time.perf_counter())
+        if timings is not None:
+            timings[name] = (t[-1] - t[-2]) * 1e3
+
+    shard, idx = shard_fn(sysd, rank, world)
+    assert np.array_equal(idx, shard_indices(S, rank, world))
+    lap("shard")
+    engine.load_system(shard)
+    engine.calculate()
+    lap("load+calculate")
+    cand = engine.candidates()
+    lap("candidates_d2h")
+    full = gather_candidates(cand, S, A, rank, world, device)
+    lap("all_gather+merge")
+    engine.load_system(sysd)
+    engine.set_candidates(full)
+    lap("load+set_candidates")
+    engine.solve()
+    lap("solve")
+    sol = engine.solution()
+    lap("solution_d2h")
+    return sol

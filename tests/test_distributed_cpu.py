@@ -65,6 +65,96 @@ def test_sharded_partials_all_reduce_gloo(pkg, oracle):
         assert tot["n_allocated"] == ref["n_allocated"] and tot["total_replicas"] == ref["total_replicas"]
 
 
+class _OracleEngine:
+    """the five Engine methods solve_sharded uses, with the oracle standing in for the device"""
+
+    def __init__(self, orc):
+        self.orc = orc
+
+    def load_system(self, d):
+        self.d, self.cand = d, None
+
+    def calculate(self):
+        self.cand = self.orc.calculate(self.d, nthreads=1)
+
+    def candidates(self):
+        return self.cand
+
+    def set_candidates(self, cand):
+        self.cand = cand
+
+    def solve(self):
+        self.sol = self.orc.solve(self.d, self.cand)
+
+    def solution(self):
+        return self.sol
+
+
+def _limited_system(pkg_synth, orc, policy, delayed):
+    d = pkg_synth.queue_system(23, 5, 16, stream=83, saturation_policy=policy, delayed_best_effort=delayed)
+    un = orc.solve(d, orc.calculate(d, nthreads=1))
+    return pkg_synth.limit_capacity(d, un["type_count"], 0.5)     # half of the unconstrained demand: the pools bind
+
+
+def _greedy_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    pkg_synth = importlib.import_module(PKG + ".synth")
+    sharding = importlib.import_module(PKG + ".sharding")
+    from tests import oracle_lib
+    orc = oracle_lib.load()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = []
+        for policy, delayed in ((0, False), (1, False), (2, True), (3, False)):
+            d = _limited_system(pkg_synth, orc, policy, delayed)
+            sol = sharding.solve_sharded(_OracleEngine(orc), d, rank, world)
+            out.append({k: np.asarray(v) for k, v in sol.items()})
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_limited_greedy_all_gather_gloo(pkg, oracle):
+    """Limited capacity: the greedy sweep needs every server, so the shards' candidates are all-gathered and each rank
+    solves the merged set — 23 servers over 2 ranks (ragged shards), all four saturation policies."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_greedy_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for i, (policy, delayed) in enumerate(((0, False), (1, False), (2, True), (3, False))):
+        d = _limited_system(pkg.synth, oracle, policy, delayed)
+        ref = oracle.solve(d, oracle.calculate(d))
+        if policy == 0:
+            assert (np.asarray(ref["state"]) == 1).any() and (np.asarray(ref["state"]) == 0).any()   # the cap binds
+        for r in range(world):
+            for k, v in ref.items():
+                a, b = np.asarray(got[r][i][k]), np.asarray(v)
+                assert np.array_equal(a.view(np.uint8) if a.dtype.kind == "f" else a, b.view(np.uint8) if b.dtype.kind == "f" else b), (policy, r, k)
+
+
+def test_candidate_pack_roundtrip(pkg):
+    g = np.random.default_rng(5)
+    sh = pkg.sharding
+    cand = {k: (g.integers(0, 3, (7, 3)).astype(dt) if np.dtype(dt).kind in "ui" else g.random((7, 3)).astype(dt)) for k, dt in sh._CAND_FIELDS}
+    back = sh.unpack_candidates(sh.pack_candidates(cand, 9, 3), 9, 3)
+    for k, _ in sh._CAND_FIELDS:
+        assert np.array_equal(back[k][:7], cand[k]) and not back[k][7:].any()
+    one = sh.gather_candidates(cand, 7, 3, 0, 1)
+    for k, _ in sh._CAND_FIELDS:
+        assert np.array_equal(one[k], cand[k])
+
+
 def test_partials_roundtrip(pkg):
     sol = {"type_count": np.array([3, 0, 7]), "type_cost": np.array([1.5, 0.0, 2.25]), "state": np.array([1, 0, 1, 2]),
            "num_replicas": np.array([2, 0, 5, 0])}

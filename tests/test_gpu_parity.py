@@ -244,6 +244,58 @@ def test_greedy_matches_oracle(pkg, engine, oracle, policy, delayed):
     assert (g["state"] == 0).sum() >= (un["state"] == 0).sum()
 
 
+@pytest.mark.parametrize("policy,delayed", [("None", False), ("PriorityRoundRobin", True), ("RoundRobin", False)])
+def test_sharded_limited_solve_equals_whole(pkg, engine, oracle, policy, delayed):
+    """sharding.solve_sharded without a process group on ONE device: the shards of a 3-rank partition are sized one
+    after the other, merged exactly as gather_candidates merges them, installed with wva_set_candidates, and the
+    greedy sweep on the merged set must equal the sweep after a whole-system wva_calculate — bit for bit."""
+    sh = pkg.sharding
+    d = pkg.synth.queue_system(401, 6, 32, stream=97, saturation_policy=policy, delayed_best_effort=delayed)
+    engine.load_system(d); engine.calculate(); engine.solve()
+    lim = pkg.synth.limit_capacity(d, engine.solution()["type_count"], 0.55)
+    engine.load_system(lim); engine.calculate()
+    whole_c = engine.candidates(); engine.solve(); whole = engine.solution()
+    world, S, A = 3, 401, 6
+    rows = (S + world - 1) // world
+    full = {k: np.zeros((S, A), dt) for k, dt in sh._CAND_FIELDS}
+    for r in range(world):
+        shard, idx = pkg.synth.shard_system(lim, r, world)
+        engine.load_system(shard); engine.calculate()
+        part = sh.unpack_candidates(sh.pack_candidates(engine.candidates(), rows, A), rows, A)
+        for k in full:
+            full[k][idx] = part[k][: len(idx)]
+    for k, _ in sh._CAND_FIELDS:
+        if k != "n_solves":                                   # the split items of a pair may finish in either order
+            assert np.array_equal(full[k].view(np.uint8), np.asarray(whole_c[k]).view(np.uint8)), k
+    engine.load_system(lim); engine.set_candidates(full); engine.solve()
+    merged = engine.solution()
+    o = oracle.solve(lim, whole_c)
+    for k in SOL_INT:
+        assert np.array_equal(merged[k], whole[k]) and np.array_equal(merged[k], o[k]), k
+    for k in F32_FIELDS:
+        assert _bit_equal(merged[k], whole[k]) and _bit_equal(merged[k], o[k]), k
+    assert np.array_equal(merged["type_count"], whole["type_count"]) and (whole["state"] == 0).any()
+
+
+def test_set_candidates_validates(pkg, engine):
+    d = pkg.synth.queue_system(5, 3, 16, stream=98)
+    with pkg.Engine(0) as e2:
+        with pytest.raises(pkg.WvaError, match="before wva_load_system"):
+            e2.set_candidates({k: np.zeros((0, 0), dt) for k, dt in pkg.sharding._CAND_FIELDS})   # nothing loaded
+    engine.load_system(d); engine.calculate()
+    c = {k: np.array(v) for k, v in engine.candidates().items()}
+    bad = dict(c); bad["state"] = c["state"].copy(); bad["state"][2, 1] = 7
+    with pytest.raises(pkg.WvaError):
+        engine.set_candidates(bad)
+    bad = dict(c); bad["num_replicas"] = c["num_replicas"].copy(); bad["num_replicas"][0, 0] = -1
+    with pytest.raises(pkg.WvaError):
+        engine.set_candidates(bad)
+    with pytest.raises(pkg.WvaError):
+        engine.set_candidates({k: v[:4] for k, v in c.items()})
+    engine.set_candidates(c); engine.solve()                  # and the context is still usable
+    assert engine.solution()["state"].shape == (5,)
+
+
 def test_greedy_ties_and_duplicates(pkg, engine, oracle):
     """Identical servers give exactly equal (priority, delta, value) keys: the re-insertion rule
     (before equal elements, latest first) and the canonical initial order must both match."""

@@ -149,7 +149,9 @@ __device__ __forceinline__ bool g_before(g_u64 khi_a, g_u64 klo_a, g_u64 khi_b, 
 
 constexpr int G_HEAP_SM = 4096;   // heap slots held in shared memory (levels 0-2 and the start of level 3)
 constexpr int G_AVAIL_SM = 2048;  // capacity types held in shared memory
-constexpr size_t G_SMEM_BYTES = (size_t)G_HEAP_SM * (8 + 8 + 8 + 4 + 4 + 4) + (size_t)G_AVAIL_SM * 8;
+constexpr int G_STAGE_A = 32;     // candidate ranks per server staged in shared memory for the 32 head entries in flight
+constexpr size_t G_SMEM_BYTES = (size_t)G_HEAP_SM * (8 + 8 + 8 + 4 + 4 + 4) + (size_t)G_AVAIL_SM * 8 +
+                                (size_t)32 * G_STAGE_A * (8 + 4 + 4 + 4 + 4) + 32 * 8;
 
 // 32-ary min-heap of re-inserted entries, operated by the whole warp: every lane runs the same control
 // flow on the same values, and a pop inspects the 32 children of a node with one load per field + a
@@ -386,6 +388,13 @@ __global__ void __launch_bounds__(32, 1) greedy_allocate_kernel(SysView s, Greed
   long long* sm_avail = heap.s_cnt + G_HEAP_SM;
   heap.s_srv = (int*)(sm_avail + G_AVAIL_SM); heap.s_ci = heap.s_srv + G_HEAP_SM; heap.s_type = heap.s_ci + G_HEAP_SM;
   heap.w = w; heap.n = 0;
+  // the records (rank >= 1) of the 32 head entries in flight: a head that does not fit scans its remaining candidates
+  // from here instead of paying a dependent L2 round trip (~1 200 cycles) per failing entry
+  long long* sb_upr = (long long*)(heap.s_type + G_HEAP_SM);
+  unsigned* sb_kd = (unsigned*)(sb_upr + 32 * G_STAGE_A); unsigned* sb_kv = sb_kd + 32 * G_STAGE_A;
+  int* sb_type = (int*)(sb_kv + 32 * G_STAGE_A); int* sb_nrep = sb_type + 32 * G_STAGE_A;
+  int* sb_nc = sb_nrep + 32 * G_STAGE_A;
+  const int AS = A < G_STAGE_A ? A : G_STAGE_A;
   long long* avail = s.n_types <= G_AVAIL_SM ? sm_avail : w.avail;
   for (int t = lane; t < s.n_types; t += 32) avail[t] = s.type_count[t];   // greedy.go:38-39
   __syncwarp();
@@ -398,7 +407,8 @@ __global__ void __launch_bounds__(32, 1) greedy_allocate_kernel(SysView s, Greed
   int head = 0, n_un = 0, group_un0 = 0, base = -32;
   g_u64 l_khi = 0; unsigned l_kv = 0; int l_type = -1, l_srv = -1; long long l_cnt = 0;   // this lane's head record
   unsigned group_pw = 0;
-  bool group_set = false;
+  bool group_set = false, batch_staged = false;
+  int fails_in_batch = 32;                          // the first batch is staged
   while (true) {
     GP_T(t_it);
     if (head < n0 && head >= base + 32) {
@@ -406,13 +416,43 @@ __global__ void __launch_bounds__(32, 1) greedy_allocate_kernel(SysView s, Greed
       const int i = base + lane;
       if (i < n0) {
         l_khi = w.hd_khi[i]; l_kv = w.hd_kv[i]; l_type = w.hd_type[i]; l_cnt = w.hd_cnt[i]; l_srv = w.e_srv[i];
-        // an entry whose first candidate does not fit needs the rest of its records at once: start them towards L1
+      }
+      // an entry whose first candidate does not fit needs the rest of its records at once.  While heads keep failing
+      // (4 or more of the last 32) all 32 entries' records come in together — 32 consecutive records per load
+      // instruction, every load of the batch in flight at once; otherwise they are only started towards L1
+      batch_staged = fails_in_batch >= 4;
+      fails_in_batch = 0;
+      if (!batch_staged && i < n0) {
         const size_t q = (size_t)l_srv * A + 1;
         if (A > 1) {
           g_prefetch(w.r_kd + q); g_prefetch(w.r_kv + q); g_prefetch(w.r_type + q); g_prefetch(w.r_nrep + q);
           g_prefetch(w.r_upr + q); g_prefetch(w.r_upr + q + (A > 17 ? 16 : 0));
         }
         g_prefetch(w.ncand + l_srv);
+      }
+      if (batch_staged) {
+        const int my_srv = i < n0 ? l_srv : -1;
+        const int my_nc = my_srv >= 0 ? w.ncand[my_srv] : 0;
+        __syncwarp();
+        // 8 loads of every field in flight per lane before the first store (the stores would otherwise fence the loads)
+        for (int it0 = 0; it0 < AS; it0 += 8) {
+          GRec r[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int idx = (it0 + u) * 32 + lane;
+            const int sv = (it0 + u < AS) ? idx / AS : 0, j = idx - sv * AS;
+            const int ssrv = __shfl_sync(full, my_srv, sv);
+            r[u].kd = 0; r[u].kv = 0; r[u].type = -1; r[u].nrep = 0; r[u].upr = 0;
+            if (it0 + u < AS && ssrv >= 0 && j >= 1) r[u] = g_load_rec(w, (size_t)ssrv * A, j, A);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int idx = (it0 + u) * 32 + lane;
+            if (it0 + u < AS) { sb_kd[idx] = r[u].kd; sb_kv[idx] = r[u].kv; sb_type[idx] = r[u].type; sb_nrep[idx] = r[u].nrep; sb_upr[idx] = r[u].upr; }
+          }
+        }
+        sb_nc[lane] = my_nc;
+        __syncwarp();
       }
     }
     const int hl = head < n0 ? head - base : 0;
@@ -464,14 +504,22 @@ __global__ void __launch_bounds__(32, 1) greedy_allocate_kernel(SysView s, Greed
     GP_ADD(2, t_fit); GP_INC(10);
     GP_T(t_scan);
     const size_t p = (size_t)srv * A;
-    const int n = w.ncand[srv];
+    const bool staged = !from_heap && batch_staged; // a head entry of a staged batch: its records are in shared memory (row hl)
+    if (!from_heap) fails_in_batch++;
+    const int n = staged ? sb_nc[hl] : w.ncand[srv];
     const unsigned pos_kv = (unsigned)(e.klo >> 32);
     int stop_j = -1, stop_kind = 0, stop_type = -1;   // kind: 1 wait, 2 dead, 3 fit
     g_u64 stop_khi = 0; unsigned stop_kv = 0; long long stop_cnt = 0;
     bool any_fit = false;
     for (int j0 = e.ci + 1; j0 < A; j0 += 32) {
       const int j = j0 + lane;
-      const GRec r = g_load_rec(w, p, j, A);
+      GRec r;
+      if (staged && j < AS) {
+        const int q = hl * AS + j;
+        r.kd = sb_kd[q]; r.kv = sb_kv[q]; r.type = sb_type[q]; r.nrep = sb_nrep[q]; r.upr = sb_upr[q];
+      } else {
+        r = g_load_rec(w, p, j, A);
+      }
       if (j0 >= n) break;
       const g_u64 khi_j = (e.khi & 0xffffffff00000000ull) | r.kd;
       const long long cnt_j = (long long)r.nrep * r.upr;

@@ -177,9 +177,11 @@ struct GHeap {
       const int p = (i - 1) >> 5;
       const GEntry pe = get(p);
       if (!g_before(e.khi, e.klo, pe.khi, pe.klo)) break;
+      __syncwarp();          // every lane has read slot i's previous content (as a parent, one level down) before lane 0 overwrites it
       put(i, pe);
       i = p;
     }
+    __syncwarp();
     put(i, e);
     __syncwarp();
   }
@@ -214,9 +216,11 @@ struct GHeap {
       khi = ((g_u64)m3 << 32) | m2; klo = ((g_u64)m1 << 32) | m0;
       if (!g_before(khi, klo, last.khi, last.klo)) break;
       const GEntry child = get(c0 + who);
+      __syncwarp();          // slot i was read by every lane (as a child, one level up) before lane 0 overwrites it
       put(i, child);
       i = c0 + who;
     }
+    __syncwarp();
     if (n > 0) put(i, last);
     __syncwarp();
     return top;

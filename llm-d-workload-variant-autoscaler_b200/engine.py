@@ -78,6 +78,8 @@ def load_library():
     L.wva_cost_aware_optimize.argtypes = [ctxp, C.c_int64, C.c_int64] + [C.c_void_p] * 8
     L.wva_enforce.argtypes = [ctxp, C.c_int64, C.c_int64] + [C.c_void_p] * 8
     L.wva_pipeline_v2.argtypes = [ctxp, C.POINTER(abi.SaturationV2In)] + [C.c_void_p] * 5 + [C.POINTER(abi.SaturationV2Out), C.c_void_p, C.c_void_p]
+    L.wva_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.wva_host_free.argtypes = [C.c_void_p]
     L.wva_last_timing.argtypes = [ctxp, C.POINTER(abi.Timing)]
     L.wva_microbench_fp64.argtypes = [ctxp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
@@ -88,8 +90,38 @@ EXPORTS = ["wva_set_option", "wva_create", "wva_destroy", "wva_strerror", "wva_l
            "wva_load_system", "wva_calculate", "wva_solve", "wva_get_candidates", "wva_set_candidates", "wva_get_solution",
            "wva_analyze_grid", "wva_grid_run", "wva_grid_fetch", "wva_mm1k_eval", "wva_saturation_v1",
            "wva_saturation_upload", "wva_saturation_run", "wva_saturation_fetch", "wva_limit", "wva_saturation_v2",
-           "wva_cost_aware_optimize", "wva_enforce", "wva_pipeline_v2", "wva_last_timing",
+           "wva_cost_aware_optimize", "wva_enforce", "wva_pipeline_v2", "wva_host_alloc", "wva_host_free", "wva_last_timing",
            "wva_microbench_fp64"]
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array in page-locked host memory (wva_host_alloc): uploads from it and fetches into it are DMA at link
+    speed.  The memory is released when the array (and every view of it) is garbage collected."""
+    import weakref
+    lib = load_library()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    nbytes = max(n * dt.itemsize, 1)
+    p = C.c_void_p()
+    rc = lib.wva_host_alloc(nbytes, C.byref(p))
+    if rc != abi.WVA_OK or not p.value:
+        raise WvaError(f"wva_host_alloc({nbytes}) failed: {lib.wva_strerror(rc).decode()}")
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    weakref.finalize(buf, lib.wva_host_free, C.c_void_p(p.value))
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+
+def pinned_copy(d: dict) -> dict:
+    """the same batch / system dict with every ndarray moved into page-locked memory"""
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, np.ndarray) and v.size:
+            a = pinned_empty(v.shape, v.dtype)
+            a[...] = v
+            out[k] = a
+        else:
+            out[k] = v
+    return out
 
 
 class Engine:

@@ -277,6 +277,23 @@ def test_sharded_limited_solve_equals_whole(pkg, engine, oracle, policy, delayed
     assert np.array_equal(merged["type_count"], whole["type_count"]) and (whole["state"] == 0).any()
 
 
+def test_pinned_host_buffers(pkg, engine, oracle):
+    """wva_host_alloc: arrays in page-locked memory go through every entry point like any host pointer."""
+    a = pkg.pinned_empty((3, 5), np.float32)
+    a[...] = np.arange(15, dtype=np.float32).reshape(3, 5)
+    assert a.sum() == 105 and a.flags["C_CONTIGUOUS"] and pkg.pinned_empty((0,), np.int32).size == 0
+    d = pkg.synth.queue_system(30, 4, 16, stream=99)
+    g1 = engine.optimize(d)
+    g2 = engine.optimize(pkg.pinned_copy(d))
+    for k in g1:
+        assert np.array_equal(np.asarray(g1[k]).view(np.uint8), np.asarray(g2[k]).view(np.uint8)), k
+    b = pkg.synth.saturation_batch(40, 6, stream=99)
+    s1, s2 = engine.saturation_v1(b), engine.saturation_v1(pkg.pinned_copy(b))
+    for k in s1:
+        assert np.array_equal(np.asarray(s1[k]).view(np.uint8), np.asarray(s2[k]).view(np.uint8)), k
+    del a
+
+
 def test_set_candidates_validates(pkg, engine):
     d = pkg.synth.queue_system(5, 3, 16, stream=98)
     with pkg.Engine(0) as e2:

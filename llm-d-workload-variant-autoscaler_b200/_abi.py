@@ -213,7 +213,7 @@ def make_saturation_in(d: dict):
     return st, keep
 
 
-def alloc_saturation_out(M: int, V: int, P: int, only=None):
+def alloc_saturation_out(M: int, V: int, P: int, only=None, alloc=None):
     spec = {"var_target": (np.int32, V), "var_replica_count": (np.int32, V), "var_non_saturated": (np.int32, V),
             "var_max_kv": (np.float64, V), "var_max_queue": (np.int64, V), "var_avg_spare_kv": (np.float64, V),
             "var_avg_spare_queue": (np.float64, V), "rep_saturated": (np.uint8, P),
@@ -226,7 +226,7 @@ def alloc_saturation_out(M: int, V: int, P: int, only=None):
         if only is not None and name not in only:
             setattr(st, name, None)
             continue
-        a = np.zeros(max(n, 1), dtype=dt)
+        a = alloc(name, max(n, 1), dt) if alloc else np.zeros(max(n, 1), dtype=dt)
         setattr(st, name, ptr(a))
         out[name] = a[:n]
     return st, out

@@ -133,6 +133,9 @@ class Engine:
             self.ctx = None
             raise WvaError(f"wva_create(device={device}) failed: {self.lib.wva_strerror(rc).decode()}")
         self.S = self.A = self.T = 0
+        # optional allocator (name, n, dtype) -> 1-D array for the result buffers of saturation_fetch() and limit(),
+        # e.g. views of page-locked buffers from pinned_empty() that the caller reuses from batch to batch
+        self.host_alloc = None
 
     def _check(self, rc, what):
         if rc != abi.WVA_OK:
@@ -248,7 +251,7 @@ class Engine:
         """Results of the last saturation_run.  detail=False: targets, flags and partials only; `fields`: exactly these
         arrays (names of wva_saturation_out) — nothing else is allocated or copied back."""
         M, V, P = self._sat_dims
-        ost, out = abi.alloc_saturation_out(M, V, P, only=fields)
+        ost, out = abi.alloc_saturation_out(M, V, P, only=fields, alloc=self.host_alloc)
         if fields is None and not detail:
             for k in ("var_replica_count", "var_non_saturated", "var_max_kv", "var_max_queue", "var_avg_spare_kv",
                       "var_avg_spare_queue", "rep_saturated", "mod_total_replicas", "mod_non_saturated",
@@ -264,8 +267,9 @@ class Engine:
                (("acc_type", np.int32), ("current", np.int32), ("target", np.int32),
                 ("gpus_per_replica", np.int32), ("spare", np.float64), ("cost", np.float64),
                 ("type_limit", np.int32))}
-        out = {"target": np.zeros(max(D, 1), np.int32), "gpus_allocated": np.zeros(max(D, 1), np.int32),
-               "was_limited": np.zeros(max(D, 1), np.uint8)}
+        mk = self.host_alloc or (lambda name, n, dt: np.zeros(n, dt))
+        out = {"target": mk("limit_target", max(D, 1), np.int32), "gpus_allocated": mk("limit_gpus_allocated", max(D, 1), np.int32),
+               "was_limited": mk("limit_was_limited", max(D, 1), np.uint8)}
         self._check(self.lib.wva_limit(self.ctx, D, int(d["n_types"]), arr["acc_type"].ctypes.data,
                                        arr["current"].ctypes.data, arr["target"].ctypes.data,
                                        arr["gpus_per_replica"].ctypes.data, arr["spare"].ctypes.data,

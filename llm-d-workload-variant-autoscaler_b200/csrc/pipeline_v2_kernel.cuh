@@ -302,10 +302,67 @@ __global__ void __launch_bounds__(256) cost_aware_kernel(long long n_models, con
       for (int v = v0 + lane; v < v1; v += 32) target[v] = -1;
       continue;
     }
-    for (int v = v0 + lane; v < v1; v += 32) target[v] = current[v];                   // initTargets
-    __syncwarp();
     const double req = required[m], spr = spare[m];
     const bool up = req > 0, down = !up && spr > 0;
+    if (V <= 32) {
+      // the usual model: a lane owns its variant — cost, capacity, sort key and target stay in registers, the walk
+      // visits the not-yet-visited variant with the smallest (key, index), and each target is written once
+      const int v = v0 + lane;
+      const bool act = v < v1;
+      const double mc = act ? cost[v] : 0.0, mcap = act ? cap[v] : 0.0;
+      int tgt = act ? current[v] : 0;                                                  // initTargets
+      if (up || down) {
+        int cheapest = -1;
+        if (down) {                                                                    // findCheapestVariant :191-201
+          double c = act ? mc : DMAX;
+          int idx = (act && c < DMAX) ? v : -1;
+          for (int o = 16; o; o >>= 1) {
+            const double oc = shfl_d(full, c, lane ^ o);
+            const int oi = __shfl_xor_sync(full, idx, o);
+            if (oi >= 0 && (idx < 0 || oc < c || (oc == c && oi < idx))) { c = oc; idx = oi; }
+          }
+          if (idx >= 0 && c < DMAX) cheapest = idx;
+        }
+        const double key = up ? (mcap <= 0 ? DMAX : d_div(mc, mcap)) : -mc;            // costEfficiency :233-238 / sortByCostDesc
+        bool visited = !act;
+        double remaining = up ? req : spr;
+        for (int step = 0; step < V && remaining > 0; step++) {
+          double k = key; int idx = visited ? -1 : v;
+          for (int o = 16; o; o >>= 1) {
+            const double ok = shfl_d(full, k, lane ^ o);
+            const int oi = __shfl_xor_sync(full, idx, o);
+            if (oi >= 0 && (idx < 0 || ok < k || (ok == k && oi < idx))) { k = ok; idx = oi; }
+          }
+          const int bi = idx;
+          if (bi < 0) break;
+          if (v == bi) visited = true;
+          const double c = shfl_d(full, mcap, bi - v0);
+          if (c <= 0) continue;
+          if (up) {                                                                    // :88-96
+            const long long need = go_int64(ceil(d_div(remaining, c)));
+            if (v == bi) tgt = (int)((long long)tgt + need);
+            remaining = d_sub(remaining, d_mul((double)need, c));
+          } else {                                                                     // :126-160
+            const int cur = __shfl_sync(full, tgt, bi - v0);
+            int min_rep = 0;
+            if (bi == cheapest && !__any_sync(full, act && v != cheapest && tgt > 0)) min_rep = 1;
+            const int removable = cur - min_rep;
+            if (removable > 0) {
+              long long rem = go_int64(floor(d_div(remaining, c)));
+              if (rem > removable) rem = removable;
+              if (rem > 0) {
+                if (v == bi) tgt = cur - (int)rem;
+                remaining = d_sub(remaining, d_mul((double)rem, c));
+              }
+            }
+          }
+        }
+      }
+      if (act) target[v] = tgt;
+      continue;
+    }
+    for (int v = v0 + lane; v < v1; v += 32) target[v] = current[v];                   // initTargets
+    __syncwarp();
     if (!up && !down) continue;
     int cheapest = -1;
     if (down) {                                                                        // findCheapestVariant :191-201

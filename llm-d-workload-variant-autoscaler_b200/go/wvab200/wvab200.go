@@ -45,6 +45,23 @@ func New(device int) (*Ctx, error) {
 
 func (x *Ctx) Close() { C.wva_destroy(x.c) }
 
+// PinnedFloat64 / PinnedInt64 return slices over page-locked C memory (wva_host_alloc): a collector that writes its
+// per-replica SoA batch into them gets DMA at link speed through every entry point (BASELINE config 5: 6.9 -> 2.1 ms per
+// 10 k-model batch).  The memory is C memory — cgo's pointer rules do not apply — and lives until Free.
+type Pinned struct{ p unsafe.Pointer }
+
+func PinnedBytes(n int) (*Pinned, error) {
+	var p unsafe.Pointer
+	if rc := C.wva_host_alloc(C.size_t(n), &p); rc != C.WVA_OK {
+		return nil, fmt.Errorf("wva_host_alloc(%d): %s", n, C.GoString(C.wva_strerror(rc)))
+	}
+	return &Pinned{p: p}, nil
+}
+func (b *Pinned) Float64(n int) []float64 { return unsafe.Slice((*float64)(b.p), n) }
+func (b *Pinned) Int64(n int) []int64     { return unsafe.Slice((*int64)(b.p), n) }
+func (b *Pinned) Int32(n int) []int32     { return unsafe.Slice((*int32)(b.p), n) }
+func (b *Pinned) Free()                   { C.wva_host_free(b.p); b.p = nil }
+
 func (x *Ctx) err(rc C.int32_t, what string) error {
 	if rc == C.WVA_OK {
 		return nil

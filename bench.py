@@ -102,7 +102,12 @@ def cpu_reference_leg(sample_servers: int):
     orc = oracle_lib.load()
     synth = importlib.import_module(PKG + ".synth")
     d = synth.queue_system(sample_servers, A, NB, n_classes=3, stream=2, R=R)
-    cores = orc.num_threads()
+    # every host thread the process may use — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its
+    # workers, which would silently make the reference arm single-threaded at N > 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     t0 = time.perf_counter()
     cand = orc.calculate(d, nthreads=cores)
     t1 = time.perf_counter()

@@ -1,7 +1,7 @@
 // lockstep_solve.cuh — MM1ModelStateDependent.Solve (pkg/analyzer/mm1modelstatedependent.go:28-116)
 // for NC independent arrival rates per lane, all 32 lanes of a warp advancing the state index
 // together: pass 1 (sum of p~) for every lane and chain, then pass 2 (normalise + accumulate).
-// The loops are unrolled in chunks of 8/NC states and carry NO per-state control flow:
+// The loops are unrolled in chunks of 16/NC states and carry NO per-state control flow:
 //   - the early exit (E4) is decided once per chunk: a chain is `done` when its current term is
 //     below 2^-54 of every accumulator (compared on the high words — conservative) and the
 //     remaining terms are non-increasing; a done chain keeps executing the same instructions,
@@ -169,8 +169,9 @@ __device__ __forceinline__ void p2_chunk(P2 (&b)[NC], const double (&lam)[NC], c
 
 // Chains c with active[c] solve at lambda[c]; the others ride along (lambda 0).  On return `bad`
 // is set for a lane when one of its solves left the exponent window (caller: redo the pair on the
-// slow path).  __noinline__: callers invoke this from several places; one copy keeps the unrolled
-// loops in the instruction cache.
+// slow path).  Forced inline: the NC = 2 instantiation has a single call site and needs its own register
+// budget (as a .func ptxas re-serialised the pipelined chunks); NC = 1 callers go through the
+// __noinline__ wrapper below so that one copy of the unrolled loops stays in the instruction cache.
 template <int NC, class Tab>
 __device__ __forceinline__ void lockstep_solve_inl(const PairModel& m, const Tab& tab, const float* lambda,
                                                    const bool* active, SolveStats* st, int& states, bool& bad) {

@@ -53,7 +53,12 @@ __device__ __forceinline__ double div_small_int(double x, int n) {
 }
 
 template <bool DETAIL>
-__global__ void __launch_bounds__(256, 4) saturation_kernel(SatIn in, SatOut out) {
+// 4 blocks per SM = the kernel's natural 64 registers; 5 / 6 blocks (48 / 40 registers, spills) measured 0.230 / 0.267 ms
+// against 0.219 ms on 28.8 M replicas
+#ifndef SAT_MINB
+#define SAT_MINB 4
+#endif
+__global__ void __launch_bounds__(256, SAT_MINB) saturation_kernel(SatIn in, SatOut out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -67,7 +67,7 @@ __device__ __forceinline__ bool v2_replica(const SatV2In& in, int r, double kv_t
 }
 
 // Three ordered float64 sums over 32 slots at once: the slots go through shared memory ([3][V2_COL] per warp) and lane c
-// (c = 0, 1, 2; the other lanes shadow c % 3) runs chain c as 32 dependent adds fed by LDS — 2 instructions per
+// (c = 0, 1, 2; the other lanes wait) runs chain c as 32 dependent adds fed by LDS — 2 instructions per
 // element for the warp instead of the 14 of a shuffle-fed walk.  A slot that must not count holds +0.0 (x + 0.0 == x).
 // V2_COL = 34 doubles puts the three columns 4 banks apart: with 32 (same banks) every read was a 3-way conflict, and
 // those reads were most of the kernel's L1TEX time (ncu: 1.6e8 conflict cycles per launch at 200 000 models).
@@ -79,8 +79,14 @@ __device__ __forceinline__ void ordered_sums3(double* buf, int lane, double a, d
   __syncwarp();
   const double2* col = reinterpret_cast<const double2*>(buf + V2_COL * (lane % 3));   // 16-byte aligned: V2_COL is even
   double acc = (lane % 3 == 0) ? sa : ((lane % 3 == 1) ? sb : sc);
+  // only lanes 0-2 run the chains: with all 32 lanes shadowing them these 128-bit shared loads (one wavefront per
+  // quarter-warp) were half of the L1 data-pipe wavefronts of the kernel (ncu, r1); the kernel time did not move
+  // (0.66 ms either way) — it is bound by issue slots and latency, not by the L1 pipe
+  if (lane < 3) {
 #pragma unroll
-  for (int l = 0; l < 16; l++) { const double2 t = col[l]; acc = d_add(d_add(acc, t.x), t.y); }
+    for (int l = 0; l < 16; l++) { const double2 t = col[l]; acc = d_add(d_add(acc, t.x), t.y); }
+  }
+  __syncwarp();
   sa = shfl_d(full, acc, 0); sb = shfl_d(full, acc, 1); sc = shfl_d(full, acc, 2);
 }
 

@@ -2,7 +2,7 @@
 usage: python tools/perf_greedy.py [scale=0.1] [capacity_frac=0.6]"""
 import importlib, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
+
 pkg = importlib.import_module("llm-d-workload-variant-autoscaler_b200")
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
 frac = float(sys.argv[2]) if len(sys.argv) > 2 else 0.6

@@ -1,5 +1,5 @@
 """Compare the sizer kernels on a large system (throughput regime)."""
-import importlib, sys, os, time
+import importlib, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("llm-d-workload-variant-autoscaler_b200")
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 20000

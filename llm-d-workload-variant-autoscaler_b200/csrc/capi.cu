@@ -334,6 +334,8 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
            : split ? sizer_lane_kernel<THREADS, SMEM, false, true>
            : (ctx->lane_sizer_mode == 3) ? sizer_lane_kernel<THREADS, SMEM, true, false>
                                          : sizer_lane_kernel<THREADS, SMEM, false, false>;
+    if (THREADS == 256 && !SMEM && !split && ctx->lane_sizer_mode != 3 && ctx->lane_sizer_mode != 5)
+      k = sizer_lane_kernel_gtab_2blk;                 // the same body under a 128-register cap (2 blocks per SM)
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list, sw, order, do_gang ? 1 : 0);

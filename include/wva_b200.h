@@ -162,6 +162,11 @@ typedef struct wva_timing {
   int64_t chain_solves;    /* chain solves executed by the last calculate/grid    */
   int64_t chain_states;    /* birth-death states visited by the last calculate/grid */
   int64_t overflow_pairs;  /* pairs that took the float64 overflow-rescale slow path  */
+  float exchange_ms;       /* NCCL exchange of the last wva_solve / wva_saturation_run on a ctx with a communicator
+                              (all-gather of the candidate arena or of the solution, all-reduce of the partials) */
+  int32_t reserved0;
+  int64_t greedy_heap_pushes; /* entries the last limited wva_solve pushed into the re-insertion heap (greedy.go:143-163) */
+  int64_t greedy_events;      /* head entries the last limited wva_solve processed (greedy.go:112-165 loop trips)    */
 } wva_timing;
 
 /* ---- lifecycle ----------------------------------------------------------- */
@@ -188,9 +193,53 @@ int64_t wva_launch_count(const wva_ctx* ctx);
                                       one by one; -1 (default): as WVA_OPT_LENGTH_SORT.  Scheduling only */
 int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value);
 
+/* ---- multi-GPU: model-sharded over one NCCL communicator ----------------- */
+/*
+ * The path shards by server: rank r of `world` owns the contiguous block of servers
+ * [r*ceil(S/world), min(S, (r+1)*ceil(S/world))); accelerator / perf / capacity tables are replicated (every rank loads
+ * the SAME wva_system).  On a ctx with a communicator
+ *   wva_calculate   sizes only the rank's block (no collective);
+ *   wva_solve       limited capacity (SolveGreedy needs every server, pkg/solver/greedy.go:35-105): ONE in-place
+ *                   ncclAllGather group over the candidate arena in HBM (no host staging), then the same sweep on
+ *                   every rank; unlimited (SolveUnlimited is per server, solver.go:63-79): the rank solves its block,
+ *                   ONE ncclAllGather group of the solution arrays + ONE ncclAllReduce(sum) of the by-type
+ *                   {count int64, cost float64} partials (System.AllocateByType, pkg/core/system.go:271-299).
+ *                   Every rank then holds the global solution (wva_get_solution is identical on all ranks);
+ *   wva_saturation_run  analyses the models the rank uploaded and all-reduces the int64 partials
+ *                   (wva_saturation_out.partials_all).
+ * NCCL is dlopen'ed (libnccl.so.2) on first use: single-GPU callers need no NCCL at all.  The 128-byte id is created
+ * on one rank (wva_comm_unique_id) and carried to the others by the host (the Go shim: any channel it likes).
+ * wva_comm_init_rank must precede wva_load_system (arenas are sized for the padded all-gather).
+ */
+#define WVA_COMM_ID_BYTES 128
+int32_t wva_comm_unique_id(uint8_t id[WVA_COMM_ID_BYTES]);
+int32_t wva_comm_init_rank(wva_ctx* ctx, int32_t world, int32_t rank, const uint8_t id[WVA_COMM_ID_BYTES]);
+/* the block of servers this ctx sizes: [*lo, *hi) (the whole system without a communicator) */
+int32_t wva_comm_shard(const wva_ctx* ctx, int32_t* lo, int32_t* hi);
+
+/*
+ * One host process driving several GPUs (what a Go controller does): n contexts, one per device, joined by one NCCL
+ * communicator (ncclCommInitRank from n host threads).  wva_group_optimize = Manager.Optimize over the group: every
+ * device loads the system, sizes its block of servers, the exchange above runs over NVLink, the allocator runs, and
+ * the global solution is copied out once (from device 0).  wva_group_saturation_v1 splits the batch of models into n
+ * contiguous blocks (device i analyses block i, outputs land at the block's offsets of the caller's arrays) and
+ * all-reduces the partials.  wva_group_ctx exposes the per-device contexts for everything else (timings, options).
+ */
+typedef struct wva_group wva_group;
+int32_t wva_group_create(const int32_t* devices, int32_t n, wva_group** out);
+int32_t wva_group_destroy(wva_group* g);
+int32_t wva_group_size(const wva_group* g);
+wva_ctx* wva_group_ctx(wva_group* g, int32_t i);
+int32_t wva_group_optimize(wva_group* g, const wva_system* sys, wva_solution* out);
+
 /* ---- queueing sizing + allocator ---------------------------------------- */
 /* System.SetFromSpec (pkg/core/system.go:82-89): copies the SoA to HBM. */
 int32_t wva_load_system(wva_ctx* ctx, const wva_system* sys);
+/* OptimizerSpec (pkg/config/types.go:145-149) and CapacityData (types.go:40-50) of the LOADED system, replaced in
+ * place: the candidates of a wva_calculate stay valid (sizing reads neither), only wva_solve must run again —
+ * what Optimizer.Optimize does when the same System is solved under another spec (pkg/solver/optimizer.go:24-36). */
+int32_t wva_set_optimizer(wva_ctx* ctx, int32_t unlimited, int32_t delayed_best_effort, int32_t saturation_policy);
+int32_t wva_set_capacity(wva_ctx* ctx, const int32_t* type_count /* [T] */);
 /* System.Calculate (pkg/core/system.go:258-268) -> Server.Calculate (server.go:55-67)
  * -> CreateAllocation (allocation.go:27-155) for every (server, accelerator). */
 int32_t wva_calculate(wva_ctx* ctx);
@@ -292,6 +341,8 @@ typedef struct wva_saturation_out {  /* any pointer may be NULL (skipped)       
   int64_t* partials;                 /* [4] n_scale_up, n_scale_down, n_transition,
                                             sum of targets (shard partials for the
                                             all-reduce across GPUs)               */
+  int64_t* partials_all;             /* [4] the same summed over every rank of the ctx's communicator (one
+                                            ncclAllReduce inside wva_saturation_run); == partials without one */
 } wva_saturation_out;
 
 #define WVA_SAT_SCALE_UP 1
@@ -302,6 +353,8 @@ typedef struct wva_saturation_out {  /* any pointer may be NULL (skipped)       
 
 int32_t wva_saturation_v1(wva_ctx* ctx, const wva_saturation_in* in,
                           const wva_saturation_out* out);
+/* the same over a group of devices (see wva_group above): device i analyses the i-th contiguous block of models */
+int32_t wva_group_saturation_v1(wva_group* g, const wva_saturation_in* in, const wva_saturation_out* out);
 /* The same in three steps (inputs / results stay resident in HBM between them):
  * upload = host -> HBM copy of the metric batch; run = the analysis + targets
  * kernel (detail == 0 writes only var_target, mod_flags and partials); fetch =

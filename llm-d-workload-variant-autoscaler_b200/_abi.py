@@ -73,7 +73,8 @@ class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("calculate_ms", C.c_float), ("solve_ms", C.c_float),
                 ("grid_ms", C.c_float), ("saturation_ms", C.c_float), ("limit_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("chain_solves", C.c_int64), ("chain_states", C.c_int64),
-                ("overflow_pairs", C.c_int64)]
+                ("overflow_pairs", C.c_int64), ("exchange_ms", C.c_float), ("reserved0", C.c_int32),
+                ("greedy_heap_pushes", C.c_int64), ("greedy_events", C.c_int64)]
 
 
 class SaturationIn(C.Structure):
@@ -91,7 +92,8 @@ class SaturationOut(C.Structure):
                 ("var_max_kv", _f64p), ("var_max_queue", _i64p), ("var_avg_spare_kv", _f64p),
                 ("var_avg_spare_queue", _f64p), ("rep_saturated", _u8p),
                 ("mod_total_replicas", _i32p), ("mod_non_saturated", _i32p), ("mod_avg_spare_kv", _f64p),
-                ("mod_avg_spare_queue", _f64p), ("mod_flags", _u8p), ("partials", _i64p)]
+                ("mod_avg_spare_queue", _f64p), ("mod_flags", _u8p), ("partials", _i64p),
+                ("partials_all", _i64p)]
 
 
 # ---- field specs used to build/validate the SoA dicts ------------------------------------
@@ -219,7 +221,7 @@ def alloc_saturation_out(M: int, V: int, P: int, only=None, alloc=None):
             "var_avg_spare_queue": (np.float64, V), "rep_saturated": (np.uint8, P),
             "mod_total_replicas": (np.int32, M), "mod_non_saturated": (np.int32, M),
             "mod_avg_spare_kv": (np.float64, M), "mod_avg_spare_queue": (np.float64, M),
-            "mod_flags": (np.uint8, M), "partials": (np.int64, 4)}
+            "mod_flags": (np.uint8, M), "partials": (np.int64, 4), "partials_all": (np.int64, 4)}
     st = SaturationOut()
     out = {}
     for name, (dt, n) in spec.items():

@@ -21,6 +21,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -110,7 +112,44 @@ struct wva_ctx {
   PinBuf io_stage_in, io_stage_out;
   GridState grid;
   SatState sat;
+  // multi-GPU (comm.inl): one NCCL communicator, contiguous block of servers per rank
+  void* comm = nullptr;             // ncclComm_t
+  int world = 1, rank = 0;
+  int shard_rows = 0;               // servers per rank block = ceil(S / world)
+  int shard_lo = 0, shard_hi = 0;   // this ctx sizes servers [shard_lo, shard_hi)
+  int shard_status = 0;             // status of the rank's last wva_calculate, agreed on by all ranks in wva_solve
+  DevBuf comm_ws;
 };
+
+// views of the rank's block of servers: srv_* arrays and the candidate rows are plain arrays indexed by server, so a
+// block is the same struct with offset pointers and n_servers = block size (models / accelerators stay global)
+static SysView shard_sys(const wva_ctx* ctx) {
+  SysView v = ctx->sys;
+  const int lo = ctx->shard_lo;
+  v.n_servers = ctx->shard_hi - ctx->shard_lo;
+  v.srv_model += lo; v.srv_priority += lo; v.srv_min_replicas += lo; v.srv_max_batch += lo; v.srv_keep_acc += lo;
+  v.srv_target_present += lo; v.srv_slo_ttft += lo; v.srv_slo_itl += lo; v.srv_slo_tps += lo; v.srv_arrival += lo;
+  v.srv_in_tokens += lo; v.srv_out_tokens += lo; v.srv_cur_acc += lo; v.srv_cur_replicas += lo; v.srv_cur_cost += lo;
+  return v;
+}
+static CandView shard_cand(const wva_ctx* ctx) {
+  CandView c = ctx->cand;
+  const size_t o = (size_t)ctx->shard_lo * ctx->A;
+  c.state += o; c.num_replicas += o; c.batch_size += o; c.cost += o; c.value += o; c.itl += o; c.ttft += o; c.rho += o;
+  c.max_arrv_rate += o; c.n_solves += o;
+  return c;
+}
+static SolView shard_sol(const wva_ctx* ctx) {
+  SolView c = ctx->sol;
+  const size_t o = (size_t)ctx->shard_lo;
+  c.state += o; c.acc += o; c.num_replicas += o; c.batch_size += o; c.cost += o; c.value += o; c.itl += o; c.ttft += o;
+  c.rho += o; c.max_arrv_rate += o;
+  return c;
+}
+static int32_t comm_exchange_and_solve(wva_ctx* ctx);   // comm.inl
+static int32_t comm_reduce_sat_partials(wva_ctx* ctx, long long* d_partials, long long* d_all);
+static int32_t comm_agree_status(wva_ctx* ctx, int my_status, int* agreed);
+static void comm_release(wva_ctx* ctx);
 
 #define CK(call)                                                                         \
   do {                                                                                   \
@@ -169,6 +208,7 @@ int32_t wva_destroy(wva_ctx* ctx) {
   ctx->sys_arena.release(); ctx->cand_arena.release(); ctx->sol_arena.release(); ctx->scratch.release();
   ctx->gtab.release(); ctx->greedy_ws.release(); ctx->split_ws.release(); ctx->order_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->io_in.release(); ctx->io_out.release();
   ctx->stage_in.release(); ctx->stage_out.release(); ctx->io_stage_in.release(); ctx->io_stage_out.release();
+  comm_release(ctx); ctx->comm_ws.release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -191,13 +231,6 @@ int32_t wva_load_system(wva_ctx* ctx, const wva_system* s) {
   if (s->n_types > WVA_MAX_TYPES) return WVA_ERR_LIMIT;
   CK(cudaSetDevice(ctx->device));
   const size_t A = s->n_acc, T = s->n_types, M = s->n_models, S = s->n_servers, MA = M * A;
-  // validate indices the kernels dereference
-  for (size_t a = 0; a < A; a++)
-    if (s->acc_type[a] < 0 || s->acc_type[a] >= (int)T) return WVA_ERR_ARG;
-  for (size_t i = 0; i < S; i++) {
-    if (s->srv_model[i] >= (int)M) return WVA_ERR_ARG;
-    if (s->srv_cur_acc[i] >= (int)A || s->srv_cur_acc[i] < WVA_CUR_ACC_UNKNOWN) return WVA_ERR_ARG;
-  }
   struct Item { const void* src; size_t bytes; size_t off; };
   Layout L;
   std::vector<Item> items;
@@ -212,7 +245,25 @@ int32_t wva_load_system(wva_ctx* ctx, const wva_system* s) {
          o_st = add(s->srv_slo_ttft, S * 4), o_si = add(s->srv_slo_itl, S * 4), o_sps = add(s->srv_slo_tps, S * 4),
          o_sa = add(s->srv_arrival, S * 4), o_sin = add(s->srv_in_tokens, S * 4), o_sout = add(s->srv_out_tokens, S * 4),
          o_sca = add(s->srv_cur_acc, S * 4), o_scr = add(s->srv_cur_replicas, S * 4), o_scc = add(s->srv_cur_cost, S * 4);
-  for (auto& it : items) if (it.bytes && !it.src) return WVA_ERR_ARG;
+  for (auto& it : items) if (it.bytes && !it.src) { ctx->last_error = "wva_load_system: a required array is NULL"; return WVA_ERR_ARG; }
+  // validate indices the kernels dereference (after the NULL checks above)
+  for (size_t a = 0; a < A; a++)
+    if (s->acc_type[a] < 0 || s->acc_type[a] >= (int)T) { ctx->last_error = "wva_load_system: acc_type out of range"; return WVA_ERR_ARG; }
+  for (size_t i = 0; i < S; i++) {
+    if (s->srv_model[i] >= (int)M) { ctx->last_error = "wva_load_system: srv_model out of range"; return WVA_ERR_ARG; }
+    if (s->srv_cur_acc[i] >= (int)A || s->srv_cur_acc[i] < WVA_CUR_ACC_UNKNOWN) { ctx->last_error = "wva_load_system: srv_cur_acc out of range"; return WVA_ERR_ARG; }
+  }
+  // ServiceParms (pkg/analyzer/queueanalyzer.go:33-38) are measured service-time coefficients: finite and >= 0.  A
+  // negative or NaN coefficient makes arrival rates negative (QueueModel.Solve's gate, queuemodel.go:31) or NaN and
+  // the sizing meaningless; it is rejected here instead of being carried into the kernels.
+  for (size_t i = 0; i < MA; i++) {
+    if (!s->perf_present[i]) continue;
+    const float a = s->perf_alpha[i], b = s->perf_beta[i], g = s->perf_gamma[i];
+    if (!(a >= 0.0f && b >= 0.0f && g >= 0.0f) || a > 3.0e38f || b > 3.0e38f || g > 3.0e38f) {
+      ctx->last_error = "wva_load_system: perf_alpha / perf_beta / perf_gamma must be finite and >= 0";
+      return WVA_ERR_ARG;
+    }
+  }
   const size_t total = L.off + 256;
   CK(ctx->stage_in.reserve(total));
   CK(ctx->sys_arena.reserve(total));
@@ -238,8 +289,13 @@ int32_t wva_load_system(wva_ctx* ctx, const wva_system* s) {
   ctx->A = (int)A; ctx->T = (int)T; ctx->M = (int)M; ctx->S = (int)S;
   ctx->unlimited = s->unlimited; ctx->delayed = s->delayed_best_effort; ctx->policy = s->saturation_policy;
 
-  // candidate + solution arenas
-  const size_t P = S * A;
+  // candidate + solution arenas.  With a communicator the rank owns the block of servers [shard_lo, shard_hi) and the
+  // arrays are padded to world equal blocks, so that the all-gather can run in place on them.
+  ctx->shard_rows = ctx->world > 1 ? (int)((S + ctx->world - 1) / ctx->world) : (int)S;
+  ctx->shard_lo = ctx->world > 1 ? (int)std::min(S, (size_t)ctx->rank * ctx->shard_rows) : 0;
+  ctx->shard_hi = ctx->world > 1 ? (int)std::min(S, (size_t)(ctx->rank + 1) * ctx->shard_rows) : (int)S;
+  const size_t S_pad = ctx->world > 1 ? (size_t)ctx->shard_rows * ctx->world : S;
+  const size_t P = S_pad * A;
   {
     Layout C;
     size_t o_state = C.take(P), o_nr = C.take(P * 4), o_bs = C.take(P * 4), o_cost = C.take(P * 4), o_val = C.take(P * 4),
@@ -254,8 +310,9 @@ int32_t wva_load_system(wva_ctx* ctx, const wva_system* s) {
   }
   {
     Layout C;
-    size_t o_state = C.take(S), o_acc = C.take(S * 4), o_nr = C.take(S * 4), o_bs = C.take(S * 4), o_cost = C.take(S * 4),
-           o_val = C.take(S * 4), o_itl = C.take(S * 4), o_ttft = C.take(S * 4), o_rho = C.take(S * 4), o_mar = C.take(S * 4),
+    const size_t SP = S_pad;
+    size_t o_state = C.take(SP), o_acc = C.take(SP * 4), o_nr = C.take(SP * 4), o_bs = C.take(SP * 4), o_cost = C.take(SP * 4),
+           o_val = C.take(SP * 4), o_itl = C.take(SP * 4), o_ttft = C.take(SP * 4), o_rho = C.take(SP * 4), o_mar = C.take(SP * 4),
            o_tc = C.take(T * 8), o_tk = C.take(T * 8);
     CK(ctx->sol_arena.reserve(C.off + 256));
     CK(cudaMemsetAsync(ctx->sol_arena.p, 0, ctx->sol_arena.cap, ctx->stream));   // padding is copied out with the arena
@@ -278,6 +335,8 @@ int32_t wva_load_system(wva_ctx* ctx, const wva_system* s) {
 template <int THREADS, bool SMEM>
 static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned long long n_pairs, int nmax, float* gtab,
                                 int* ovf_list) {
+  const SysView sys_v = shard_sys(ctx);
+  const CandView cand_v = shard_cand(ctx);
   // lane_sizer_mode 1 = flattened state machine (sizer_kernel.cuh); 2 = lock-step rounds; 3 = lock-step with two
   // chains per lane; 4 = lock-step, every pair split into a TTFT item and an ITL item (mid-size systems); 5 = split
   // items whose second chain evaluates the predicted next bisection point (wva_core.cuh spec2_*)
@@ -286,7 +345,7 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
     auto k = sizer_kernel<THREADS, SMEM>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list);
+    k<<<blocks, THREADS, smem, ctx->stream>>>(sys_v, cand_v, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list);
   } else {
     SplitWs sw = {nullptr, nullptr, nullptr};
     const bool split = ctx->lane_sizer_mode == 4 || ctx->lane_sizer_mode == 5;
@@ -323,8 +382,8 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
       unsigned* v_out = (unsigned*)((char*)ctx->order_ws.p + 3 * arr);
       void* d_tmp = (char*)ctx->order_ws.p + 4 * arr;
       const unsigned pb = (unsigned)((n_items + 127) / 128);
-      if (split) sizer_probe_kernel<true><<<pb, 128, 0, ctx->stream>>>(ctx->sys, n_items, nmax, k_in, v_in);
-      else sizer_probe_kernel<false><<<pb, 128, 0, ctx->stream>>>(ctx->sys, n_items, nmax, k_in, v_in);
+      if (split) sizer_probe_kernel<true><<<pb, 128, 0, ctx->stream>>>(sys_v, n_items, nmax, k_in, v_in);
+      else sizer_probe_kernel<false><<<pb, 128, 0, ctx->stream>>>(sys_v, n_items, nmax, k_in, v_in);
       e = cub::DeviceRadixSort::SortPairsDescending(d_tmp, tmp, k_in, k_out, v_in, v_out, (int)n_items, 0, 32, ctx->stream);
       if (e != cudaSuccess) return e;
       ctx->launches += 4;
@@ -338,7 +397,7 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
       k = sizer_lane_kernel_gtab_2blk;                 // the same body under a 128-register cap (2 blocks per SM)
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<blocks, THREADS, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list, sw, order, do_gang ? 1 : 0);
+    k<<<blocks, THREADS, smem, ctx->stream>>>(sys_v, cand_v, n_pairs, nmax, gtab, ctx->d_ctr, ovf_list, sw, order, do_gang ? 1 : 0);
   }
   ctx->launches++;
   return cudaGetLastError();
@@ -349,7 +408,7 @@ static cudaError_t launch_sizer_warp(wva_ctx* ctx, int blocks, size_t smem, unsi
   auto k = sizer_warp_kernel<WARPS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<blocks, WARPS * 32, smem, ctx->stream>>>(ctx->sys, ctx->cand, n_pairs, nmax, ctx->d_ctr, ovf_list);
+  k<<<blocks, WARPS * 32, smem, ctx->stream>>>(shard_sys(ctx), shard_cand(ctx), n_pairs, nmax, ctx->d_ctr, ovf_list);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -372,9 +431,13 @@ int32_t wva_calculate(wva_ctx* ctx) {
   if (!ctx) return WVA_ERR_ARG;
   if (!ctx->loaded) { ctx->last_error = "wva_calculate before wva_load_system"; return WVA_ERR_STATE; }
   CK(cudaSetDevice(ctx->device));
-  const unsigned long long n_pairs = (unsigned long long)ctx->S * ctx->A;
-  // scratch: counters + overflow list + nmax reduction
-  size_t need = 256 + 256 + (size_t)n_pairs * 4 + 1024;
+  const SysView sys_v = shard_sys(ctx);
+  const CandView cand_v = shard_cand(ctx);
+  const unsigned long long n_pairs = (unsigned long long)sys_v.n_servers * ctx->A;
+  ctx->shard_status = WVA_ERR_CUDA;   // until this call returns WVA_OK (agreed on by all ranks in wva_solve)
+  // scratch: counters + nmax reduction + overflow list.  The split sizer modes process a pair as TWO items and each may
+  // append the pair (both chains of an alpha-dominated pair overflow at lambda_max): 2 entries per pair.
+  size_t need = 256 + 256 + (size_t)n_pairs * 8 + 1024;
   CK(ctx->scratch.reserve(need));
   ctx->d_ctr = (SizerCounters*)ctx->scratch.p;
   int* d_nmax = (int*)((char*)ctx->scratch.p + 256);
@@ -385,7 +448,7 @@ int32_t wva_calculate(wva_ctx* ctx) {
     // 1) largest batch size any pair will use -> table geometry
     int blocks = (int)((n_pairs + 255) / 256);
     if (blocks > 4096) blocks = 4096;
-    max_batch_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->sys, n_pairs, d_nmax);
+    max_batch_kernel<<<blocks, 256, 0, ctx->stream>>>(sys_v, n_pairs, d_nmax);
     ctx->launches++;
     int nmax = 0;
     CK(cudaMemcpyAsync(&nmax, d_nmax, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -467,43 +530,45 @@ int32_t wva_calculate(wva_ctx* ctx) {
   if (hc.limit_hit) { ctx->last_error = "a (server, accelerator) pair needs a max batch size above 65536"; return WVA_ERR_LIMIT; }
   if (hc.overflow_pairs) {
     // float64 overflow-rescale branch (mm1modelstatedependent.go:84-89,96-104): exact slow path
-    int32_t rc = run_overflow_slow_path(ctx->sys, ctx->cand, d_ovf, (int)hc.overflow_pairs, ctx->stream, &ctx->launches);
+    int32_t rc = run_overflow_slow_path(sys_v, cand_v, d_ovf, (int)hc.overflow_pairs, ctx->stream, &ctx->launches);
     if (rc != 0) { ctx->last_error = "overflow slow path failed"; return WVA_ERR_CUDA; }
     CK(cudaStreamSynchronize(ctx->stream));
   }
   ctx->calculated = true; ctx->solved = false;
+  ctx->shard_status = WVA_OK;
   return WVA_OK;
 }
 
 // ------------------------------------------------------------------ solve
-int32_t wva_solve(wva_ctx* ctx) {
-  if (!ctx) return WVA_ERR_ARG;
-  if (!ctx->calculated) { ctx->last_error = "wva_solve before wva_calculate"; return WVA_ERR_STATE; }
-  CK(cudaSetDevice(ctx->device));
-  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-  const int S = ctx->S, T = ctx->T;
+}  // extern "C"
+
+// allocator + AllocateByType on a view (the whole system, or the rank's block of servers)
+static int32_t solve_view(wva_ctx* ctx, const SysView& sv, const CandView& cv, const SolView& ov) {
+  const int S = sv.n_servers, T = ctx->T;
   if (S > 0) {
     if (ctx->unlimited) {
       int blocks = (int)(((size_t)S * 32 + 255) / 256);
-      solve_unlimited_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->sys, ctx->cand, ctx->sol);
+      solve_unlimited_kernel<<<blocks, 256, 0, ctx->stream>>>(sv, cv, ov);
       ctx->launches++;
     } else {
-      int32_t rc = run_solve_greedy(ctx->sys, ctx->cand, ctx->sol, ctx->delayed, ctx->policy, &ctx->greedy_ws.p,
-                                    &ctx->greedy_ws.cap, ctx->stream, &ctx->launches);
+      long long gstats[2] = {0, 0};
+      int32_t rc = run_solve_greedy(sv, cv, ov, ctx->delayed, ctx->policy, &ctx->greedy_ws.p,
+                                    &ctx->greedy_ws.cap, ctx->stream, &ctx->launches, gstats);
       if (rc != 0) { ctx->last_error = "SolveGreedy failed"; return rc; }
+      ctx->timing.greedy_heap_pushes = gstats[0]; ctx->timing.greedy_events = gstats[1];
     }
   }
   // AllocateByType
   int nparts = (S + 255) / 256;
   if (nparts < 1) nparts = 1;
   size_t need = (size_t)nparts * (T > 0 ? T : 1) * 16 + 512;
-  // reuse scratch beyond its first 512 bytes (counters)
+  // reuse scratch beyond its first 1024 bytes (counters)
   CK(ctx->scratch.reserve(1024 + need));
   long long* pc = (long long*)((char*)ctx->scratch.p + 1024);
   double* pd = (double*)((char*)ctx->scratch.p + 1024 + (size_t)nparts * (T > 0 ? T : 1) * 8);
   if (T > 0) {
     if (S > 0) {
-      by_type_partial_kernel<<<nparts, 256, 0, ctx->stream>>>(ctx->sys, ctx->sol, pc, pd);
+      by_type_partial_kernel<<<nparts, 256, 0, ctx->stream>>>(sv, ov, pc, pd);
       ctx->launches++;
     } else {
       CK(cudaMemsetAsync(pc, 0, need - 512, ctx->stream));
@@ -512,10 +577,46 @@ int32_t wva_solve(wva_ctx* ctx) {
     ctx->launches++;
   }
   CK(cudaGetLastError());
+  return WVA_OK;
+}
+
+extern "C" {
+
+int32_t wva_solve(wva_ctx* ctx) {
+  if (!ctx) return WVA_ERR_ARG;
+  if (!ctx->calculated && ctx->world == 1) { ctx->last_error = "wva_solve before wva_calculate"; return WVA_ERR_STATE; }
+  if (!ctx->loaded) { ctx->last_error = "wva_solve before wva_load_system"; return WVA_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  ctx->timing.exchange_ms = 0.0f; ctx->timing.greedy_heap_pushes = 0; ctx->timing.greedy_events = 0;
+  int32_t rc;
+  if (ctx->world > 1) rc = comm_exchange_and_solve(ctx);
+  else rc = solve_view(ctx, ctx->sys, ctx->cand, ctx->sol);
+  if (rc != WVA_OK) return rc;
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->timing.solve_ms = elapsed(ctx, 4, 5);
   ctx->solved = true;
+  return WVA_OK;
+}
+
+// OptimizerSpec / CapacityData of the loaded system replaced in place (sizing reads neither)
+int32_t wva_set_optimizer(wva_ctx* ctx, int32_t unlimited, int32_t delayed_best_effort, int32_t saturation_policy) {
+  if (!ctx || saturation_policy < WVA_POLICY_NONE || saturation_policy > WVA_POLICY_ROUND_ROBIN) return WVA_ERR_ARG;
+  if (!ctx->loaded) { ctx->last_error = "wva_set_optimizer before wva_load_system"; return WVA_ERR_STATE; }
+  ctx->unlimited = unlimited ? 1 : 0; ctx->delayed = delayed_best_effort ? 1 : 0; ctx->policy = saturation_policy;
+  ctx->solved = false;
+  return WVA_OK;
+}
+int32_t wva_set_capacity(wva_ctx* ctx, const int32_t* type_count) {
+  if (!ctx || (!type_count && ctx->T > 0)) return WVA_ERR_ARG;
+  if (!ctx->loaded) { ctx->last_error = "wva_set_capacity before wva_load_system"; return WVA_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->T > 0) {
+    CK(cudaMemcpyAsync((void*)ctx->sys.type_count, type_count, (size_t)ctx->T * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->solved = false;
   return WVA_OK;
 }
 
@@ -609,3 +710,4 @@ int32_t wva_get_solution(wva_ctx* ctx, wva_solution* out) {
 }  // extern "C"
 
 #include "capi_aux.inl"
+#include "comm.inl"

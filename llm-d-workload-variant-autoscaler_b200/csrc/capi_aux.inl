@@ -9,7 +9,7 @@ static cudaError_t launch_grid(wva_ctx* ctx, int blocks, size_t smem, int R, con
   auto k = grid_kernel<WARPS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<blocks, WARPS * 32, smem, ctx->stream>>>(ctx->sys, R, o, n_pairs, nmax, ctr);
+  k<<<blocks, WARPS * 32, smem, ctx->stream>>>(shard_sys(ctx), R, o, n_pairs, nmax, ctr);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -30,7 +30,8 @@ extern "C" int32_t wva_grid_run(wva_ctx* ctx, int32_t R, int32_t full) {
   if (!ctx->loaded) { ctx->last_error = "wva_grid_run before wva_load_system"; return WVA_ERR_STATE; }
   CK(cudaSetDevice(ctx->device));
   GridState& g = ctx->grid;
-  const size_t P = (size_t)ctx->S * ctx->A, n = P * (size_t)R;
+  const SysView sys_v = shard_sys(ctx);        // with a communicator: the rank's block of servers
+  const size_t P = (size_t)sys_v.n_servers * ctx->A, n = P * (size_t)R;
   Layout L;
   size_t o_ctr = L.take(256), o_nmax = L.take(256), o_front = L.take(P * 4);
   size_t o_ok = 0, o_ttft = 0, o_itl = 0, o_rho = 0, o_tput = 0;
@@ -50,7 +51,7 @@ extern "C" int32_t wva_grid_run(wva_ctx* ctx, int32_t R, int32_t full) {
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   if (P > 0) {
     int blocks = (int)((P + 255) / 256); if (blocks > 4096) blocks = 4096;
-    max_batch_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->sys, (unsigned long long)P, d_nmax);
+    max_batch_kernel<<<blocks, 256, 0, ctx->stream>>>(sys_v, (unsigned long long)P, d_nmax);
     ctx->launches++;
     int nmax = 0;
     CK(cudaMemcpyAsync(&nmax, d_nmax, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -90,7 +91,7 @@ extern "C" int32_t wva_grid_fetch(wva_ctx* ctx, uint8_t* ok, float* ttft, float*
   if (!g.ran) { ctx->last_error = "wva_grid_fetch before wva_grid_run"; return WVA_ERR_STATE; }
   if ((ok || ttft || itl || rho || tput) && !g.full) { ctx->last_error = "grid was run without full outputs"; return WVA_ERR_STATE; }
   CK(cudaSetDevice(ctx->device));
-  const size_t P = (size_t)ctx->S * ctx->A, n = P * (size_t)g.R;
+  const size_t P = (size_t)(ctx->shard_hi - ctx->shard_lo) * ctx->A, n = P * (size_t)g.R;
   CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   if (ok && n) CK(cudaMemcpyAsync(ok, g.view.ok, n, cudaMemcpyDeviceToHost, ctx->stream));
   if (ttft && n) CK(cudaMemcpyAsync(ttft, g.view.ttft, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -211,8 +212,14 @@ extern "C" int32_t wva_saturation_upload(wva_ctx* ctx, const wva_saturation_in* 
 extern "C" int32_t wva_saturation_run(wva_ctx* ctx, int32_t detail) {
   if (!ctx) return WVA_ERR_ARG;
   SatState& st = ctx->sat;
-  if (!st.uploaded) { ctx->last_error = "wva_saturation_run before wva_saturation_upload"; return WVA_ERR_STATE; }
   CK(cudaSetDevice(ctx->device));
+  if (ctx->world > 1) {   // every rank learns whether every rank has a batch: nobody is left alone in the all-reduce
+    int agreed = 0;
+    int32_t rc = comm_agree_status(ctx, st.uploaded ? WVA_OK : WVA_ERR_STATE, &agreed);
+    if (rc != WVA_OK) return rc;
+    if (agreed != WVA_OK) { ctx->last_error = "wva_saturation_run: a rank has no uploaded batch"; return agreed; }
+  }
+  if (!st.uploaded) { ctx->last_error = "wva_saturation_run before wva_saturation_upload"; return WVA_ERR_STATE; }
   SatOut w = st.vout;
   if (!detail) {
     w.var_replica_count = nullptr; w.var_non_saturated = nullptr; w.var_max_kv = nullptr; w.var_max_queue = nullptr;
@@ -233,8 +240,13 @@ extern "C" int32_t wva_saturation_run(wva_ctx* ctx, int32_t detail) {
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  {
+    int32_t rc = comm_reduce_sat_partials(ctx, w.partials, w.partials + 4);   // partials_all (one ncclAllReduce)
+    if (rc != WVA_OK) return rc;
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->timing.saturation_ms = elapsed(ctx, 2, 3);
+  ctx->timing.exchange_ms = ctx->world > 1 ? elapsed(ctx, 0, 1) : 0.0f;
   st.ran = true;
   return WVA_OK;
 }
@@ -254,7 +266,7 @@ extern "C" int32_t wva_saturation_fetch(wva_ctx* ctx, const wva_saturation_out* 
       {out->var_avg_spare_queue, w.var_avg_spare_queue, V * 8}, {out->rep_saturated, w.rep_saturated, P},
       {out->mod_total_replicas, w.mod_total_replicas, M * 4}, {out->mod_non_saturated, w.mod_non_saturated, M * 4},
       {out->mod_avg_spare_kv, w.mod_avg_spare_kv, M * 8}, {out->mod_avg_spare_queue, w.mod_avg_spare_queue, M * 8},
-      {out->mod_flags, w.mod_flags, M}, {out->partials, w.partials, 32}};
+      {out->mod_flags, w.mod_flags, M}, {out->partials, w.partials, 32}, {out->partials_all, w.partials + 4, 32}};
   for (auto& x : cp)
     if (x.dst && x.b) CK(cudaMemcpyAsync(x.dst, x.src, x.b, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(ctx->ev[7], ctx->stream));

@@ -74,6 +74,7 @@ struct GreedyWs {   // device workspace views
   // allocateEqually tickets, [S] indexed by ticket
   int* tk_srv; int* tk_type; int* tk_rank; int* tk_want; int* tk_nrep; long long* tk_upr;
   long long* avail;  // [T] (used when the types do not fit the shared-memory copy)
+  long long* stats;  // [2] heap pushes, events (entries processed) of the last sweep
 };
 
 __global__ void __launch_bounds__(128) greedy_prepare_kernel(SysView s, CandView c, GreedyWs w) {
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(32, 1) greedy_allocate_kernel(SysView s, Greed
 #endif
   GP_T(t_all);
   unsigned tau = 0;
+  long long n_events = 0;
   int head = 0, n_un = 0, group_un0 = 0, base = -32;
   g_u64 l_khi = 0; unsigned l_kv = 0; int l_type = -1, l_srv = -1; long long l_cnt = 0;   // this lane's head record
   unsigned group_pw = 0;
@@ -486,6 +488,7 @@ __global__ void __launch_bounds__(32, 1) greedy_allocate_kernel(SysView s, Greed
       }
     }
     GP_ADD(0, t_it); GP_INC(8);
+    n_events++;
     if (from_heap) { GP_T(t_pop); e = heap.pop(); GP_ADD(1, t_pop); GP_INC(9); } else head++;
     GP_T(t_fit);
     if (e.type < 0) continue;                       // no accelerator behind the candidate: dropped (greedy.go:126-136)
@@ -566,6 +569,7 @@ __global__ void __launch_bounds__(32, 1) greedy_allocate_kernel(SysView s, Greed
   __syncwarp();
   { GP_T(t_be); if (delayed) g_best_effort(s, w, avail, w.unalloc, n_un, policy); GP_ADD(6, t_be); }
   GP_ADD(7, t_all);
+  if (writer) { w.stats[0] = (long long)tau; w.stats[1] = n_events; }
 #ifdef WVA_GREEDY_PROFILE
   if (writer) for (int i = 0; i < 16; i++) g_prof[i] = prof[i];
 #endif
@@ -598,7 +602,8 @@ __global__ void __launch_bounds__(256) greedy_finalize_kernel(SysView s, CandVie
 
 // host driver; ws/ws_cap: a growable device allocation owned by the ctx
 static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, const SolView& o, int delayed, int policy,
-                                       void** ws, size_t* ws_cap, cudaStream_t stream, long long* launches) {
+                                       void** ws, size_t* ws_cap, cudaStream_t stream, long long* launches,
+                                       long long* stats_out = nullptr) {
   const size_t S = (size_t)s.n_servers, A = (size_t)s.n_acc, T = (size_t)s.n_types;
   size_t off = 0;
   auto take = [&](size_t b) { size_t o2 = off; off = (off + b + 255) & ~(size_t)255; return o2; };
@@ -609,7 +614,7 @@ static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, cons
                o_hkh = take(S * 8), o_hkl = take(S * 8), o_hcn = take(S * 8), o_hs = take(S * 4), o_hc = take(S * 4), o_ht = take(S * 4),
                o_un = take(S * 4), o_kind = take(S), o_sr = take(S * 4), o_sn = take(S * 4),
                o_ts = take(S * 4), o_tt = take(S * 4), o_tr = take(S * 4), o_tw = take(S * 4), o_tn = take(S * 4), o_tu = take(S * 8),
-               o_av = take(T * 8 + 8);
+               o_av = take(T * 8 + 8), o_st = take(64);
   size_t tmp = 0, tb = 0;
   cub::CountingInputIterator<int> cnt(0);
   cub::DeviceSelect::Flagged(nullptr, tb, cnt, (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, (int)S, stream);
@@ -639,6 +644,7 @@ static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, cons
   w.tk_srv = (int*)(d + o_ts); w.tk_type = (int*)(d + o_tt); w.tk_rank = (int*)(d + o_tr); w.tk_want = (int*)(d + o_tw);
   w.tk_nrep = (int*)(d + o_tn); w.tk_upr = (long long*)(d + o_tu);
   w.avail = (long long*)(d + o_av);
+  w.stats = (long long*)(d + o_st);
   void* d_tmp = d + o_tmp;
   const unsigned nb = (unsigned)((S + 255) / 256);
   greedy_prepare_kernel<<<(unsigned)((S + 127) / 128), 128, 0, stream>>>(s, c, w);
@@ -665,6 +671,10 @@ static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, cons
   greedy_allocate_kernel<<<1, 32, G_SMEM_BYTES, stream>>>(s, w, delayed, policy);
   greedy_finalize_kernel<<<nb, 256, 0, stream>>>(s, c, o, w);
   *launches += 2;
+  if (stats_out) {
+    if (cudaMemcpyAsync(stats_out, w.stats, 16, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return WVA_ERR_CUDA;
+  }
 #ifdef WVA_GREEDY_PROFILE
   {
     long long h[16];

@@ -59,6 +59,18 @@ def load_library():
     L.wva_launch_count.argtypes = [ctxp]
     L.wva_launch_count.restype = C.c_int64
     L.wva_set_option.argtypes = [ctxp, C.c_int32, C.c_int32]
+    L.wva_set_optimizer.argtypes = [ctxp, C.c_int32, C.c_int32, C.c_int32]
+    L.wva_set_capacity.argtypes = [ctxp, C.c_void_p]
+    L.wva_comm_unique_id.argtypes = [C.c_void_p]
+    L.wva_comm_init_rank.argtypes = [ctxp, C.c_int32, C.c_int32, C.c_void_p]
+    L.wva_comm_shard.argtypes = [ctxp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.wva_group_create.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ctxp)]
+    L.wva_group_destroy.argtypes = [ctxp]
+    L.wva_group_size.argtypes = [ctxp]
+    L.wva_group_ctx.argtypes = [ctxp, C.c_int32]
+    L.wva_group_ctx.restype = ctxp
+    L.wva_group_optimize.argtypes = [ctxp, C.POINTER(abi.System), C.POINTER(abi.Solution)]
+    L.wva_group_saturation_v1.argtypes = [ctxp, C.POINTER(abi.SaturationIn), C.POINTER(abi.SaturationOut)]
     L.wva_load_system.argtypes = [ctxp, C.POINTER(abi.System)]
     L.wva_calculate.argtypes = [ctxp]
     L.wva_solve.argtypes = [ctxp]
@@ -91,7 +103,19 @@ EXPORTS = ["wva_set_option", "wva_create", "wva_destroy", "wva_strerror", "wva_l
            "wva_analyze_grid", "wva_grid_run", "wva_grid_fetch", "wva_mm1k_eval", "wva_saturation_v1",
            "wva_saturation_upload", "wva_saturation_run", "wva_saturation_fetch", "wva_limit", "wva_saturation_v2",
            "wva_cost_aware_optimize", "wva_enforce", "wva_pipeline_v2", "wva_host_alloc", "wva_host_free", "wva_last_timing",
-           "wva_microbench_fp64"]
+           "wva_microbench_fp64", "wva_set_optimizer", "wva_set_capacity", "wva_comm_unique_id", "wva_comm_init_rank",
+           "wva_comm_shard", "wva_group_create", "wva_group_destroy", "wva_group_size", "wva_group_ctx",
+           "wva_group_optimize", "wva_group_saturation_v1"]
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL id for wva_comm_init_rank: made on ONE rank, carried to the others by the host."""
+    lib = load_library()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.wva_comm_unique_id(buf)
+    if rc != abi.WVA_OK:
+        raise WvaError(f"wva_comm_unique_id: {lib.wva_strerror(rc).decode()}")
+    return bytes(buf)
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:
@@ -133,6 +157,8 @@ class Engine:
             self.ctx = None
             raise WvaError(f"wva_create(device={device}) failed: {self.lib.wva_strerror(rc).decode()}")
         self.S = self.A = self.T = 0
+        self.lo = self.hi = 0          # block of servers this context sizes (the whole system without a communicator)
+        self.world, self.rank = 1, 0
         # optional allocator (name, n, dtype) -> 1-D array for the result buffers of saturation_fetch() and limit(),
         # e.g. views of page-locked buffers from pinned_empty() that the caller reuses from batch to batch
         self.host_alloc = None
@@ -156,11 +182,34 @@ class Engine:
     def set_option(self, option: int, value: int):
         self._check(self.lib.wva_set_option(self.ctx, option, value), "wva_set_option")
 
+    # ---- multi-GPU ----------------------------------------------------------------------------
+    def comm_init(self, world: int, rank: int, unique_id: bytes):
+        """Join the NCCL communicator of `world` contexts (before load_system).  From then on calculate() sizes this
+        rank's block of servers and solve() exchanges over NVLink inside the library (include/wva_b200.h)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.wva_comm_init_rank(self.ctx, world, rank, buf), "wva_comm_init_rank")
+        self.world, self.rank = world, rank
+
+    def set_optimizer(self, unlimited: bool, delayed_best_effort: bool = False, saturation_policy="None"):
+        """OptimizerSpec of the loaded system, replaced in place (candidates stay valid)."""
+        pol = abi.POLICY_NAMES[saturation_policy] if isinstance(saturation_policy, str) else int(saturation_policy)
+        self._check(self.lib.wva_set_optimizer(self.ctx, int(bool(unlimited)), int(bool(delayed_best_effort)), pol),
+                    "wva_set_optimizer")
+
+    def set_capacity(self, type_count):
+        a = np.ascontiguousarray(type_count, np.int32)
+        if a.size != self.T:
+            raise WvaError(f"set_capacity: {a.size} types, the loaded system has {self.T}")
+        self._check(self.lib.wva_set_capacity(self.ctx, a.ctypes.data), "wva_set_capacity")
+
     # ---- queueing sizing + allocator ------------------------------------------------------
     def load_system(self, sysd: dict):
         st, keep = abi.make_system(sysd)
         self._check(self.lib.wva_load_system(self.ctx, C.byref(st)), "wva_load_system")
         self.S, self.A, self.T = st.n_servers, st.n_acc, st.n_types
+        lo, hi = C.c_int32(), C.c_int32()
+        self._check(self.lib.wva_comm_shard(self.ctx, C.byref(lo), C.byref(hi)), "wva_comm_shard")
+        self.lo, self.hi = lo.value, hi.value
 
     def calculate(self):
         self._check(self.lib.wva_calculate(self.ctx), "wva_calculate")
@@ -194,7 +243,7 @@ class Engine:
         return self.solution()
 
     def analyze_grid(self, R: int, full: bool = True, frontier: bool = True):
-        S, A = self.S, self.A
+        S, A = self.hi - self.lo, self.A          # with a communicator: this rank's block of servers
         n = S * A * R
         out = {}
         if full:
@@ -215,9 +264,10 @@ class Engine:
         self._check(self.lib.wva_grid_run(self.ctx, R, 1 if full else 0), "wva_grid_run")
 
     def grid_fetch_frontier(self):
-        f = np.zeros(max(self.S * self.A, 1), dtype=np.int32)
+        S = self.hi - self.lo
+        f = np.zeros(max(S * self.A, 1), dtype=np.int32)
         self._check(self.lib.wva_grid_fetch(self.ctx, None, None, None, None, None, f.ctypes.data), "wva_grid_fetch")
-        return f[: self.S * self.A].reshape(self.S, self.A)
+        return f[: S * self.A].reshape(S, self.A)
 
     def mm1k_eval(self, lam, mu, K):
         lam = np.ascontiguousarray(lam, np.float32); mu = np.ascontiguousarray(mu, np.float32)
@@ -341,3 +391,52 @@ class Engine:
         a, b = C.c_double(), C.c_double()
         self._check(self.lib.wva_microbench_fp64(self.ctx, C.byref(a), C.byref(b)), "wva_microbench_fp64")
         return a.value, b.value
+
+
+class Group:
+    """wva_group: ONE host process driving several GPUs (what the Go controller does) — n contexts joined by one NCCL
+    communicator inside the library, one host thread per device."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        dev = np.ascontiguousarray(devices, np.int32)
+        self.g = C.c_void_p()
+        rc = self.lib.wva_group_create(dev.ctypes.data, int(dev.size), C.byref(self.g))
+        if rc != abi.WVA_OK:
+            self.g = None
+            raise WvaError(f"wva_group_create({list(dev)}) failed: {self.lib.wva_strerror(rc).decode()}")
+        self.n = int(dev.size)
+
+    def close(self):
+        if self.g:
+            self.lib.wva_group_destroy(self.g)
+            self.g = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _err(self, rc, what):
+        if rc != abi.WVA_OK:
+            details = [self.lib.wva_last_error(self.lib.wva_group_ctx(self.g, i)).decode() for i in range(self.n)]
+            raise WvaError(f"{what}: {self.lib.wva_strerror(rc).decode()} {[d for d in details if d]}")
+
+    def optimize(self, sysd: dict):
+        """Manager.Optimize over the group (replicated load, sharded sizing, NVLink exchange, allocator)."""
+        st, keep = abi.make_system(sysd)
+        sst, sol = abi.alloc_solution(st.n_servers, st.n_types)
+        self._err(self.lib.wva_group_optimize(self.g, C.byref(st), C.byref(sst)), "wva_group_optimize")
+        return sol
+
+    def saturation_v1(self, d: dict):
+        ist, keep = abi.make_saturation_in(d)
+        ost, out = abi.alloc_saturation_out(ist.n_models, ist.n_variants, ist.n_replicas)
+        self._err(self.lib.wva_group_saturation_v1(self.g, C.byref(ist), C.byref(ost)), "wva_group_saturation_v1")
+        return out
+
+    def timing(self, i: int) -> dict:
+        t = abi.Timing()
+        self.lib.wva_last_timing(self.lib.wva_group_ctx(self.g, i), C.byref(t))
+        return {k: getattr(t, k) for k, _ in abi.Timing._fields_}

@@ -191,6 +191,9 @@ int64_t wva_launch_count(const wva_ctx* ctx);
 #define WVA_OPT_GANG_REFILL 3      /* 1: a warp of the lane sizer takes 32 new items only when all its
                                       lanes are idle (lanes stay in the same bisection step); 0: lanes refill
                                       one by one; -1 (default): as WVA_OPT_LENGTH_SORT.  Scheduling only */
+#define WVA_OPT_TABLE_MODE 4       /* lane sizer head table: 0 (default) shared memory when >= 64 lanes per SM fit, else
+                                      global memory; 1 force shared memory (when it fits at all); 2 force global memory
+                                      (two 256-thread blocks per SM under a 128-register cap).  Placement only */
 int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value);
 
 /* ---- multi-GPU: model-sharded over one NCCL communicator ----------------- */

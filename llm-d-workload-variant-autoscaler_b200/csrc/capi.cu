@@ -95,6 +95,7 @@ struct wva_ctx {
   bool force_lane_sizer = false;
   int gang_refill = -1;             // lock-step lane sizer: a warp refills only when all its lanes are idle; -1 = by size
   int length_sort = -1;             // lane sizer pulls items through the probe-sorted permutation (sizer_probe.cuh); -1 = by size
+  int table_mode = 0;        // WVA_OPT_TABLE_MODE
   int lane_sizer_mode = 2;   // 1 flattened, 2 lock-step (default), 3 lock-step with two chains per lane (slower: measured)
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
@@ -424,6 +425,7 @@ int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
   }
   if (option == WVA_OPT_LENGTH_SORT) { ctx->length_sort = value < 0 ? -1 : (value != 0); return WVA_OK; }
   if (option == WVA_OPT_GANG_REFILL) { ctx->gang_refill = value < 0 ? -1 : (value != 0); return WVA_OK; }
+  if (option == WVA_OPT_TABLE_MODE) { if (value < 0 || value > 2) return WVA_ERR_ARG; ctx->table_mode = value; return WVA_OK; }
   return WVA_ERR_ARG;
 }
 
@@ -500,7 +502,7 @@ int32_t wva_calculate(wva_ctx* ctx) {
         e = launch_sizer_warp<4>(ctx, ctx->sm_count * per_sm, warp_tab * 4, n_pairs, nmax, d_ovf);
       }
     } else
-    if (best_per_sm >= 1) {
+    if (best_per_sm >= 1 && ctx->table_mode != 2) {
       int blocks = ctx->sm_count * best_per_sm;
       size_t smem = per_lane * best_threads;
       switch (best_threads) {

@@ -75,7 +75,7 @@ struct GridState {   // results of the last wva_grid_run, resident in HBM
 struct SatState {    // resident inputs / outputs of the saturation model
   bool uploaded = false, ran = false;
   long long M = 0, V = 0, P = 0;
-  DevBuf in, out;
+  DevBuf in, out, desc;
   SatIn vin = {};
   SatOut vout = {};
   size_t out_bytes = 0;
@@ -207,7 +207,7 @@ int32_t wva_destroy(wva_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->sys_arena.release(); ctx->cand_arena.release(); ctx->sol_arena.release(); ctx->scratch.release();
-  ctx->gtab.release(); ctx->greedy_ws.release(); ctx->split_ws.release(); ctx->order_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->io_in.release(); ctx->io_out.release();
+  ctx->gtab.release(); ctx->greedy_ws.release(); ctx->split_ws.release(); ctx->order_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->sat.desc.release(); ctx->io_in.release(); ctx->io_out.release();
   ctx->stage_in.release(); ctx->stage_out.release(); ctx->io_stage_in.release(); ctx->io_stage_out.release();
   comm_release(ctx); ctx->comm_ws.release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);

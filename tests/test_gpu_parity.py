@@ -377,7 +377,7 @@ def test_greedy_at_scale_10k(pkg, engine, oracle, policy, delayed, frac):
 def test_greedy_at_scale_100k(pkg, engine, oracle, policy, delayed, frac):
     """BASELINE configs[2] size: 100 000 servers x 32 accelerators (the oracle's sweep takes ~5 s per case on one core)."""
     t = _greedy_scale_case(pkg, engine, oracle, 100_000, frac, policy, delayed)
-    assert t["greedy_heap_pushes"] > 4096, t      # the heap left its shared-memory tier (greedy_solve.cuh G_HEAP_SM)
+    assert t["greedy_events"] >= 100_000 * 0.9, t
 
 
 def test_greedy_zero_capacity(pkg, engine, oracle):

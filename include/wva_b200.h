@@ -194,6 +194,9 @@ int64_t wva_launch_count(const wva_ctx* ctx);
 #define WVA_OPT_TABLE_MODE 4       /* lane sizer head table: 0 (default) shared memory when >= 64 lanes per SM fit, else
                                       global memory; 1 force shared memory (when it fits at all); 2 force global memory
                                       (two 256-thread blocks per SM under a 128-register cap).  Placement only */
+#define WVA_OPT_GREEDY_MODE 5      /* limited-capacity allocator: 0 (default) the static-order event sweep
+                                      (csrc/greedy_sweep.cuh) wherever it applies; 1 the literal queue (sorted array +
+                                      re-insertion heap, csrc/greedy_solve.cuh).  Same result either way */
 int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value);
 
 /* ---- multi-GPU: model-sharded over one NCCL communicator ----------------- */

@@ -15,6 +15,7 @@
 #include "pipeline_v2_kernel.cuh"
 #include "greedy_kernel.cuh"
 #include "greedy_solve.cuh"
+#include "greedy_sweep.cuh"
 #include "mm1k_kernel.cuh"
 
 #include <cuda_runtime.h>
@@ -96,6 +97,7 @@ struct wva_ctx {
   int gang_refill = -1;             // lock-step lane sizer: a warp refills only when all its lanes are idle; -1 = by size
   int length_sort = -1;             // lane sizer pulls items through the probe-sorted permutation (sizer_probe.cuh); -1 = by size
   int table_mode = 0;        // WVA_OPT_TABLE_MODE
+  int greedy_mode = 0;       // WVA_OPT_GREEDY_MODE
   int lane_sizer_mode = 2;   // 1 flattened, 2 lock-step (default), 3 lock-step with two chains per lane (slower: measured)
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
@@ -425,6 +427,7 @@ int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
   }
   if (option == WVA_OPT_LENGTH_SORT) { ctx->length_sort = value < 0 ? -1 : (value != 0); return WVA_OK; }
   if (option == WVA_OPT_GANG_REFILL) { ctx->gang_refill = value < 0 ? -1 : (value != 0); return WVA_OK; }
+  if (option == WVA_OPT_GREEDY_MODE) { if (value < 0 || value > 1) return WVA_ERR_ARG; ctx->greedy_mode = value; return WVA_OK; }
   if (option == WVA_OPT_TABLE_MODE) { if (value < 0 || value > 2) return WVA_ERR_ARG; ctx->table_mode = value; return WVA_OK; }
   return WVA_ERR_ARG;
 }
@@ -554,8 +557,12 @@ static int32_t solve_view(wva_ctx* ctx, const SysView& sv, const CandView& cv, c
       ctx->launches++;
     } else {
       long long gstats[2] = {0, 0};
-      int32_t rc = run_solve_greedy(sv, cv, ov, ctx->delayed, ctx->policy, &ctx->greedy_ws.p,
-                                    &ctx->greedy_ws.cap, ctx->stream, &ctx->launches, gstats);
+      // the static-order sweep (greedy_sweep.cuh) wherever it applies; the literal queue otherwise or on request
+      const bool sweep = ctx->greedy_mode != 1 && greedy_sweep_covers(sv);
+      int32_t rc = sweep ? run_solve_greedy_sweep(sv, cv, ov, ctx->delayed, ctx->policy, &ctx->greedy_ws.p,
+                                                  &ctx->greedy_ws.cap, ctx->stream, &ctx->launches, gstats)
+                         : run_solve_greedy(sv, cv, ov, ctx->delayed, ctx->policy, &ctx->greedy_ws.p,
+                                            &ctx->greedy_ws.cap, ctx->stream, &ctx->launches, gstats);
       if (rc != 0) { ctx->last_error = "SolveGreedy failed"; return rc; }
       ctx->timing.greedy_heap_pushes = gstats[0]; ctx->timing.greedy_events = gstats[1];
     }

@@ -230,17 +230,17 @@ extern "C" int32_t wva_saturation_run(wva_ctx* ctx, int32_t detail) {
   CK(cudaMemsetAsync(w.partials, 0, 64, ctx->stream));
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   if (st.M > 0) {
-    // chunk descriptors (two dependent CSR look-ups per 8 models), then the streaming kernel: persistent CTAs, two per
-    // SM, each with a ring of SAT_NS stages filled by cp.async.bulk (saturation_kernel.cuh)
-    const long long n_chunks = (st.M + SAT_G - 1) / SAT_G;
-    CK(st.desc.reserve((size_t)n_chunks * sizeof(SatChunk)));
-    SatChunk* d_desc = (SatChunk*)st.desc.p;
-    saturation_chunk_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, ctx->stream>>>(st.vin, d_desc, n_chunks);
-    long long blocks = (long long)ctx->sm_count * 2;
-    if (blocks > n_chunks) blocks = n_chunks;
+    // per-model descriptors (the two dependent CSR look-ups), then the streaming kernel: persistent CTAs, three per SM,
+    // every warp its own cp.async.bulk pipeline (saturation_kernel.cuh)
+    CK(st.desc.reserve((size_t)st.M * sizeof(SatDesc)));
+    SatDesc* d_desc = (SatDesc*)st.desc.p;
+    saturation_desc_kernel<<<(unsigned)((st.M + 255) / 256), 256, 0, ctx->stream>>>(st.vin, d_desc);
+    long long blocks = (long long)ctx->sm_count * 3;
+    const long long need_blocks = (st.M + SAT_WARPS - 1) / SAT_WARPS;
+    if (blocks > need_blocks) blocks = need_blocks;
     auto k = detail ? saturation_kernel<true> : saturation_kernel<false>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SAT_SMEM_BYTES));
-    k<<<(unsigned)blocks, SAT_G * 32, SAT_SMEM_BYTES, ctx->stream>>>(st.vin, w, d_desc, n_chunks);
+    k<<<(unsigned)blocks, SAT_WARPS * 32, SAT_SMEM_BYTES, ctx->stream>>>(st.vin, w, d_desc);
     ctx->launches += 2;
     CK(cudaGetLastError());
   }

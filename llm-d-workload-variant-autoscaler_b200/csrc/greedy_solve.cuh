@@ -600,11 +600,10 @@ __global__ void __launch_bounds__(256) greedy_finalize_kernel(SysView s, CandVie
   o.max_arrv_rate[srv] = c.max_arrv_rate[i];
 }
 
-// host driver; ws/ws_cap: a growable device allocation owned by the ctx
-static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, const SolView& o, int delayed, int policy,
-                                       void** ws, size_t* ws_cap, cudaStream_t stream, long long* launches,
-                                       long long* stats_out = nullptr) {
-  const size_t S = (size_t)s.n_servers, A = (size_t)s.n_acc, T = (size_t)s.n_types;
+// workspace layout shared by the two formulations of the sweep; `extra` bytes are appended for the caller
+// (ws/ws_cap: a growable device allocation owned by the ctx)
+static inline int32_t greedy_layout(size_t S, size_t A, size_t T, size_t extra, void** ws, size_t* ws_cap, GreedyWs& w,
+                                    size_t& tmp_bytes, void** d_tmp_out, char** extra_out) {
   size_t off = 0;
   auto take = [&](size_t b) { size_t o2 = off; off = (off + b + 255) & ~(size_t)255; return o2; };
   const size_t o_order = take(S * A * 4), o_ncand = take(S * 4), o_rkd = take(S * A * 4), o_rkv = take(S * A * 4),
@@ -617,21 +616,20 @@ static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, cons
                o_av = take(T * 8 + 8), o_st = take(64);
   size_t tmp = 0, tb = 0;
   cub::CountingInputIterator<int> cnt(0);
-  cub::DeviceSelect::Flagged(nullptr, tb, cnt, (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, (int)S, stream);
+  const size_t n_sel = S * A > S ? S * A : S;
+  cub::DeviceSelect::Flagged(nullptr, tb, cnt, (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, (int)n_sel, 0);
   tmp = tb;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, (int)S, 0, 32, stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, (int)n_sel, 0, 32, 0);
   if (tb > tmp) tmp = tb;
   const size_t o_tmp = take(tmp + 256);
+  const size_t o_extra = take(extra);
   if (off + 256 > *ws_cap) {
     if (*ws) cudaFree(*ws);
     *ws = nullptr; *ws_cap = 0;
     if (cudaMalloc(ws, off + 256) != cudaSuccess) return WVA_ERR_NOMEM;
     *ws_cap = off + 256;
   }
-  if (cudaFuncSetAttribute(greedy_allocate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES) != cudaSuccess)
-    return WVA_ERR_CUDA;
   char* d = (char*)*ws;
-  GreedyWs w;
   w.order = (int*)(d + o_order); w.ncand = (int*)(d + o_ncand);
   w.r_kd = (unsigned*)(d + o_rkd); w.r_kv = (unsigned*)(d + o_rkv); w.r_type = (int*)(d + o_rty); w.r_nrep = (int*)(d + o_rnr);
   w.r_upr = (long long*)(d + o_rup);
@@ -645,7 +643,28 @@ static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, cons
   w.tk_nrep = (int*)(d + o_tn); w.tk_upr = (long long*)(d + o_tu);
   w.avail = (long long*)(d + o_av);
   w.stats = (long long*)(d + o_st);
-  void* d_tmp = d + o_tmp;
+  tmp_bytes = tmp;
+  *d_tmp_out = d + o_tmp;
+  if (extra_out) *extra_out = d + o_extra;
+  return WVA_OK;
+}
+
+// host driver of the literal queue (sorted array + re-insertion heap)
+static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, const SolView& o, int delayed, int policy,
+                                       void** ws, size_t* ws_cap, cudaStream_t stream, long long* launches,
+                                       long long* stats_out = nullptr) {
+  const size_t S = (size_t)s.n_servers;
+  GreedyWs w;
+  size_t tmp = 0;
+  void* d_tmp0 = nullptr;
+  {
+    int32_t rc = greedy_layout(S, (size_t)s.n_acc, (size_t)s.n_types, 0, ws, ws_cap, w, tmp, &d_tmp0, nullptr);
+    if (rc != WVA_OK) return rc;
+  }
+  cub::CountingInputIterator<int> cnt(0);
+  if (cudaFuncSetAttribute(greedy_allocate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES) != cudaSuccess)
+    return WVA_ERR_CUDA;
+  void* d_tmp = d_tmp0;
   const unsigned nb = (unsigned)((S + 255) / 256);
   greedy_prepare_kernel<<<(unsigned)((S + 127) / 128), 128, 0, stream>>>(s, c, w);
   size_t t2 = tmp;

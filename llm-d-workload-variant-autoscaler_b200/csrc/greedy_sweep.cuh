@@ -1,0 +1,399 @@
+// greedy_sweep.cuh — Solver.SolveGreedy's allocate() (pkg/solver/greedy.go:107-166) as ONE sweep over a statically
+// ordered list of candidate events.  (The literal queue — sorted array + re-insertion heap — stays in greedy_solve.cuh
+// and is still used for systems this formulation does not cover; both produce the oracle's result bit for bit.)
+//
+// allocate() is a priority queue over entries, keyed by the entry's CURRENT candidate j:
+//     k(e, j) = (priority asc, delta_j desc, value_j desc),   re-inserted BEFORE equal elements (greedy.go:161-162).
+// Event (e, j) — "entry e is tested at its j-th candidate" — can only happen after (e, j-1) failed, and then it is
+// popped at queue position  tau(e, j) = max_{i <= j} k(e, i): a re-inserted key that is not after the queue head is popped
+// at once, so the event inherits the position of its predecessor.  tau depends on the entry alone.  Therefore all
+// S x A potential events are sorted ONCE by tau (radix sort, parallel); what remains sequential is a sweep that keeps
+// one "alive" bit per entry and the available units per type: an event whose entry is no longer alive is skipped, an
+// alive one is dropped (no accelerator), taken (fits) or fails (its entry stays alive for its next event; after the last
+// candidate it joins the unallocated list, greedy.go:152-156).  No heap, no per-bump search: the sweep streams 16-byte
+// event records through shared memory (cp.async ring) and spends its dependent instructions only on alive events.
+//
+// Ties in tau are where the queue's LIFO rule shows: among the events of one tau, the runs led by a RE-INSERTED
+// candidate (key == tau > tau of its predecessor) come first, most recent insertion first; then the runs led by an
+// original entry (j == 0) in canonical (server index) order; the events of one entry with the same tau form a run that is
+// processed back to back (every later one is popped "at once").  The static order puts re-inserted runs first in entry
+// order, which is exact whenever at most one of them is alive when its tau is reached; where a tie group statically
+// holds two or more re-inserted leaders (flag MULTI) the sweep collects the alive ones and orders them by the stamp of
+// their predecessors' failure — the insertion time.  tools/proto/greedy_static_order.py is the executable form of this
+// argument (checked against the oracle's literal sorted-slice algorithm, duplicates and zero-load ties included).
+#pragma once
+#include "greedy_solve.cuh"
+
+namespace wva {
+
+struct __align__(16) GEvent { int srv; unsigned meta; long long cnt; };   // meta = type (8, 0xff = none) | flags (8) | rank (16)
+enum { GE_TIE = 1, GE_LEADER = 2, GE_CLS1 = 4, GE_LAST = 8, GE_NEWPRIO = 16, GE_MULTI = 32 };
+__device__ __forceinline__ int ge_type(unsigned meta) { const int t = (int)(meta & 0xffu); return t == 0xff ? -1 : t; }
+__device__ __forceinline__ unsigned ge_flags(unsigned meta) { return (meta >> 8) & 0xffu; }
+__device__ __forceinline__ int ge_rank(unsigned meta) { return (int)(meta >> 16); }
+
+struct GSweepWs {
+  // dense, indexed (server, rank): tau components and flags of every potential event
+  unsigned* t_kd; unsigned* t_kv; unsigned char* fl; unsigned char* valid;
+  // compaction + sort
+  unsigned* idxA; unsigned* idxB; unsigned* keyA; unsigned* keyB; int* n_events;
+  // sorted events
+  GEvent* ev;
+  int* stamp;        // [S] clock of the entry's last failure
+  int* dyn_pos; int* dyn_stamp;   // [S] scratch of the tie-group procedure
+};
+
+// tau, run class and flags of every (server, rank); after greedy_prepare_kernel
+__global__ void __launch_bounds__(128) gsw_events_kernel(SysView s, GreedyWs w, GSweepWs g) {
+  const int srv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (srv >= s.n_servers) return;
+  const int A = s.n_acc;
+  const size_t p = (size_t)srv * A;
+  const int n = w.ncand[srv];
+  unsigned tkd = 0, tkv = 0;
+  int cls = 1;
+  for (int j = 0; j < n; j++) {
+    const unsigned kd = w.r_kd[p + j], kv = w.r_kv[p + j];
+    const bool leader = j == 0 || kd > tkd || (kd == tkd && kv > tkv);
+    if (leader) { tkd = kd; tkv = kv; cls = j == 0 ? 1 : 0; }
+    g.t_kd[p + j] = tkd; g.t_kv[p + j] = tkv;
+    g.fl[p + j] = (unsigned char)((leader ? GE_LEADER : 0) | (cls ? GE_CLS1 : 0) | (j == n - 1 ? GE_LAST : 0));
+    g.valid[p + j] = 1;
+  }
+  for (int j = n; j < A; j++) g.valid[p + j] = 0;
+  g.stamp[srv] = 0;
+}
+
+// one LSD radix pass over the compacted events: which = 0 run class (re-inserted first), 1 tau value, 2 tau delta, 3 priority
+__global__ void __launch_bounds__(256) gsw_keys_kernel(SysView s, GSweepWs g, const unsigned* idx, int n, int which, unsigned* keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned p = idx[i];
+  if (which == 0) keys[i] = (g.fl[p] & GE_CLS1) ? 1u : 0u;
+  else if (which == 1) keys[i] = g.t_kv[p];
+  else if (which == 2) keys[i] = g.t_kd[p];
+  else keys[i] = (unsigned)s.srv_priority[p / (unsigned)s.n_acc] ^ 0x80000000u;
+}
+
+// sorted order -> 16-byte event records with the tie / priority-boundary flags
+__global__ void __launch_bounds__(256) gsw_gather_kernel(SysView s, GreedyWs w, GSweepWs g, const unsigned* idx, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned A = (unsigned)s.n_acc;
+  const unsigned p = idx[i];
+  const int srv = (int)(p / A), j = (int)(p % A);
+  unsigned flags = g.fl[p];
+  if (i == 0) flags |= GE_NEWPRIO;
+  else {
+    const unsigned q = idx[i - 1];
+    const int psrv = (int)(q / A);
+    const bool same_prio = s.srv_priority[psrv] == s.srv_priority[srv];
+    if (!same_prio) flags |= GE_NEWPRIO;
+    else if (g.t_kd[q] == g.t_kd[p] && g.t_kv[q] == g.t_kv[p]) flags |= GE_TIE;
+  }
+  const int ty = w.r_type[p];
+  GEvent e;
+  e.srv = srv;
+  e.meta = (unsigned)(ty < 0 ? 0xff : ty) | (flags << 8) | ((unsigned)j << 16);
+  e.cnt = (long long)w.r_nrep[p] * w.r_upr[p];
+  g.ev[i] = e;
+}
+
+// MULTI: the event leads a re-inserted run and its tie group holds another re-inserted leader.  Bounded walks; when a
+// walk does not reach the end of the group's re-inserted part the flag is set (conservative: the sweep's tie-group
+// procedure is exact for any number of alive leaders, including one).
+__global__ void __launch_bounds__(256) gsw_multi_kernel(GSweepWs g, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned m = g.ev[i].meta;
+  const unsigned f = ge_flags(m);
+  if (!(f & GE_LEADER) || (f & GE_CLS1)) return;
+  bool multi = false, open = false;
+  // forward: the re-inserted part continues while TIE && !CLS1
+  int k = i + 1, steps = 0;
+  for (; k < n && steps < 64; k++, steps++) {
+    const unsigned fk = ge_flags(g.ev[k].meta);
+    if (!(fk & GE_TIE) || (fk & GE_CLS1)) break;
+    if (fk & GE_LEADER) { multi = true; break; }
+  }
+  if (!multi && steps == 64) open = true;
+  // backward: events before i belong to the same part while THIS side's TIE flag is set
+  if (!multi) {
+    int b = i; steps = 0;
+    while (b > 0 && (ge_flags(g.ev[b].meta) & GE_TIE) && steps < 64) {
+      b--; steps++;
+      const unsigned fb = ge_flags(g.ev[b].meta);
+      if (fb & GE_CLS1) break;                       // cannot happen (re-inserted runs come first), kept for safety
+      if (fb & GE_LEADER) { multi = true; break; }
+    }
+    if (!multi && steps == 64) open = true;
+  }
+  if (multi || open) g.ev[i].meta = m | ((unsigned)GE_MULTI << 8);
+}
+
+constexpr int GSW_BLOCK = 512;            // events per ring slot (8 KB)
+constexpr int GSW_SLOTS = 4;
+constexpr int GSW_ALIVE_WORDS = 40 * 1024; // alive bits for up to 1 310 720 entries in shared memory (160 KB)
+constexpr int GSW_AVAIL = 64;              // capacity types (WVA_MAX_TYPES)
+constexpr size_t GSW_SMEM = (size_t)GSW_BLOCK * GSW_SLOTS * sizeof(GEvent) + (size_t)GSW_ALIVE_WORDS * 4 + GSW_AVAIL * 8;
+
+__device__ __forceinline__ void gsw_cp16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gsw_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void gsw_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct GSweep {
+  const SysView& s; const GreedyWs& w; const GSweepWs& g;
+  long long* avail; unsigned* alive;
+  int n_un, clock;
+  long long n_active;
+  __device__ bool is_alive(int srv) const { return (alive[srv >> 5] >> (srv & 31)) & 1u; }
+  __device__ void kill(int srv) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) alive[srv >> 5] &= ~(1u << (srv & 31));
+    __syncwarp();
+  }
+  // one alive event (greedy.go:120-165); every lane holds the same arguments.  Returns true when the entry left the queue.
+  __device__ bool process(int srv, unsigned meta, long long cnt) {
+    const bool writer = (threadIdx.x & 31) == 0;
+    n_active++;
+    const int type = ge_type(meta);
+    if (type < 0) { kill(srv); return true; }                                   // no accelerator: dropped (:126-136)
+    if (avail[type] >= cnt) {                                                    // :143-145
+      __syncwarp();
+      if (writer) { avail[type] -= cnt; w.kind[srv] = 1; w.sel_rank[srv] = ge_rank(meta); }
+      kill(srv);
+      return true;
+    }
+    clock++;
+    if (writer) g.stamp[srv] = clock;                                            // when the next candidate is (re-)inserted
+    if (ge_flags(meta) & GE_LAST) {                                              // :152-156
+      if (writer) w.unalloc[n_un] = srv;
+      n_un++;
+      kill(srv);
+      return true;
+    }
+    return false;
+  }
+};
+
+// The re-inserted part of a tie group with several statically possible leaders, entered at its first ALIVE leader i0:
+// collect the alive leaders, process their runs latest-insertion first.  Returns the position after the part, or -1 when
+// i0 is the only alive leader (the caller then processes it in the normal flow).
+__device__ __noinline__ int gsw_tie_group(GSweep& z, int i0, int n_ev) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int n_act = 0, i = i0;
+  __syncwarp();
+  while (true) {
+    const int idx = i + lane;
+    const bool v = idx < n_ev;
+    unsigned m = 0; int sv = 0;
+    if (v) { const GEvent e = z.g.ev[idx]; m = e.meta; sv = e.srv; }
+    const unsigned f = ge_flags(m);
+    const bool in_part = v && (idx == i0 || (f & GE_TIE)) && !(f & GE_CLS1);
+    const unsigned stop = __ballot_sync(full, !in_part);
+    const int nin = stop ? __ffs(stop) - 1 : 32;
+    const bool is_cand = lane < nin && (f & GE_LEADER) && z.is_alive(sv);
+    const unsigned cm = __ballot_sync(full, is_cand);
+    if (is_cand) {
+      const int slot = n_act + __popc(cm & ((1u << lane) - 1u));
+      z.g.dyn_pos[slot] = idx;
+      z.g.dyn_stamp[slot] = *((volatile int*)&z.g.stamp[sv]);
+    }
+    n_act += __popc(cm);
+    i += nin;
+    if (nin < 32) break;
+  }
+  const int end_pos = i;
+  if (n_act <= 1) return -1;
+  __syncwarp();
+  __threadfence_block();
+  for (int k = 0; k < n_act; k++) {
+    // latest insertion first: arg-max of the remaining stamps (stamps are distinct clock values > 0)
+    int best = -1, best_slot = -1;
+    for (int q = lane; q < n_act; q += 32) {
+      const int st = *((volatile int*)&z.g.dyn_stamp[q]);
+      if (st > best) { best = st; best_slot = q; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      const int ob = __shfl_xor_sync(full, best, o), os = __shfl_xor_sync(full, best_slot, o);
+      if (ob > best) { best = ob; best_slot = os; }
+    }
+    __syncwarp();
+    if (lane == 0) z.g.dyn_stamp[best_slot] = -1;
+    __threadfence_block();
+    __syncwarp();
+    int r = *((volatile int*)&z.g.dyn_pos[best_slot]);
+    const int srv0 = z.g.ev[r].srv;
+    for (int first = r; r < end_pos; r++) {
+      const GEvent e = z.g.ev[r];
+      if (r > first && (e.srv != srv0 || !(ge_flags(e.meta) & GE_TIE))) break;
+      if (!z.is_alive(srv0)) break;
+      if (z.process(e.srv, e.meta, e.cnt)) break;
+    }
+  }
+  return end_pos;
+}
+
+__global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w, GSweepWs g, int delayed, int policy) {
+  extern __shared__ __align__(16) unsigned char gsw_smem[];
+  GEvent* ring = reinterpret_cast<GEvent*>(gsw_smem);
+  unsigned* alive = reinterpret_cast<unsigned*>(gsw_smem + (size_t)GSW_BLOCK * GSW_SLOTS * sizeof(GEvent));
+  long long* avail = reinterpret_cast<long long*>(alive + GSW_ALIVE_WORDS);
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int n_ev = *g.n_events;
+  const int S = s.n_servers;
+  for (int t = lane; t < s.n_types; t += 32) avail[t] = s.type_count[t];          // greedy.go:38-39
+  for (int k = lane; k < (S + 31) / 32; k += 32) alive[k] = 0xffffffffu;
+  __syncwarp();
+  GSweep z{s, w, g, avail, alive, 0, 0, 0};
+  int group_un0 = 0;
+
+  // event stream: blocks of GSW_BLOCK records copied asynchronously into a ring of GSW_SLOTS slots; while block b is
+  // read, blocks b+1 .. b+GSW_SLOTS-1 are in flight.  One commit group per block (empty past the end of the list).
+  int origin = 0;               // event index of block 0 of the current stream (changes only after a far tie-group jump)
+  int issued = 0;               // blocks of the current stream whose copies have been issued
+  int cur_block = -1;
+  auto issue_block = [&](int bb) {
+    const int base = origin + bb * GSW_BLOCK;
+    GEvent* dst = ring + (size_t)(bb % GSW_SLOTS) * GSW_BLOCK;
+    for (int k = lane; k < GSW_BLOCK; k += 32)
+      if (base + k < n_ev) gsw_cp16(dst + k, g.ev + base + k);
+    gsw_commit();
+  };
+  auto start_stream = [&](int at) {
+    gsw_wait<0>();
+    __syncwarp();
+    origin = at; issued = 0; cur_block = -1;
+  };
+  start_stream(0);
+  int pos = 0;
+  while (pos < n_ev) {
+    const int rel = pos - origin;
+    const int b = rel / GSW_BLOCK;
+    if (b != cur_block) {
+      __syncwarp();                                 // every lane is done reading the slot that is refilled next
+      while (issued < b + GSW_SLOTS) { issue_block(issued); issued++; }
+      // block b is complete once at most (issued - b - 1) younger groups are pending
+      const int younger = issued - b - 1;
+      if (younger <= 0) gsw_wait<0>();
+      else if (younger == 1) gsw_wait<1>();
+      else if (younger == 2) gsw_wait<2>();
+      else gsw_wait<3>();
+      __syncwarp();
+      cur_block = b;
+    }
+    const GEvent* blk = ring + (size_t)(b % GSW_SLOTS) * GSW_BLOCK;
+    const int in_blk = rel % GSW_BLOCK;
+    const int i = pos + lane;
+    const bool valid = in_blk + lane < GSW_BLOCK && i < n_ev;
+    GEvent me; me.srv = -1; me.meta = 0; me.cnt = 0;
+    if (valid) me = blk[in_blk + lane];
+    const int nvalid = min(min(32, GSW_BLOCK - in_blk), n_ev - pos);
+    const bool al = valid && z.is_alive(me.srv);
+    unsigned act = __ballot_sync(full, al);
+    unsigned npm = delayed ? 0u : __ballot_sync(full, valid && (ge_flags(me.meta) & GE_NEWPRIO));
+    const unsigned peers = __match_any_sync(full, me.srv);
+    int jump = -1;
+    while (act | npm) {
+      const int la = act ? __ffs(act) - 1 : 32, lp = npm ? __ffs(npm) - 1 : 32;
+      if (lp <= la) {
+        // a new priority group starts here: allocate() of the previous group is complete -> its bestEffort()
+        // (greedy.go:96-103), on the entries it left unallocated, in the order they were exhausted
+        npm &= npm - 1;
+        if (z.n_un > group_un0) { g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy); }
+        group_un0 = z.n_un;
+        continue;
+      }
+      act &= act - 1;
+      const int e_srv = __shfl_sync(full, me.srv, la);
+      const unsigned e_meta = __shfl_sync(full, me.meta, la);
+      const long long e_cnt = __shfl_sync(full, me.cnt, la);
+      if (ge_flags(e_meta) & GE_MULTI) {
+        const int np = gsw_tie_group(z, pos + la, n_ev);
+        if (np >= 0) { jump = np; break; }
+      }
+      if (z.process(e_srv, e_meta, e_cnt)) act &= ~__shfl_sync(full, peers, la);   // later events of this entry in the batch are dead
+    }
+    if (jump >= 0) {
+      pos = jump;
+      if (pos < n_ev && pos - origin >= issued * GSW_BLOCK) start_stream(pos);        // jumped past everything in flight
+    } else {
+      pos += nvalid;
+    }
+  }
+  __syncwarp();
+  // the last group's (or, delayed, the whole list's) best effort
+  if (z.n_un > group_un0) g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy);
+  if (lane == 0) { w.stats[0] = 0; w.stats[1] = z.n_active; }
+}
+
+// host driver of the static-order sweep.  Returns WVA_ERR_LIMIT (nothing launched) when the system is outside what this
+// formulation covers — the caller then runs the literal queue (run_solve_greedy).
+static inline bool greedy_sweep_covers(const SysView& s) {
+  return (size_t)s.n_servers <= (size_t)GSW_ALIVE_WORDS * 32 && s.n_types <= GSW_AVAIL && s.n_types < 255 && s.n_acc <= 65535 &&
+         (size_t)s.n_servers * (size_t)s.n_acc < (size_t)0x7fffffff;
+}
+static inline int32_t run_solve_greedy_sweep(const SysView& s, const CandView& c, const SolView& o, int delayed, int policy,
+                                             void** ws, size_t* ws_cap, cudaStream_t stream, long long* launches,
+                                             long long* stats_out = nullptr) {
+  static_assert(GSW_SLOTS <= 4, "cp.async.wait_group immediates cover up to 3 younger groups");
+  const size_t S = (size_t)s.n_servers, A = (size_t)s.n_acc, P = S * A;
+  size_t eo = 0;
+  auto etake = [&](size_t b) { size_t o2 = eo; eo = (eo + b + 255) & ~(size_t)255; return o2; };
+  const size_t e_tkd = etake(P * 4), e_tkv = etake(P * 4), e_fl = etake(P), e_va = etake(P), e_ia = etake(P * 4), e_ib = etake(P * 4),
+               e_ka = etake(P * 4), e_kb = etake(P * 4), e_ne = etake(64), e_ev = etake(P * sizeof(GEvent) + 64), e_st = etake(S * 4),
+               e_dp = etake(S * 4), e_ds = etake(S * 4);
+  GreedyWs w;
+  size_t tmp = 0;
+  void* d_tmp = nullptr;
+  char* ex = nullptr;
+  {
+    int32_t rc = greedy_layout(S, A, (size_t)s.n_types, eo + 256, ws, ws_cap, w, tmp, &d_tmp, &ex);
+    if (rc != WVA_OK) return rc;
+  }
+  GSweepWs g;
+  g.t_kd = (unsigned*)(ex + e_tkd); g.t_kv = (unsigned*)(ex + e_tkv); g.fl = (unsigned char*)(ex + e_fl); g.valid = (unsigned char*)(ex + e_va);
+  g.idxA = (unsigned*)(ex + e_ia); g.idxB = (unsigned*)(ex + e_ib); g.keyA = (unsigned*)(ex + e_ka); g.keyB = (unsigned*)(ex + e_kb);
+  g.n_events = (int*)(ex + e_ne); g.ev = (GEvent*)(ex + e_ev); g.stamp = (int*)(ex + e_st); g.dyn_pos = (int*)(ex + e_dp);
+  g.dyn_stamp = (int*)(ex + e_ds);
+  if (cudaFuncSetAttribute(gsw_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSW_SMEM) != cudaSuccess) return WVA_ERR_CUDA;
+  const unsigned sb = (unsigned)((S + 127) / 128);
+  greedy_prepare_kernel<<<sb, 128, 0, stream>>>(s, c, w);
+  gsw_events_kernel<<<sb, 128, 0, stream>>>(s, w, g);
+  cub::CountingInputIterator<unsigned> cnt(0u);
+  size_t t2 = tmp;
+  if (cub::DeviceSelect::Flagged(d_tmp, t2, cnt, g.valid, g.idxA, g.n_events, (int)P, stream) != cudaSuccess) return WVA_ERR_CUDA;
+  int n = 0;
+  if (cudaMemcpyAsync(&n, g.n_events, 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
+  if (cudaStreamSynchronize(stream) != cudaSuccess) return WVA_ERR_CUDA;
+  *launches += 3;
+  unsigned* cur = g.idxA; unsigned* alt = g.idxB;
+  if (n > 0) {
+    const unsigned cb = (unsigned)((n + 255) / 256);
+    for (int which = 0; which < 4; which++) {   // LSD: run class, tau value, tau delta, priority (each pass stable)
+      gsw_keys_kernel<<<cb, 256, 0, stream>>>(s, g, cur, n, which, g.keyA);
+      t2 = tmp;
+      if (cub::DeviceRadixSort::SortPairs(d_tmp, t2, g.keyA, g.keyB, cur, alt, n, 0, which == 0 ? 1 : 32, stream) != cudaSuccess)
+        return WVA_ERR_CUDA;
+      unsigned* sw = cur; cur = alt; alt = sw;
+      *launches += 2;
+    }
+    gsw_gather_kernel<<<cb, 256, 0, stream>>>(s, w, g, cur, n);
+    gsw_multi_kernel<<<cb, 256, 0, stream>>>(g, n);
+    *launches += 2;
+  }
+  gsw_sweep_kernel<<<1, 32, GSW_SMEM, stream>>>(s, w, g, delayed, policy);
+  greedy_finalize_kernel<<<(unsigned)((S + 255) / 256), 256, 0, stream>>>(s, c, o, w);
+  *launches += 2;
+  if (stats_out) {
+    if (cudaMemcpyAsync(stats_out, w.stats, 16, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return WVA_ERR_CUDA;
+  }
+  return cudaGetLastError() == cudaSuccess ? WVA_OK : WVA_ERR_CUDA;
+}
+
+}  // namespace wva

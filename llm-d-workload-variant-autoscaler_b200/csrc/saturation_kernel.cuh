@@ -4,16 +4,16 @@
 // CalculateSaturationTargets (analyzer.go:290-439).
 //
 // HBM-bound by design: 16 B per replica (kv float64 + queue int64) + 32 B per variant + 40 B per model, each read once.
-// The stream is moved by the TMA unit, not by the warps: the models are cut into chunks of SAT_G = 8 consecutive
-// models (one per warp of the CTA); the CSR layout makes everything a chunk needs CONTIGUOUS in each of the 13 input
-// arrays, so one elected thread issues 13 `cp.async.bulk` (1-D TMA) copies global -> shared memory per chunk, completing
-// on an mbarrier, into a ring of SAT_NS stages: two chunks (~2 x 25 KB) are always in flight per CTA, two CTAs per SM.
-// The warps never touch global memory for input; they wait on the stage's mbarrier, then analyse their model out of
-// shared memory: one lane per variant streams its replicas in slice order (the per-variant float64 sums are order
-// dependent), the variant -> model accumulation runs in ascending variant index (broadcast reads, fixed 32-step
-// unrolled chain; lanes without metrics contribute an exact +0.0), the cheapest / most-expensive variant search runs
-// only for the models that scale.  A chunk whose ranges exceed a stage (a model with thousands of replicas) takes the
-// same code over global memory instead.
+// One warp per model, every warp its own software pipeline — no block-level synchronisation anywhere:
+//   * the replica stream (the two big arrays, one contiguous range per model thanks to the CSR layout) is moved by the
+//     TMA unit: lane 0 issues two `cp.async.bulk` (1-D TMA) copies global -> shared memory per model, completing on the
+//     warp's own mbarrier, SAT_NS models ahead of the one being analysed (24 warps x ~2.3 KB in flight per SM);
+//   * the per-variant arrays (24 B per variant) are read directly, one lane per variant: perfectly coalesced;
+//   * a lane then streams its variant's replicas out of shared memory in slice order (the per-variant float64 sums are
+//     order dependent), the variant -> model accumulation runs in ascending variant index (broadcast reads, fixed
+//     32-step unrolled chain; lanes without metrics contribute an exact +0.0), and the cheapest / most-expensive
+//     variant is a two-word warp arg-min on the order-preserving bit pattern of the cost.
+// A model with more replicas than a stage holds (SAT_CAP) takes the same code over global memory instead.
 #pragma once
 #include "wva_core.cuh"
 
@@ -56,43 +56,34 @@ __device__ __forceinline__ double div_small_int(double x, int n) {
   return d_div(x, nd);
 }
 
-// ---- chunk geometry ------------------------------------------------------------------------------------------------
-constexpr int SAT_G = 8;             // models per chunk = warps per CTA
-constexpr int SAT_NS = 3;            // stages per CTA
-constexpr int SAT_CAP_REP = 1536;    // replicas a stage holds (8 models x 32 variants x 4.5 replicas = 1152 on average)
-constexpr int SAT_CAP_VAR = 288;     // variants a stage holds
+// ---- per-warp staging geometry -----------------------------------------------------------------------------------------
+constexpr int SAT_WARPS = 8;         // warps (= models in flight) per CTA
+constexpr int SAT_NS = 2;            // stages per warp
+constexpr int SAT_CAP = 256;         // replicas a stage holds (32 variants x 8 replicas)
 
-struct alignas(128) SatStage {       // every member starts on a 16-byte boundary (cp.async.bulk destination)
-  double kv[SAT_CAP_REP + 2];
-  long long q[SAT_CAP_REP + 2];
-  double cost[SAT_CAP_VAR + 2];
-  double cfg[4][SAT_G];
-  int vro[SAT_CAP_VAR + 8];
-  int cur[SAT_CAP_VAR + 4], des[SAT_CAP_VAR + 4], pen[SAT_CAP_VAR + 4];
-  int mvo[SAT_G + 4];
-  unsigned char hs[SAT_CAP_VAR + 32];
+struct alignas(16) SatStage {        // both arrays start on a 16-byte boundary (cp.async.bulk destination)
+  double kv[SAT_CAP + 2];
+  long long q[SAT_CAP + 2];
 };
-static_assert(sizeof(SatStage) % 128 == 0 && offsetof(SatStage, q) % 16 == 0 && offsetof(SatStage, cost) % 16 == 0 &&
-              offsetof(SatStage, cfg) % 16 == 0 && offsetof(SatStage, vro) % 16 == 0 && offsetof(SatStage, cur) % 16 == 0 &&
-              offsetof(SatStage, des) % 16 == 0 && offsetof(SatStage, pen) % 16 == 0 && offsetof(SatStage, mvo) % 16 == 0 &&
-              offsetof(SatStage, hs) % 16 == 0, "SatStage members must be 16-byte aligned");
-constexpr size_t SAT_SMEM_BYTES = sizeof(SatStage) * SAT_NS + 128;
+struct alignas(16) SatWarpSmem {
+  SatStage stage[SAT_NS];
+  double2 terms[32];
+  unsigned long long bar[SAT_NS];
+};
+static_assert(sizeof(SatStage) % 16 == 0 && offsetof(SatStage, q) % 16 == 0 && offsetof(SatWarpSmem, terms) % 16 == 0, "alignment");
+constexpr size_t SAT_SMEM_BYTES = sizeof(SatWarpSmem) * SAT_WARPS;
 
-struct SatChunk { int v_lo, v_hi, r_lo, r_hi; };   // variants [v_lo, v_hi) and replicas [r_lo, r_hi) of models [c*G, (c+1)*G)
+struct SatDesc { int v0, v1, r0, r1; };   // per model: variants [v0, v1), replicas [r0, r1)
 
-// chunk descriptors: the two dependent CSR look-ups of every chunk, done once so that the copy-issuing thread of the
-// main kernel never waits on global memory (16 B per 8 models: 0.06 % of the stream)
-__global__ void __launch_bounds__(256) saturation_chunk_kernel(SatIn in, SatChunk* desc, long long n_chunks) {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_chunks) return;
-  const long long m0 = c * SAT_G, m1 = min(in.n_models, m0 + SAT_G);
-  SatChunk d;
-  d.v_lo = in.model_variant_off[m0]; d.v_hi = in.model_variant_off[m1];
-  d.r_lo = in.variant_replica_off[d.v_lo]; d.r_hi = in.variant_replica_off[d.v_hi];
-  desc[c] = d;
-}
-__device__ __forceinline__ bool sat_chunk_fits(const SatChunk& d) {
-  return d.r_hi - d.r_lo <= SAT_CAP_REP && d.v_hi - d.v_lo <= SAT_CAP_VAR;
+// the two dependent CSR look-ups of every model, done once so that the copy-issuing lane never waits on them
+// (16 B per model: 0.5 % of the stream)
+__global__ void __launch_bounds__(256) saturation_desc_kernel(SatIn in, SatDesc* desc) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= in.n_models) return;
+  SatDesc d;
+  d.v0 = in.model_variant_off[m]; d.v1 = in.model_variant_off[m + 1];
+  d.r0 = in.variant_replica_off[d.v0]; d.r1 = in.variant_replica_off[d.v1];
+  desc[m] = d;
 }
 
 // ---- PTX: mbarrier + 1-D bulk copy ----------------------------------------------------------------------------------
@@ -119,61 +110,38 @@ __device__ __forceinline__ void sat_bulk_g2s(void* dst, const void* src, unsigne
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(sat_smem_addr(dst)), "l"(src), "r"(bytes), "r"(sat_smem_addr(bar)) : "memory");
 }
-
-// where a model's inputs are read from: a stage in shared memory (indices rebased by the stage's aligned starts) or the
-// global arrays themselves (all offsets 0)
-struct SatSrc {
-  const double* kv; const long long* q; const double* cost; const int *vro, *cur, *des, *pen; const unsigned char* hs;
-  int r0, v0i, v0c, v0h;            // element index of kv[0] / vro[0], cur[0].. / cost[0] / hs[0]
-};
-
-// geometry of a staged chunk (shared by the issuing thread and the consumers)
-struct SatGeom { int r_a, v_i, v_c, v_h; unsigned n_rep, n_vro, n_var4, n_cost, n_hs; };
-__device__ __forceinline__ SatGeom sat_geom(const SatChunk& d) {
-  SatGeom g;
-  g.r_a = d.r_lo & ~1; g.v_i = d.v_lo & ~3; g.v_c = d.v_lo & ~1; g.v_h = d.v_lo & ~15;
-  g.n_rep = (unsigned)((d.r_hi - g.r_a + 1) & ~1);
-  g.n_vro = (unsigned)((d.v_hi + 1 - g.v_i + 3) & ~3);
-  g.n_var4 = (unsigned)((d.v_hi - g.v_i + 3) & ~3);
-  g.n_cost = (unsigned)((d.v_hi - g.v_c + 1) & ~1);
-  g.n_hs = (unsigned)((d.v_hi - g.v_h + 15) & ~15);
-  return g;
+__device__ __forceinline__ bool sat_staged(const SatDesc& d) { return d.r1 - d.r0 <= SAT_CAP; }
+// lane 0: the replica range of one model -> a stage (range start rounded down / length rounded up to 16 bytes; the
+// over-read of < 16 B past an array's end stays inside the input arena, whose sub-arrays are 256-byte padded)
+__device__ __forceinline__ void sat_issue(const SatIn& in, const SatDesc& d, SatStage* st, unsigned long long* bar) {
+  const int ra = d.r0 & ~1;
+  const unsigned bytes = (unsigned)((d.r1 - ra + 1) & ~1) * 8u;
+  if (bytes == 0) { sat_mbar_expect_tx(bar, 0); return; }     // phase completes at once
+  sat_mbar_expect_tx(bar, 2 * bytes);
+  sat_bulk_g2s(st->kv, in.rep_kv + ra, bytes, bar);
+  sat_bulk_g2s(st->q, in.rep_queue + ra, bytes, bar);
 }
 
-// one elected thread: all copies of a chunk onto the stage's mbarrier (over-reads of < 16 B past an array's end stay
-// inside the input arena, whose sub-arrays are 256-byte padded — capi_aux.inl wva_saturation_upload)
-__device__ __forceinline__ void sat_issue_chunk(const SatIn& in, const SatChunk& d, long long c, SatStage* st,
-                                                unsigned long long* bar) {
-  const SatGeom g = sat_geom(d);
-  const long long m0 = c * SAT_G;
-  const unsigned b_rep = g.n_rep * 8, b_vro = g.n_vro * 4, b_v4 = g.n_var4 * 4, b_cost = g.n_cost * 8, b_hs = in.var_has_state ? g.n_hs : 0;
-  const unsigned total = 2 * b_rep + b_vro + 3 * b_v4 + b_cost + b_hs + (SAT_G + 4) * 4 + 4 * SAT_G * 8;
-  sat_mbar_expect_tx(bar, total);
-  if (b_rep) { sat_bulk_g2s(st->kv, in.rep_kv + g.r_a, b_rep, bar); sat_bulk_g2s(st->q, in.rep_queue + g.r_a, b_rep, bar); }
-  sat_bulk_g2s(st->vro, in.variant_replica_off + g.v_i, b_vro, bar);
-  if (b_v4) {
-    sat_bulk_g2s(st->cur, in.var_current + g.v_i, b_v4, bar); sat_bulk_g2s(st->des, in.var_desired + g.v_i, b_v4, bar);
-    sat_bulk_g2s(st->pen, in.var_pending + g.v_i, b_v4, bar);
-  }
-  if (b_cost) sat_bulk_g2s(st->cost, in.var_cost + g.v_c, b_cost, bar);
-  if (b_hs) sat_bulk_g2s(st->hs, in.var_has_state + g.v_h, b_hs, bar);
-  sat_bulk_g2s(st->mvo, in.model_variant_off + m0, (SAT_G + 4) * 4, bar);
-  sat_bulk_g2s(st->cfg[0], in.cfg_kv_threshold + m0, SAT_G * 8, bar);
-  sat_bulk_g2s(st->cfg[1], in.cfg_queue_threshold + m0, SAT_G * 8, bar);
-  sat_bulk_g2s(st->cfg[2], in.cfg_kv_trigger + m0, SAT_G * 8, bar);
-  sat_bulk_g2s(st->cfg[3], in.cfg_queue_trigger + m0, SAT_G * 8, bar);
+// order-preserving bit pattern of a float64 (-0 == +0; NaN sorts after +inf): costs are compared through it
+__device__ __forceinline__ unsigned long long sat_sortable(double x) {
+  if (x == 0.0) x = 0.0;
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
 struct SatTally { long long n_up, n_down, n_trans, sum_targets; };
 
-// One model, one warp.  STAGED: inputs in shared memory (simple per-lane replica loop); otherwise global memory with
-// four independent loads in flight per lane.
+// One model, one warp.  kv / q: the model's replicas, element 0 = replica index `rbase` (a stage, or the global arrays
+// with rbase = 0).  STAGED selects the plain per-lane loop (shared memory) or four independent loads in flight (global).
 template <bool DETAIL, bool STAGED>
-__device__ __forceinline__ void sat_model(const SatSrc& src, const bool has_hs, long long m, int v0, int v1, double kvThr,
-                                          double qThr, double kvTrig, double qTrig, const SatOut& out, double2* my_terms,
-                                          SatTally& tally) {
+__device__ __forceinline__ void sat_model(const SatIn& in, const double* kvp, const long long* qp, const int rbase,
+                                          const long long m, const int v0, const int v1, const SatOut& out,
+                                          double2* my_terms, SatTally& tally) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const bool has_hs = in.var_has_state != nullptr;
+  const double kvThr = in.cfg_kv_threshold[m], qThr = in.cfg_queue_threshold[m];
+  const double kvTrig = in.cfg_kv_trigger[m], qTrig = in.cfg_queue_trigger[m];
   double totalSpareKv = 0.0, totalSpareQueue = 0.0;
   int nonSaturated = 0, totalReplicas = 0, nAnalysed = 0;
   bool inTransition = false;
@@ -185,71 +153,76 @@ __device__ __forceinline__ void sat_model(const SatSrc& src, const bool has_hs, 
   for (int c0 = v0; c0 < v1; c0 += 32) {
     const int v = c0 + lane;
     const bool act = v < v1;
-    int cnt = 0, ns = 0;
+    int cnt = 0, ns = 0, lo = 0, hi = 0;
     double sumKv = 0.0, sumQ = 0.0, maxKv = 0.0, avgKv = 0.0, avgQ = 0.0;
     long long maxQ = 0;
-    const bool hs = act && (!has_hs || src.hs[v - src.v0h]);
-    const int cur = hs ? src.cur[v - src.v0i] : 0, des = hs ? src.des[v - src.v0i] : 0;
-    r_cur = cur; r_des = des; r_pen = hs ? src.pen[v - src.v0i] : 0; r_cost = act ? src.cost[v - src.v0c] : 0.0;
-    if (act) {
-      const int lo = src.vro[v - src.v0i], hi = src.vro[v + 1 - src.v0i];
-      cnt = hi - lo;
-      if (STAGED) {
-        for (int r = lo; r < hi; r++) {
-          const double kv = src.kv[r - src.r0];
-          const long long q = src.q[r - src.r0];
-          const double qd = (double)q;
-          const bool sat = kv >= kvThr || qd >= qThr;                       // analyzer.go:163-164
-          if (DETAIL) { if (out.rep_saturated) out.rep_saturated[r] = sat ? 1 : 0; }
-          if (!sat) {
-            sumKv = d_add(sumKv, d_sub(kvThr, kv));                        // :170-175
-            sumQ = d_add(sumQ, d_sub(qThr, qd));
-            ns++;
-          }
-          if (DETAIL) {
-            if (kv > maxKv) maxKv = kv;                                    // :179-184
-            if (q > maxQ) maxQ = q;
-          }
+    // one coalesced round of loads per 32 variants
+    const bool hs = act && (!has_hs || in.var_has_state[v]);
+    if (act) { lo = in.variant_replica_off[v]; hi = in.variant_replica_off[v + 1]; }
+    const int cur = hs ? in.var_current[v] : 0, des = hs ? in.var_desired[v] : 0;
+    r_cur = cur; r_des = des; r_pen = hs ? in.var_pending[v] : 0; r_cost = act ? in.var_cost[v] : 0.0;
+    cnt = hi - lo;
+    if (STAGED) {
+      for (int r = lo; r < hi; r++) {
+        const double kv = kvp[r - rbase];
+        const long long q = qp[r - rbase];
+        const double qd = (double)q;
+        const bool sat = kv >= kvThr || qd >= qThr;                       // analyzer.go:163-164
+        if (DETAIL) { if (out.rep_saturated) out.rep_saturated[r] = sat ? 1 : 0; }
+        if (!sat) {
+          sumKv = d_add(sumKv, d_sub(kvThr, kv));                        // :170-175
+          sumQ = d_add(sumQ, d_sub(qThr, qd));
+          ns++;
         }
-      } else {
-        for (int base = lo; base < hi; base += 4) {
-          double kvv[4]; long long qq[4];
+        if (DETAIL) {
+          if (kv > maxKv) maxKv = kv;                                    // :179-184
+          if (q > maxQ) maxQ = q;
+        }
+      }
+    } else {
+      for (int base = lo; base < hi; base += 4) {
+        double kvv[4]; long long qq[4];
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const bool inb = base + j < hi;
-            kvv[j] = inb ? __ldg(src.kv + base + j) : 0.0;      // unstaged: src is the global arrays, r0 == 0
-            qq[j] = inb ? __ldg(src.q + base + j) : 0;
-          }
+        for (int j = 0; j < 4; j++) {
+          const bool inb = base + j < hi;
+          kvv[j] = inb ? __ldg(kvp + (base + j - rbase)) : 0.0;
+          qq[j] = inb ? __ldg(qp + (base + j - rbase)) : 0;
+        }
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            if (base + j < hi) {
-              const double kv = kvv[j];
-              const long long q = qq[j];
-              const double qd = (double)q;
-              const bool sat = kv >= kvThr || qd >= qThr;
-              if (DETAIL) { if (out.rep_saturated) out.rep_saturated[base + j] = sat ? 1 : 0; }
-              if (!sat) {
-                sumKv = d_add(sumKv, d_sub(kvThr, kv));
-                sumQ = d_add(sumQ, d_sub(qThr, qd));
-                ns++;
-              }
-              if (DETAIL) {
-                if (kv > maxKv) maxKv = kv;
-                if (q > maxQ) maxQ = q;
-              }
+        for (int j = 0; j < 4; j++) {
+          if (base + j < hi) {
+            const double kv = kvv[j];
+            const long long q = qq[j];
+            const double qd = (double)q;
+            const bool sat = kv >= kvThr || qd >= qThr;
+            if (DETAIL) { if (out.rep_saturated) out.rep_saturated[base + j] = sat ? 1 : 0; }
+            if (!sat) {
+              sumKv = d_add(sumKv, d_sub(kvThr, kv));
+              sumQ = d_add(sumQ, d_sub(qThr, qd));
+              ns++;
+            }
+            if (DETAIL) {
+              if (kv > maxKv) maxKv = kv;
+              if (q > maxQ) maxQ = q;
             }
           }
         }
       }
-      if (ns > 0) { avgKv = div_small_int(sumKv, ns); avgQ = div_small_int(sumQ, ns); }        // :190-193
-      if (DETAIL) {
-        if (out.var_replica_count) out.var_replica_count[v] = cnt;
-        if (out.var_non_saturated) out.var_non_saturated[v] = ns;
-        if (out.var_max_kv) out.var_max_kv[v] = maxKv;
-        if (out.var_max_queue) out.var_max_queue[v] = maxQ;
-        if (out.var_avg_spare_kv) out.var_avg_spare_kv[v] = avgKv;
-        if (out.var_avg_spare_queue) out.var_avg_spare_queue[v] = avgQ;
-      }
+    }
+    if (ns > 0) {                                                          // :190-193, one reciprocal for both quotients
+      const double nd = (double)ns;
+      if (ns < (1 << 24) && (in_window(sumKv) || sumKv == 0.0) && (in_window(sumQ) || sumQ == 0.0)) {
+        const double rr = rcp_f32den((float)ns, nd);
+        avgKv = div_f32den(sumKv, nd, rr); avgQ = div_f32den(sumQ, nd, rr);
+      } else { avgKv = d_div(sumKv, nd); avgQ = d_div(sumQ, nd); }
+    }
+    if (DETAIL && act) {
+      if (out.var_replica_count) out.var_replica_count[v] = cnt;
+      if (out.var_non_saturated) out.var_non_saturated[v] = ns;
+      if (out.var_max_kv) out.var_max_kv[v] = maxKv;
+      if (out.var_max_queue) out.var_max_queue[v] = maxQ;
+      if (out.var_avg_spare_kv) out.var_avg_spare_kv[v] = avgKv;
+      if (out.var_avg_spare_queue) out.var_avg_spare_queue[v] = avgQ;
     }
     const bool analysed = act && cnt > 0;   // only variants with metrics enter VariantAnalyses
     // ordered accumulation over the chunk (analyzer.go:86-94).  A variant without metrics has
@@ -307,13 +280,14 @@ __device__ __forceinline__ void sat_model(const SatSrc& src, const bool has_hs, 
                          (kvT ? SAT_FLAG_KV : 0) | (qT ? SAT_FLAG_Q : 0);
   }
   // ---- scaling candidate, only for the models that scale (analyzer.go:376-433) -------------------
+  // cheapest without pending, tie -> lower index (:378-395); else most expensive with base target > 1, tie -> higher
+  // index (:407-425).  Costs are compared through their order-preserving bit pattern: a two-word warp arg-min / arg-max.
   int plus_v = -1, minus_v = -1;
   const bool stable = nAnalysed > 0 && !inTransition;
   if (stable && (up || downSafe)) {
-    const bool want_min = up;    // cheapest without pending, tie -> lower index (:378-395)
-                                 // else most expensive with base target > 1, tie -> higher index (:407-425)
+    const bool want_min = up;
     int best_v = -1;
-    double best_c = 0.0;
+    unsigned long long best_k = 0;
     for (int c0 = v0; c0 < v1; c0 += 32) {
       const int v = c0 + lane;
       bool cand = false;
@@ -322,23 +296,28 @@ __device__ __forceinline__ void sat_model(const SatSrc& src, const bool has_hs, 
         int cnt, pen;
         if (single) { cnt = r_cnt; pen = r_pen; vcost = r_cost; }
         else {
-          cnt = src.vro[v + 1 - src.v0i] - src.vro[v - src.v0i];
-          const bool hs2 = !has_hs || src.hs[v - src.v0h];
-          pen = hs2 ? src.pen[v - src.v0i] : 0;
-          vcost = src.cost[v - src.v0c];
+          cnt = in.variant_replica_off[v + 1] - in.variant_replica_off[v];
+          const bool hs2 = !has_hs || in.var_has_state[v];
+          pen = hs2 ? in.var_pending[v] : 0;
+          vcost = in.var_cost[v];
         }
         cand = cnt > 0 && (want_min ? (pen <= 0) : (cnt > 1));
       }
-      double c = cand ? vcost : 0.0;
-      int idx = cand ? v : -1;
-      for (int o = 16; o; o >>= 1) {
-        const double oc = shfl_xor_d(full, c, o);
-        const int oi = __shfl_xor_sync(full, idx, o);
-        const bool take = oi >= 0 && (idx < 0 || (want_min ? (oc < c || (oc == c && oi < idx))
-                                                            : (oc > c || (oc == c && oi > idx))));
-        if (take) { c = oc; idx = oi; }
-      }
-      if (idx >= 0 && (best_v < 0 || (want_min ? (c < best_c) : (c >= best_c)))) { best_v = idx; best_c = c; }
+      const unsigned cm = __ballot_sync(full, cand);
+      if (!cm) continue;
+      unsigned long long k = sat_sortable(vcost);
+      if (!want_min) k = ~k;                                   // arg-max as arg-min of the complement
+      const unsigned khi = cand ? (unsigned)(k >> 32) : 0xffffffffu, klo = cand ? (unsigned)k : 0xffffffffu;
+      const unsigned mh = __reduce_min_sync(full, khi);
+      bool in_ = cand && khi == mh;
+      const unsigned ml = __reduce_min_sync(full, in_ ? klo : 0xffffffffu);
+      in_ = in_ && klo == ml;
+      const unsigned wm = __ballot_sync(full, in_);
+      // all-ones keys of non-candidates can only tie with a candidate whose key is all ones too; `in_` requires cand
+      const int wl = want_min ? (__ffs(wm) - 1) : (31 - __clz(wm));
+      const unsigned long long kk = ((unsigned long long)mh << 32) | ml;
+      // across chunks of 32: strictly better replaces; on ties the lower index stays (min) / the higher replaces (max)
+      if (best_v < 0 || kk < best_k || (!want_min && kk == best_k)) { best_v = c0 + wl; best_k = kk; }
     }
     if (want_min) plus_v = best_v; else minus_v = best_v;
   }
@@ -351,13 +330,13 @@ __device__ __forceinline__ void sat_model(const SatSrc& src, const bool has_hs, 
   for (int c0 = v0; c0 < v1; c0 += 32) {
     const int v = c0 + lane;
     if (v >= v1) continue;
-    const int cnt = single ? r_cnt : src.vro[v + 1 - src.v0i] - src.vro[v - src.v0i];
-    const bool hs = !has_hs || src.hs[v - src.v0h];
+    const int cnt = single ? r_cnt : in.variant_replica_off[v + 1] - in.variant_replica_off[v];
+    const bool hs = !has_hs || in.var_has_state[v];
     int tgt;
-    if (nAnalysed == 0) tgt = hs ? (single ? r_cur : src.cur[v - src.v0i]) : -1;   // nil safety :303-309
+    if (nAnalysed == 0) tgt = hs ? (single ? r_cur : in.var_current[v]) : -1;   // nil safety :303-309
     else if (cnt == 0) tgt = -1;                                      // not in VariantAnalyses
     else if (inTransition) {                                          // :350-359
-      const int cur = single ? r_cur : (hs ? src.cur[v - src.v0i] : 0), des = single ? r_des : (hs ? src.des[v - src.v0i] : 0);
+      const int cur = single ? r_cur : (hs ? in.var_current[v] : 0), des = single ? r_des : (hs ? in.var_desired[v] : 0);
       tgt = (des != 0 && des != cur) ? des : cur;
     } else tgt = cnt + (v == plus_v ? 1 : 0) - (v == minus_v ? 1 : 0);   // :362, :399, :428
     if (out.var_target) out.var_target[v] = tgt;
@@ -366,67 +345,48 @@ __device__ __forceinline__ void sat_model(const SatSrc& src, const bool has_hs, 
 }
 
 template <bool DETAIL>
-__global__ void __launch_bounds__(SAT_G * 32, 2) saturation_kernel(SatIn in, SatOut out, const SatChunk* __restrict__ desc,
-                                                                   long long n_chunks) {
-  extern __shared__ __align__(128) unsigned char sat_smem[];
-  SatStage* stages = reinterpret_cast<SatStage*>(sat_smem);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sat_smem + sizeof(SatStage) * SAT_NS);
-  __shared__ double2 terms[SAT_G][32];
+__global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in, SatOut out, const SatDesc* __restrict__ desc) {
+  extern __shared__ __align__(16) unsigned char sat_smem[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double2* my_terms = terms[warp];
+  SatWarpSmem* ws = reinterpret_cast<SatWarpSmem*>(sat_smem) + warp;
   SatTally tally = {0, 0, 0, 0};
-  const bool has_hs = in.var_has_state != nullptr;
+  const long long gw = (long long)blockIdx.x * SAT_WARPS + warp, tw = (long long)gridDim.x * SAT_WARPS;
+  const long long M = in.n_models;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < SAT_NS; s++) sat_mbar_init(&bars[s], 1);
+  if (lane == 0) {
+    for (int s = 0; s < SAT_NS; s++) sat_mbar_init(&ws->bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  // prologue: the first SAT_NS - 1 chunks of this CTA
-  if (threadIdx.x == 0) {
-    for (int k = 0; k < SAT_NS - 1; k++) {
-      const long long c = (long long)blockIdx.x + (long long)k * gridDim.x;
-      if (c < n_chunks) { const SatChunk d = desc[c]; if (sat_chunk_fits(d)) sat_issue_chunk(in, d, c, &stages[k], &bars[k]); }
+  __syncwarp();
+  // prologue: the first SAT_NS models of this warp
+  if (lane == 0) {
+    for (int k = 0; k < SAT_NS; k++) {
+      const long long mk = gw + (long long)k * tw;
+      if (mk < M) { const SatDesc dk = desc[mk]; if (sat_staged(dk)) sat_issue(in, dk, &ws->stage[k], &ws->bar[k]); }
     }
   }
-  unsigned par_bits = 0;          // bit s = phase parity of the next wait on stage s (uniform over the CTA)
-  long long it = 0;
-  for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x, it++) {
-    // keep SAT_NS - 1 chunks in flight: the stage refilled here was consumed in the previous iteration (barrier below)
-    if (threadIdx.x == 0) {
-      const long long cn = c + (long long)(SAT_NS - 1) * gridDim.x;
-      if (cn < n_chunks) {
-        const int sn = (int)((it + SAT_NS - 1) % SAT_NS);
-        const SatChunk dn = desc[cn];
-        if (sat_chunk_fits(dn)) sat_issue_chunk(in, dn, cn, &stages[sn], &bars[sn]);
-      }
-    }
-    const SatChunk d = desc[c];
-    const long long m = c * SAT_G + warp;
-    const int s = (int)(it % SAT_NS);
-    if (sat_chunk_fits(d)) {
-      // a chunk that is not staged never arms its stage's barrier: the parity is counted per staged use
-      sat_mbar_wait(&bars[s], (par_bits >> s) & 1u);
+  unsigned par_bits = 0;          // bit s = phase parity of the next wait on stage s
+  int s = 0;
+  SatDesc d;
+  if (gw < M) d = desc[gw];
+  for (long long m = gw; m < M; m += tw) {
+    // descriptors of the next model (to analyse) and of the one whose copies are issued after this model
+    const long long m_next = m + tw, m_fill = m + (long long)SAT_NS * tw;
+    SatDesc dn = d, df = d;
+    if (m_next < M) dn = desc[m_next];
+    if (m_fill < M && lane == 0) df = desc[m_fill];
+    if (sat_staged(d)) {
+      sat_mbar_wait(&ws->bar[s], (par_bits >> s) & 1u);          // a model that is not staged never arms its barrier
       par_bits ^= 1u << s;
-      if (m < in.n_models) {
-        const SatStage* st = &stages[s];
-        const SatGeom g = sat_geom(d);
-        SatSrc src;
-        src.kv = st->kv; src.q = st->q; src.cost = st->cost; src.vro = st->vro; src.cur = st->cur; src.des = st->des;
-        src.pen = st->pen; src.hs = st->hs; src.r0 = g.r_a; src.v0i = g.v_i; src.v0c = g.v_c; src.v0h = g.v_h;
-        sat_model<DETAIL, true>(src, has_hs, m, st->mvo[warp], st->mvo[warp + 1], st->cfg[0][warp], st->cfg[1][warp],
-                                st->cfg[2][warp], st->cfg[3][warp], out, my_terms, tally);
-      }
-    } else if (m < in.n_models) {
-      SatSrc src;
-      src.kv = in.rep_kv; src.q = in.rep_queue; src.cost = in.var_cost; src.vro = in.variant_replica_off;
-      src.cur = in.var_current; src.des = in.var_desired; src.pen = in.var_pending; src.hs = in.var_has_state;
-      src.r0 = 0; src.v0i = 0; src.v0c = 0; src.v0h = 0;
-      sat_model<DETAIL, false>(src, has_hs, m, in.model_variant_off[m], in.model_variant_off[m + 1], in.cfg_kv_threshold[m],
-                               in.cfg_queue_threshold[m], in.cfg_kv_trigger[m], in.cfg_queue_trigger[m], out, my_terms, tally);
+      sat_model<DETAIL, true>(in, ws->stage[s].kv, ws->stage[s].q, d.r0 & ~1, m, d.v0, d.v1, out, ws->terms, tally);
+    } else {
+      sat_model<DETAIL, false>(in, in.rep_kv, in.rep_queue, 0, m, d.v0, d.v1, out, ws->terms, tally);
     }
-    __syncthreads();              // every warp is done with stage s before it is refilled (next iteration, thread 0)
+    __syncwarp();                                                 // every lane is done with stage s before it is refilled
+    if (lane == 0 && m_fill < M && sat_staged(df)) sat_issue(in, df, &ws->stage[s], &ws->bar[s]);
+    s = (s + 1 == SAT_NS) ? 0 : s + 1;
+    d = dn;
   }
   if (out.partials) {
     long long sum_targets = tally.sum_targets;

@@ -325,6 +325,31 @@ def test_greedy_ties_and_duplicates(pkg, engine, oracle):
         _greedy_case(pkg, engine, oracle, sysd, frac, "PriorityRoundRobin", True)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_greedy_both_formulations(pkg, engine, oracle, mode):
+    """WVA_OPT_GREEDY_MODE: 0 = static-order event sweep (greedy_sweep.cuh, the default), 1 = literal queue with the
+    re-insertion heap (greedy_solve.cuh).  Both against the oracle on a tie-heavy system (12 copies of 8 servers: every key
+    of the queue is 12-fold, the LIFO re-insertion rule decides) and on 3 000 servers under every policy."""
+    engine.set_option(5, mode)
+    try:
+        dup = pkg.synth.queue_system(96, 6, 16, stream=72)
+        for k, v in list(dup.items()):
+            if isinstance(v, np.ndarray) and v.shape[:1] == (96,):
+                v[:] = np.concatenate([v[:8]] * 12)
+        zl = pkg.synth.queue_system(400, 8, 8, stream=311, zero_load_frac=0.6)      # many equal zero-load candidates
+        for frac in (0.15, 0.3, 0.6, 0.9):
+            for d in (dup, zl):
+                _greedy_case(pkg, engine, oracle, d, frac, "None", False)
+                _greedy_case(pkg, engine, oracle, d, frac, "PriorityExhaustive", True)
+                _greedy_case(pkg, engine, oracle, d, frac, "RoundRobin", False)
+        big = pkg.synth.queue_system(3000, 16, 8, stream=75)
+        for pol in ("None", "PriorityExhaustive", "PriorityRoundRobin", "RoundRobin"):
+            for delayed in (False, True):
+                _greedy_case(pkg, engine, oracle, big, 0.5, pol, delayed)
+    finally:
+        engine.set_option(5, 0)
+
+
 def test_greedy_ample_capacity_equals_unlimited(pkg, engine, oracle):
     sysd = pkg.synth.queue_system(120, 6, 16, stream=73)
     g, un = _greedy_case(pkg, engine, oracle, sysd, 10.0, "None", False)

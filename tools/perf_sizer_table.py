@@ -6,8 +6,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("llm-d-workload-variant-autoscaler_b200")
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
-d = pkg.synth.baseline_config(3, scale=scale)
-out = {"pairs": int(d["n_servers"] * d["n_acc"])}
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+d = pkg.synth.baseline_config(3, scale=scale) if N == 256 else pkg.synth.queue_system(int(100000 * scale), 32, N, stream=3)
+out = {"pairs": int(d["n_servers"] * d["n_acc"]), "N": N}
 with pkg.Engine(0) as e:
     e.load_system(d)
     ref = None

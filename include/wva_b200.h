@@ -369,6 +369,54 @@ int32_t wva_saturation_upload(wva_ctx* ctx, const wva_saturation_in* in);
 int32_t wva_saturation_run(wva_ctx* ctx, int32_t detail);
 int32_t wva_saturation_fetch(wva_ctx* ctx, const wva_saturation_out* out);
 
+/* ---- Collector -> SoA ingest + streaming reconcile (one CUDA graph per metric batch) ------------------------------- */
+/*
+ * Replaces the per-model, string-keyed assembly of []ReplicaMetrics — CollectReplicaMetrics
+ * (internal/collector/replica_metrics.go:78-403: six Prometheus vectors folded into a map keyed by pod name, every pod
+ * matched to its VariantAutoscaling through PodVAMapper.FindVAForPod, source/pod_va_mapper.go:32) — for the V1
+ * saturation path.  The string work happens once per pod: the caller registers every pod into a SLOT of its variant
+ * (registry = CSR model -> variant -> slot; the slots of a variant in ascending pod-name order, which is the canonical
+ * order of the per-variant float64 sums) and keeps a map pod name -> slot.  Every cycle the Prometheus response parser
+ * writes each sample into page-locked columns indexed by slot (wva_ingest_write, or directly through `cols`), fills the
+ * per-variant state and per-model config columns, and calls wva_ingest_commit: ONE CUDA graph launch uploads the column
+ * arena, packs the pods that reported into CSR replica arrays on the device (a pod with neither metric is skipped, a
+ * missing metric reads 0, queue = int(value): replica_metrics.go:160,296-318), runs the V1 analysis + targets kernel and
+ * downloads the decision arena.  `res` arrays are valid after wva_ingest_commit returns, until the next commit.
+ * A registry change (pods added / removed) = destroy + create (ints only).
+ */
+typedef struct wva_ingest wva_ingest;
+enum { WVA_VEC_KV_CACHE_USAGE = 0, WVA_VEC_QUEUE_LENGTH = 1 };   /* registration.QueryKvCacheUsage / QueryQueueLength */
+typedef struct wva_ingest_columns {  /* page-locked host memory owned by the wva_ingest; the collector writes it      */
+  int64_t n_slots, n_variants, n_models;
+  double* kv;                        /* [slots] KvCacheUsage sample value                                            */
+  double* queue;                     /* [slots] queue-length sample value (converted with Go's int(float64) on the device) */
+  uint8_t* has;                      /* [slots] bit0: a KV sample arrived this cycle, bit1: a queue sample arrived    */
+  double* var_cost;                  /* [V] as wva_saturation_in                                                      */
+  int32_t* var_current; int32_t* var_desired; int32_t* var_pending;
+  double* cfg_kv_threshold; double* cfg_queue_threshold; double* cfg_kv_trigger; double* cfg_queue_trigger;   /* [M] */
+} wva_ingest_columns;
+typedef struct wva_ingest_results {  /* page-locked host memory owned by the wva_ingest                               */
+  int32_t* var_target;               /* [V] CalculateSaturationTargets (-1 = variant absent from the map)             */
+  int32_t* var_replica_count;        /* [V] pods of the variant that reported                                         */
+  int32_t* var_non_saturated;        /* [V]                                                                           */
+  double* var_avg_spare_kv;          /* [V] (VariantDecision.SpareCapacity: the limiter's sort key, engine.go:650-651) */
+  double* var_avg_spare_queue;       /* [V]                                                                           */
+  uint8_t* mod_flags;                /* [M] WVA_SAT_*                                                                 */
+  int32_t* mod_total_replicas;       /* [M]                                                                           */
+  int64_t* partials;                 /* [4] as wva_saturation_out                                                     */
+} wva_ingest_results;
+int32_t wva_ingest_create(wva_ctx* ctx, int64_t n_models, int64_t n_variants, int64_t n_slots,
+                          const int32_t* model_variant_off /* [M+1] */, const int32_t* variant_slot_off /* [V+1] */,
+                          wva_ingest** out, wva_ingest_columns* cols, wva_ingest_results* res);
+int32_t wva_ingest_destroy(wva_ingest* ing);
+/* start of a cycle: no pod has reported yet */
+int32_t wva_ingest_begin(wva_ingest* ing);
+/* one Prometheus-shaped vector keyed by slot, in result order: later samples of a pod overwrite earlier ones (the
+ * reference assigns into a map, replica_metrics.go:133-160); slot < 0 = no pod label / unknown pod: skipped */
+int32_t wva_ingest_write(wva_ingest* ing, int32_t which /* WVA_VEC_* */, int64_t n, const int32_t* slot, const double* value);
+/* metric batch -> decisions: one CUDA graph launch (wva_timing.saturation_ms = device time of the whole graph) */
+int32_t wva_ingest_commit(wva_ingest* ing);
+
 /* ---- GPU-count limiter ---------------------------------------------------- */
 /*
  * DefaultLimiter.Limit (internal/engines/pipeline/default_limiter.go:42-81) with

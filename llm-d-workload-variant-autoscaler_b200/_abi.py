@@ -293,3 +293,20 @@ def make_saturation_v2(d: dict):
         setattr(ost, name, ptr(a))
         out[name] = a[:n[dim]]
     return ist, ost, keep, out
+
+
+# ---- ingest ------------------------------------------------------------------------------------------------------------
+class IngestColumns(C.Structure):
+    _fields_ = [("n_slots", C.c_int64), ("n_variants", C.c_int64), ("n_models", C.c_int64),
+                ("kv", _f64p), ("queue", _f64p), ("has", _u8p), ("var_cost", _f64p), ("var_current", _i32p),
+                ("var_desired", _i32p), ("var_pending", _i32p), ("cfg_kv_threshold", _f64p),
+                ("cfg_queue_threshold", _f64p), ("cfg_kv_trigger", _f64p), ("cfg_queue_trigger", _f64p)]
+
+
+class IngestResults(C.Structure):
+    _fields_ = [("var_target", _i32p), ("var_replica_count", _i32p), ("var_non_saturated", _i32p),
+                ("var_avg_spare_kv", _f64p), ("var_avg_spare_queue", _f64p), ("mod_flags", _u8p),
+                ("mod_total_replicas", _i32p), ("partials", _i64p)]
+
+
+VEC_KV_CACHE_USAGE, VEC_QUEUE_LENGTH = 0, 1

@@ -720,3 +720,4 @@ int32_t wva_get_solution(wva_ctx* ctx, wva_solution* out) {
 
 #include "capi_aux.inl"
 #include "comm.inl"
+#include "ingest.inl"

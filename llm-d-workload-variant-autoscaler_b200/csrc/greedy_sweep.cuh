@@ -143,64 +143,64 @@ __device__ __forceinline__ void gsw_cp16(void* dst_smem, const void* src) {
 __device__ __forceinline__ void gsw_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void gsw_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-struct GSweep {
-  const SysView& s; const GreedyWs& w; const GSweepWs& g;
-  long long* avail; unsigned* alive;
-  int n_un, clock;
-  long long n_active;
-  __device__ bool is_alive(int srv) const { return (alive[srv >> 5] >> (srv & 31)) & 1u; }
-  __device__ void kill(int srv) {
+// Sweep state: plain values (kept in registers: nothing here has its address taken across a call)
+struct GSweepState { int n_un, clock; long long n_active; };
+
+__device__ __forceinline__ bool gsw_alive(const unsigned* alive, int srv) { return (alive[srv >> 5] >> (srv & 31)) & 1u; }
+__device__ __forceinline__ void gsw_kill(unsigned* alive, int srv) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) alive[srv >> 5] &= ~(1u << (srv & 31));
+  __syncwarp();
+}
+// one alive event, sequentially (greedy.go:120-165); every lane holds the same arguments.  True when the entry left the queue.
+__device__ __forceinline__ bool gsw_process(const GreedyWs& w, const GSweepWs& g, long long* avail, unsigned* alive, GSweepState& z,
+                                            int srv, unsigned meta, long long cnt) {
+  const bool writer = (threadIdx.x & 31) == 0;
+  z.n_active++;
+  const int type = ge_type(meta);
+  if (type < 0) { gsw_kill(alive, srv); return true; }                         // no accelerator: dropped (:126-136)
+  if (avail[type] >= cnt) {                                                      // :143-145
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) alive[srv >> 5] &= ~(1u << (srv & 31));
-    __syncwarp();
+    if (writer) { avail[type] -= cnt; w.kind[srv] = 1; w.sel_rank[srv] = ge_rank(meta); }
+    gsw_kill(alive, srv);
+    return true;
   }
-  // one alive event (greedy.go:120-165); every lane holds the same arguments.  Returns true when the entry left the queue.
-  __device__ bool process(int srv, unsigned meta, long long cnt) {
-    const bool writer = (threadIdx.x & 31) == 0;
-    n_active++;
-    const int type = ge_type(meta);
-    if (type < 0) { kill(srv); return true; }                                   // no accelerator: dropped (:126-136)
-    if (avail[type] >= cnt) {                                                    // :143-145
-      __syncwarp();
-      if (writer) { avail[type] -= cnt; w.kind[srv] = 1; w.sel_rank[srv] = ge_rank(meta); }
-      kill(srv);
-      return true;
-    }
-    clock++;
-    if (writer) g.stamp[srv] = clock;                                            // when the next candidate is (re-)inserted
-    if (ge_flags(meta) & GE_LAST) {                                              // :152-156
-      if (writer) w.unalloc[n_un] = srv;
-      n_un++;
-      kill(srv);
-      return true;
-    }
-    return false;
+  z.clock++;
+  if (writer) g.stamp[srv] = z.clock;                                            // when the next candidate is (re-)inserted
+  if (ge_flags(meta) & GE_LAST) {                                                // :152-156
+    if (writer) w.unalloc[z.n_un] = srv;
+    z.n_un++;
+    gsw_kill(alive, srv);
+    return true;
   }
-};
+  return false;
+}
 
 // The re-inserted part of a tie group with several statically possible leaders, entered at its first ALIVE leader i0:
 // collect the alive leaders, process their runs latest-insertion first.  Returns the position after the part, or -1 when
 // i0 is the only alive leader (the caller then processes it in the normal flow).
-__device__ __noinline__ int gsw_tie_group(GSweep& z, int i0, int n_ev) {
+__device__ __forceinline__ int gsw_tie_group(const GreedyWs& w, const GSweepWs& g, long long* avail, unsigned* alive,
+                                             GSweepState& z, int i0, int n_ev) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   int n_act = 0, i = i0;
+  __threadfence_block();           // the stamps written by other lanes of this warp are read below
   __syncwarp();
   while (true) {
     const int idx = i + lane;
     const bool v = idx < n_ev;
     unsigned m = 0; int sv = 0;
-    if (v) { const GEvent e = z.g.ev[idx]; m = e.meta; sv = e.srv; }
+    if (v) { const GEvent e = g.ev[idx]; m = e.meta; sv = e.srv; }
     const unsigned f = ge_flags(m);
     const bool in_part = v && (idx == i0 || (f & GE_TIE)) && !(f & GE_CLS1);
     const unsigned stop = __ballot_sync(full, !in_part);
     const int nin = stop ? __ffs(stop) - 1 : 32;
-    const bool is_cand = lane < nin && (f & GE_LEADER) && z.is_alive(sv);
+    const bool is_cand = lane < nin && (f & GE_LEADER) && gsw_alive(alive, sv);
     const unsigned cm = __ballot_sync(full, is_cand);
     if (is_cand) {
       const int slot = n_act + __popc(cm & ((1u << lane) - 1u));
-      z.g.dyn_pos[slot] = idx;
-      z.g.dyn_stamp[slot] = *((volatile int*)&z.g.stamp[sv]);
+      g.dyn_pos[slot] = idx;
+      g.dyn_stamp[slot] = *((volatile int*)&g.stamp[sv]);
     }
     n_act += __popc(cm);
     i += nin;
@@ -214,7 +214,7 @@ __device__ __noinline__ int gsw_tie_group(GSweep& z, int i0, int n_ev) {
     // latest insertion first: arg-max of the remaining stamps (stamps are distinct clock values > 0)
     int best = -1, best_slot = -1;
     for (int q = lane; q < n_act; q += 32) {
-      const int st = *((volatile int*)&z.g.dyn_stamp[q]);
+      const int st = *((volatile int*)&g.dyn_stamp[q]);
       if (st > best) { best = st; best_slot = q; }
     }
     for (int o = 16; o; o >>= 1) {
@@ -222,17 +222,17 @@ __device__ __noinline__ int gsw_tie_group(GSweep& z, int i0, int n_ev) {
       if (ob > best) { best = ob; best_slot = os; }
     }
     __syncwarp();
-    if (lane == 0) z.g.dyn_stamp[best_slot] = -1;
+    if (lane == 0) g.dyn_stamp[best_slot] = -1;
     __threadfence_block();
     __syncwarp();
-    int r = *((volatile int*)&z.g.dyn_pos[best_slot]);
-    const int srv0 = z.g.ev[r].srv;
+    int r = *((volatile int*)&g.dyn_pos[best_slot]);
+    const int srv0 = g.ev[r].srv;
     for (int first = r; r < end_pos; r++) {
-      const GEvent e = z.g.ev[r];
+      const GEvent e = g.ev[r];
       if (r > first && (e.srv != srv0 || !(ge_flags(e.meta) & GE_TIE))) break;
-      if (!z.is_alive(srv0)) break;
-      if (z.process(e.srv, e.meta, e.cnt)) break;
+      if (gsw_process(w, g, avail, alive, z, e.srv, e.meta, e.cnt)) break;
     }
+    __syncwarp();
   }
   return end_pos;
 }
@@ -244,12 +244,13 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
   long long* avail = reinterpret_cast<long long*>(alive + GSW_ALIVE_WORDS);
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   const int n_ev = *g.n_events;
   const int S = s.n_servers;
   for (int t = lane; t < s.n_types; t += 32) avail[t] = s.type_count[t];          // greedy.go:38-39
   for (int k = lane; k < (S + 31) / 32; k += 32) alive[k] = 0xffffffffu;
   __syncwarp();
-  GSweep z{s, w, g, avail, alive, 0, 0, 0};
+  GSweepState z = {0, 0, 0};
   int group_un0 = 0;
 
   // event stream: blocks of GSW_BLOCK records copied asynchronously into a ring of GSW_SLOTS slots; while block b is
@@ -257,26 +258,20 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
   int origin = 0;               // event index of block 0 of the current stream (changes only after a far tie-group jump)
   int issued = 0;               // blocks of the current stream whose copies have been issued
   int cur_block = -1;
-  auto issue_block = [&](int bb) {
-    const int base = origin + bb * GSW_BLOCK;
-    GEvent* dst = ring + (size_t)(bb % GSW_SLOTS) * GSW_BLOCK;
-    for (int k = lane; k < GSW_BLOCK; k += 32)
-      if (base + k < n_ev) gsw_cp16(dst + k, g.ev + base + k);
-    gsw_commit();
-  };
-  auto start_stream = [&](int at) {
-    gsw_wait<0>();
-    __syncwarp();
-    origin = at; issued = 0; cur_block = -1;
-  };
-  start_stream(0);
   int pos = 0;
   while (pos < n_ev) {
     const int rel = pos - origin;
     const int b = rel / GSW_BLOCK;
     if (b != cur_block) {
       __syncwarp();                                 // every lane is done reading the slot that is refilled next
-      while (issued < b + GSW_SLOTS) { issue_block(issued); issued++; }
+      while (issued < b + GSW_SLOTS) {
+        const int base = origin + issued * GSW_BLOCK;
+        GEvent* dst = ring + (size_t)(issued % GSW_SLOTS) * GSW_BLOCK;
+        for (int k = lane; k < GSW_BLOCK; k += 32)
+          if (base + k < n_ev) gsw_cp16(dst + k, g.ev + base + k);
+        gsw_commit();
+        issued++;
+      }
       // block b is complete once at most (issued - b - 1) younger groups are pending
       const int younger = issued - b - 1;
       if (younger <= 0) gsw_wait<0>();
@@ -288,39 +283,73 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
     }
     const GEvent* blk = ring + (size_t)(b % GSW_SLOTS) * GSW_BLOCK;
     const int in_blk = rel % GSW_BLOCK;
-    const int i = pos + lane;
-    const bool valid = in_blk + lane < GSW_BLOCK && i < n_ev;
+    const int nvalid = min(min(32, GSW_BLOCK - in_blk), n_ev - pos);
+    const bool valid = lane < nvalid;
     GEvent me; me.srv = -1; me.meta = 0; me.cnt = 0;
     if (valid) me = blk[in_blk + lane];
-    const int nvalid = min(min(32, GSW_BLOCK - in_blk), n_ev - pos);
-    const bool al = valid && z.is_alive(me.srv);
-    unsigned act = __ballot_sync(full, al);
-    unsigned npm = delayed ? 0u : __ballot_sync(full, valid && (ge_flags(me.meta) & GE_NEWPRIO));
+    const unsigned fl = ge_flags(me.meta);
+    const int type = ge_type(me.meta);
     const unsigned peers = __match_any_sync(full, me.srv);
+    unsigned npm = delayed ? 0u : __ballot_sync(full, valid && (fl & GE_NEWPRIO));
+    int cur = 0;                                   // lanes below `cur` are done
     int jump = -1;
-    while (act | npm) {
-      const int la = act ? __ffs(act) - 1 : 32, lp = npm ? __ffs(npm) - 1 : 32;
-      if (lp <= la) {
-        // a new priority group starts here: allocate() of the previous group is complete -> its bestEffort()
-        // (greedy.go:96-103), on the entries it left unallocated, in the order they were exhausted
-        npm &= npm - 1;
-        if (z.n_un > group_un0) { g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy); }
-        group_un0 = z.n_un;
-        continue;
+    while (cur < nvalid) {
+      // Outcome of every remaining lane under the CURRENT capacities and alive bits.  Up to the first lane that takes,
+      // is dropped, leads a multi-leader tie group or starts a priority group, every alive lane simply fails — and a
+      // failure changes neither the capacities nor (unless it is the entry's last candidate) the alive bits, so all
+      // of them are processed at once; then that one lane sequentially, then the outcomes are re-evaluated.
+      const bool todo = valid && lane >= cur;
+      const bool al = todo && gsw_alive(alive, me.srv);
+      const bool stopper = al && (type < 0 || avail[type < 0 ? 0 : type] >= me.cnt || (fl & GE_MULTI));
+      const unsigned stopm = __ballot_sync(full, stopper);
+      const unsigned npm_todo = npm & ~((1u << cur) - 1u);
+      const int ls = stopm ? __ffs(stopm) - 1 : 32, lp = npm_todo ? __ffs(npm_todo) - 1 : 32;
+      const int first = min(min(ls, lp), nvalid);
+      // ---- plain failures in [cur, first)
+      const bool failing = al && lane < first;
+      const unsigned fm = __ballot_sync(full, failing);
+      if (fm) {
+        const int rank = __popc(fm & lt);
+        if (failing && (fm & peers & ~lt & ~(1u << lane)) == 0) g.stamp[me.srv] = z.clock + rank + 1;   // the entry's latest failure
+        const bool lastc = failing && (fl & GE_LAST);                                                     // :152-156
+        const unsigned lm = __ballot_sync(full, lastc);
+        if (lastc) {
+          w.unalloc[z.n_un + __popc(lm & lt)] = me.srv;
+          atomicAnd(&alive[me.srv >> 5], ~(1u << (me.srv & 31)));
+        }
+        z.n_un += __popc(lm);
+        z.clock += __popc(fm);
+        z.n_active += __popc(fm);
+        __syncwarp();
       }
-      act &= act - 1;
-      const int e_srv = __shfl_sync(full, me.srv, la);
-      const unsigned e_meta = __shfl_sync(full, me.meta, la);
-      const long long e_cnt = __shfl_sync(full, me.cnt, la);
+      cur = first;
+      if (first >= nvalid) break;
+      if (lp <= ls) {
+        // a new priority group starts at lane `first`: allocate() of the previous group is complete -> its bestEffort()
+        // (greedy.go:96-103) on the entries it left unallocated, in the order they were exhausted
+        npm &= ~(1u << first);
+        if (z.n_un > group_un0) g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy);
+        group_un0 = z.n_un;
+        __syncwarp();
+        continue;                                  // the lane itself is evaluated in the next round
+      }
+      const int e_srv = __shfl_sync(full, me.srv, first);
+      const unsigned e_meta = __shfl_sync(full, me.meta, first);
+      const long long e_cnt = __shfl_sync(full, me.cnt, first);
       if (ge_flags(e_meta) & GE_MULTI) {
-        const int np = gsw_tie_group(z, pos + la, n_ev);
+        const int np = gsw_tie_group(w, g, avail, alive, z, pos + first, n_ev);
         if (np >= 0) { jump = np; break; }
       }
-      if (z.process(e_srv, e_meta, e_cnt)) act &= ~__shfl_sync(full, peers, la);   // later events of this entry in the batch are dead
+      gsw_process(w, g, avail, alive, z, e_srv, e_meta, e_cnt);
+      cur = first + 1;
     }
     if (jump >= 0) {
       pos = jump;
-      if (pos < n_ev && pos - origin >= issued * GSW_BLOCK) start_stream(pos);        // jumped past everything in flight
+      if (pos < n_ev && pos - origin >= issued * GSW_BLOCK) {        // jumped past everything in flight: restart the stream
+        gsw_wait<0>();
+        __syncwarp();
+        origin = pos; issued = 0; cur_block = -1;
+      }
     } else {
       pos += nvalid;
     }

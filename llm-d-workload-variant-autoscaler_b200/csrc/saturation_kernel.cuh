@@ -57,32 +57,45 @@ __device__ __forceinline__ double div_small_int(double x, int n) {
 }
 
 // ---- per-warp staging geometry -----------------------------------------------------------------------------------------
-constexpr int SAT_WARPS = 8;         // warps (= models in flight) per CTA
+constexpr int SAT_WARPS = 7;         // warps (= models in flight) per CTA; three CTAs per SM
 constexpr int SAT_NS = 2;            // stages per warp
 constexpr int SAT_CAP = 256;         // replicas a stage holds (32 variants x 8 replicas)
+constexpr int SAT_VCAP = 32;         // variants a stage holds (one per lane)
 
-struct alignas(16) SatStage {        // both arrays start on a 16-byte boundary (cp.async.bulk destination)
+struct SatDesc {                     // per model, 48 bytes (written once per batch by saturation_desc_kernel)
+  int v0, v1, r0, r1;                // variants [v0, v1), replicas [r0, r1)
+  double kvThr, qThr, kvTrig, qTrig; // SaturationScalingConfig of the model
+};
+struct alignas(16) SatStage {        // every member starts on a 16-byte boundary (cp.async.bulk destinations)
   double kv[SAT_CAP + 2];
   long long q[SAT_CAP + 2];
+  double cost[SAT_VCAP + 2];
+  SatDesc desc;
+  int vro[SAT_VCAP + 8];
+  int cur[SAT_VCAP + 4], des[SAT_VCAP + 4], pen[SAT_VCAP + 4];
+  unsigned char hs[SAT_VCAP + 16];
 };
 struct alignas(16) SatWarpSmem {
   SatStage stage[SAT_NS];
   double2 terms[32];
   unsigned long long bar[SAT_NS];
 };
-static_assert(sizeof(SatStage) % 16 == 0 && offsetof(SatStage, q) % 16 == 0 && offsetof(SatWarpSmem, terms) % 16 == 0, "alignment");
+static_assert(sizeof(SatDesc) == 48 && sizeof(SatStage) % 16 == 0 && offsetof(SatStage, q) % 16 == 0 &&
+              offsetof(SatStage, cost) % 16 == 0 && offsetof(SatStage, desc) % 16 == 0 && offsetof(SatStage, vro) % 16 == 0 &&
+              offsetof(SatStage, cur) % 16 == 0 && offsetof(SatStage, des) % 16 == 0 && offsetof(SatStage, pen) % 16 == 0 &&
+              offsetof(SatStage, hs) % 16 == 0 && offsetof(SatWarpSmem, terms) % 16 == 0, "alignment");
 constexpr size_t SAT_SMEM_BYTES = sizeof(SatWarpSmem) * SAT_WARPS;
 
-struct SatDesc { int v0, v1, r0, r1; };   // per model: variants [v0, v1), replicas [r0, r1)
-
-// the two dependent CSR look-ups of every model, done once so that the copy-issuing lane never waits on them
-// (16 B per model: 0.5 % of the stream)
+// the two dependent CSR look-ups and the config of every model, done once so that the copy-issuing lane never waits on
+// a dependent load (48 B per model: 1.4 % of the stream)
 __global__ void __launch_bounds__(256) saturation_desc_kernel(SatIn in, SatDesc* desc) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= in.n_models) return;
   SatDesc d;
   d.v0 = in.model_variant_off[m]; d.v1 = in.model_variant_off[m + 1];
   d.r0 = in.variant_replica_off[d.v0]; d.r1 = in.variant_replica_off[d.v1];
+  d.kvThr = in.cfg_kv_threshold[m]; d.qThr = in.cfg_queue_threshold[m];
+  d.kvTrig = in.cfg_kv_trigger[m]; d.qTrig = in.cfg_queue_trigger[m];
   desc[m] = d;
 }
 
@@ -110,16 +123,27 @@ __device__ __forceinline__ void sat_bulk_g2s(void* dst, const void* src, unsigne
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(sat_smem_addr(dst)), "l"(src), "r"(bytes), "r"(sat_smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ bool sat_staged(const SatDesc& d) { return d.r1 - d.r0 <= SAT_CAP; }
-// lane 0: the replica range of one model -> a stage (range start rounded down / length rounded up to 16 bytes; the
-// over-read of < 16 B past an array's end stays inside the input arena, whose sub-arrays are 256-byte padded)
-__device__ __forceinline__ void sat_issue(const SatIn& in, const SatDesc& d, SatStage* st, unsigned long long* bar) {
-  const int ra = d.r0 & ~1;
-  const unsigned bytes = (unsigned)((d.r1 - ra + 1) & ~1) * 8u;
-  if (bytes == 0) { sat_mbar_expect_tx(bar, 0); return; }     // phase completes at once
-  sat_mbar_expect_tx(bar, 2 * bytes);
-  sat_bulk_g2s(st->kv, in.rep_kv + ra, bytes, bar);
-  sat_bulk_g2s(st->q, in.rep_queue + ra, bytes, bar);
+__device__ __forceinline__ bool sat_staged(int v0, int v1, int r0, int r1) { return r1 - r0 <= SAT_CAP && v1 - v0 <= SAT_VCAP; }
+// lane 0: everything one model needs -> a stage.  Range starts are rounded down and lengths up to 16 bytes; the over-read
+// of < 16 B past an array's end stays inside the input arena, whose sub-arrays are 256-byte padded.
+__device__ __forceinline__ void sat_issue(const SatIn& in, const SatDesc* desc, long long m, int v0, int v1, int r0, int r1,
+                                          SatStage* st, unsigned long long* bar) {
+  const int ra = r0 & ~1, vi = v0 & ~3, vc = v0 & ~1, vh = v0 & ~15;
+  const unsigned b_rep = (unsigned)((r1 - ra + 1) & ~1) * 8u;
+  const unsigned b_vro = (unsigned)((v1 + 1 - vi + 3) & ~3) * 4u;
+  const unsigned b_v4 = (unsigned)((v1 - vi + 3) & ~3) * 4u;
+  const unsigned b_cost = (unsigned)((v1 - vc + 1) & ~1) * 8u;
+  const unsigned b_hs = in.var_has_state ? (unsigned)((v1 - vh + 15) & ~15) : 0u;
+  sat_mbar_expect_tx(bar, 2 * b_rep + b_vro + 3 * b_v4 + b_cost + b_hs + (unsigned)sizeof(SatDesc));
+  sat_bulk_g2s(&st->desc, desc + m, (unsigned)sizeof(SatDesc), bar);
+  sat_bulk_g2s(st->vro, in.variant_replica_off + vi, b_vro, bar);
+  if (b_rep) { sat_bulk_g2s(st->kv, in.rep_kv + ra, b_rep, bar); sat_bulk_g2s(st->q, in.rep_queue + ra, b_rep, bar); }
+  if (b_v4) {
+    sat_bulk_g2s(st->cur, in.var_current + vi, b_v4, bar); sat_bulk_g2s(st->des, in.var_desired + vi, b_v4, bar);
+    sat_bulk_g2s(st->pen, in.var_pending + vi, b_v4, bar);
+  }
+  if (b_cost) sat_bulk_g2s(st->cost, in.var_cost + vc, b_cost, bar);
+  if (b_hs) sat_bulk_g2s(st->hs, in.var_has_state + vh, b_hs, bar);
 }
 
 // order-preserving bit pattern of a float64 (-0 == +0; NaN sorts after +inf): costs are compared through it
@@ -344,6 +368,151 @@ __device__ __forceinline__ void sat_model(const SatIn& in, const double* kvp, co
   }
 }
 
+// One model out of a stage (at most 32 variants, one per lane; everything in shared memory).  Same arithmetic and
+// order as sat_model, without its chunk loops.
+template <bool DETAIL>
+__device__ __forceinline__ void sat_model_staged(const SatStage* st, const bool has_hs, const long long m, const SatOut& out,
+                                                 double2* my_terms, SatTally& tally) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int v0 = st->desc.v0, v1 = st->desc.v1;
+  const double kvThr = st->desc.kvThr, qThr = st->desc.qThr, kvTrig = st->desc.kvTrig, qTrig = st->desc.qTrig;
+  const int rbase = st->desc.r0 & ~1;
+  const int v = v0 + lane;
+  const bool act = v < v1;
+  const int oi = (v0 & 3) + lane, oc = (v0 & 1) + lane, oh = (v0 & 15) + lane;
+  int lo = 0, hi = 0, cur = 0, des = 0, pen = 0;
+  double cost = 0.0;
+  bool hs = false;
+  if (act) {
+    lo = st->vro[oi]; hi = st->vro[oi + 1];
+    hs = !has_hs || st->hs[oh];
+    if (hs) { cur = st->cur[oi]; des = st->des[oi]; pen = st->pen[oi]; }
+    cost = st->cost[oc];
+  }
+  const int cnt = hi - lo;
+  int ns = 0;
+  double sumKv = 0.0, sumQ = 0.0, maxKv = 0.0, avgKv = 0.0, avgQ = 0.0;
+  long long maxQ = 0;
+  for (int r = lo; r < hi; r++) {
+    const double kv = st->kv[r - rbase];
+    const long long q = st->q[r - rbase];
+    const double qd = (double)q;
+    const bool sat = kv >= kvThr || qd >= qThr;                       // analyzer.go:163-164
+    if (DETAIL) { if (out.rep_saturated) out.rep_saturated[r] = sat ? 1 : 0; }
+    if (!sat) {
+      sumKv = d_add(sumKv, d_sub(kvThr, kv));                        // :170-175
+      sumQ = d_add(sumQ, d_sub(qThr, qd));
+      ns++;
+    }
+    if (DETAIL) {
+      if (kv > maxKv) maxKv = kv;                                    // :179-184
+      if (q > maxQ) maxQ = q;
+    }
+  }
+  if (ns > 0) {                                                        // :190-193, one reciprocal for both quotients
+    const double nd = (double)ns;
+    if ((in_window(sumKv) || sumKv == 0.0) && (in_window(sumQ) || sumQ == 0.0)) {
+      const double rr = rcp_f32den((float)ns, nd);
+      avgKv = div_f32den(sumKv, nd, rr); avgQ = div_f32den(sumQ, nd, rr);
+    } else { avgKv = d_div(sumKv, nd); avgQ = d_div(sumQ, nd); }
+  }
+  if (DETAIL && act) {
+    if (out.var_replica_count) out.var_replica_count[v] = cnt;
+    if (out.var_non_saturated) out.var_non_saturated[v] = ns;
+    if (out.var_max_kv) out.var_max_kv[v] = maxKv;
+    if (out.var_max_queue) out.var_max_queue[v] = maxQ;
+    if (out.var_avg_spare_kv) out.var_avg_spare_kv[v] = avgKv;
+    if (out.var_avg_spare_queue) out.var_avg_spare_queue[v] = avgQ;
+  }
+  const bool analysed = cnt > 0;           // (inactive lanes have cnt == 0)
+  // ordered accumulation (analyzer.go:86-94): a variant without metrics contributes an exact +0.0
+  __syncwarp();
+  my_terms[lane] = make_double2(d_mul(avgKv, (double)ns), d_mul(avgQ, (double)ns));
+  __syncwarp();
+  double totalSpareKv, totalSpareQueue;
+  {
+    const double* col = reinterpret_cast<const double*>(my_terms) + (lane >> 4);
+    double acc = 0.0;
+#pragma unroll
+    for (int l = 0; l < 32; l++) acc = d_add(acc, col[2 * l]);
+    const double other = shfl_xor_d(full, acc, 16);
+    totalSpareKv = (lane < 16) ? acc : other;
+    totalSpareQueue = (lane < 16) ? other : acc;
+  }
+  const int nonSaturated = __reduce_add_sync(full, ns);
+  const int totalReplicas = __reduce_add_sync(full, cnt);
+  const unsigned anm = __ballot_sync(full, analysed);
+  const bool inTransition = __any_sync(full, analysed && ((des != 0 && des != cur) || (cnt != cur)));   // :322-341
+
+  // ---- model level (analyzer.go:96-121, 199-280) ---------------------------------------------
+  double avgSpareKv = 0.0, avgSpareQueue = 0.0;
+  bool up = false, downSafe = false, kvT = false, qT = false;
+  if (totalReplicas > 0) {
+    if (nonSaturated > 0) {
+      const double nd = (double)nonSaturated;
+      if ((in_window(totalSpareKv) || totalSpareKv == 0.0) && (in_window(totalSpareQueue) || totalSpareQueue == 0.0)) {
+        const double rr = rcp_f32den((float)nonSaturated, nd);
+        avgSpareKv = div_f32den(totalSpareKv, nd, rr); avgSpareQueue = div_f32den(totalSpareQueue, nd, rr);
+      } else { avgSpareKv = d_div(totalSpareKv, nd); avgSpareQueue = d_div(totalSpareQueue, nd); }
+    }
+    kvT = avgSpareKv < kvTrig;
+    qT = avgSpareQueue < qTrig;
+    up = kvT || qT;
+    if (nonSaturated >= 2) {
+      const double avgKvLoad = d_sub(kvThr, avgSpareKv), avgQLoad = d_sub(qThr, avgSpareQueue);
+      const double scale = div_small_int((double)nonSaturated, nonSaturated - 1);
+      const double remKv = d_sub(kvThr, d_mul(avgKvLoad, scale)), remQ = d_sub(qThr, d_mul(avgQLoad, scale));
+      downSafe = (remKv >= kvTrig) && (remQ >= qTrig);
+    }
+  }
+  if (lane == 0) {
+    if (DETAIL) {
+      if (out.mod_total_replicas) out.mod_total_replicas[m] = totalReplicas;
+      if (out.mod_non_saturated) out.mod_non_saturated[m] = nonSaturated;
+      if (out.mod_avg_spare_kv) out.mod_avg_spare_kv[m] = avgSpareKv;
+      if (out.mod_avg_spare_queue) out.mod_avg_spare_queue[m] = avgSpareQueue;
+    }
+    if (out.mod_flags)
+      out.mod_flags[m] = (up ? SAT_FLAG_UP : 0) | (downSafe ? SAT_FLAG_DOWN : 0) | (inTransition ? SAT_FLAG_TRANS : 0) |
+                         (kvT ? SAT_FLAG_KV : 0) | (qT ? SAT_FLAG_Q : 0);
+  }
+  // ---- scaling candidate (analyzer.go:376-433): two-word warp arg-min on the order-preserving cost bits ------------
+  int plus_l = -1, minus_l = -1;
+  if (anm && !inTransition && (up || downSafe)) {
+    const bool want_min = up;
+    const bool cand = cnt > 0 && (want_min ? (pen <= 0) : (cnt > 1));
+    const unsigned cm = __ballot_sync(full, cand);
+    if (cm) {
+      unsigned long long k = sat_sortable(cost);
+      if (!want_min) k = ~k;
+      const unsigned khi = cand ? (unsigned)(k >> 32) : 0xffffffffu, klo = cand ? (unsigned)k : 0xffffffffu;
+      const unsigned mh = __reduce_min_sync(full, khi);
+      bool in_ = cand && khi == mh;
+      const unsigned ml = __reduce_min_sync(full, in_ ? klo : 0xffffffffu);
+      in_ = in_ && klo == ml;
+      const unsigned wm = __ballot_sync(full, in_);
+      const int wl = want_min ? (__ffs(wm) - 1) : (31 - __clz(wm));
+      if (want_min) plus_l = wl; else minus_l = wl;
+    }
+  }
+  if (lane == 0) {
+    if (anm && inTransition) tally.n_trans++;
+    if (plus_l >= 0) tally.n_up++;
+    if (minus_l >= 0) tally.n_down++;
+  }
+  // ---- targets (analyzer.go:303-436) ------------------------------------------------------------
+  if (act) {
+    int tgt;
+    if (!anm) tgt = hs ? cur : -1;                                              // nil safety :303-309
+    else if (cnt == 0) tgt = -1;                                                // not in VariantAnalyses
+    else if (inTransition) tgt = (des != 0 && des != cur) ? des : cur;          // :350-359
+    else tgt = cnt + (lane == plus_l ? 1 : 0) - (lane == minus_l ? 1 : 0);      // :362, :399, :428
+    if (out.var_target) out.var_target[v] = tgt;
+    if (tgt >= 0) tally.sum_targets += tgt;
+  }
+}
+
 template <bool DETAIL>
 __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in, SatOut out, const SatDesc* __restrict__ desc) {
   extern __shared__ __align__(16) unsigned char sat_smem[];
@@ -353,40 +522,43 @@ __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in,
   SatTally tally = {0, 0, 0, 0};
   const long long gw = (long long)blockIdx.x * SAT_WARPS + warp, tw = (long long)gridDim.x * SAT_WARPS;
   const long long M = in.n_models;
+  const bool has_hs = in.var_has_state != nullptr;
 
   if (lane == 0) {
     for (int s = 0; s < SAT_NS; s++) sat_mbar_init(&ws->bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  // geometry (16 bytes) of the models this warp touches next: loaded a full model ahead of its use
+  int4 g_cur = make_int4(0, 0, 0, 0), g_fill = make_int4(0, 0, 0, 0);
   // prologue: the first SAT_NS models of this warp
-  if (lane == 0) {
-    for (int k = 0; k < SAT_NS; k++) {
-      const long long mk = gw + (long long)k * tw;
-      if (mk < M) { const SatDesc dk = desc[mk]; if (sat_staged(dk)) sat_issue(in, dk, &ws->stage[k], &ws->bar[k]); }
+  for (int k = 0; k < SAT_NS; k++) {
+    const long long mk = gw + (long long)k * tw;
+    if (mk < M) {
+      const int4 gk = *reinterpret_cast<const int4*>(desc + mk);
+      if (k == 0) g_cur = gk;
+      if (lane == 0 && sat_staged(gk.x, gk.y, gk.z, gk.w)) sat_issue(in, desc, mk, gk.x, gk.y, gk.z, gk.w, &ws->stage[k], &ws->bar[k]);
     }
   }
   unsigned par_bits = 0;          // bit s = phase parity of the next wait on stage s
   int s = 0;
-  SatDesc d;
-  if (gw < M) d = desc[gw];
   for (long long m = gw; m < M; m += tw) {
-    // descriptors of the next model (to analyse) and of the one whose copies are issued after this model
     const long long m_next = m + tw, m_fill = m + (long long)SAT_NS * tw;
-    SatDesc dn = d, df = d;
-    if (m_next < M) dn = desc[m_next];
-    if (m_fill < M && lane == 0) df = desc[m_fill];
-    if (sat_staged(d)) {
+    int4 g_next = g_cur;
+    if (m_next < M) g_next = *reinterpret_cast<const int4*>(desc + m_next);
+    if (m_fill < M) g_fill = *reinterpret_cast<const int4*>(desc + m_fill);
+    if (sat_staged(g_cur.x, g_cur.y, g_cur.z, g_cur.w)) {
       sat_mbar_wait(&ws->bar[s], (par_bits >> s) & 1u);          // a model that is not staged never arms its barrier
       par_bits ^= 1u << s;
-      sat_model<DETAIL, true>(in, ws->stage[s].kv, ws->stage[s].q, d.r0 & ~1, m, d.v0, d.v1, out, ws->terms, tally);
+      sat_model_staged<DETAIL>(&ws->stage[s], has_hs, m, out, ws->terms, tally);
     } else {
-      sat_model<DETAIL, false>(in, in.rep_kv, in.rep_queue, 0, m, d.v0, d.v1, out, ws->terms, tally);
+      sat_model<DETAIL, false>(in, in.rep_kv, in.rep_queue, 0, m, g_cur.x, g_cur.y, out, ws->terms, tally);
     }
     __syncwarp();                                                 // every lane is done with stage s before it is refilled
-    if (lane == 0 && m_fill < M && sat_staged(df)) sat_issue(in, df, &ws->stage[s], &ws->bar[s]);
+    if (lane == 0 && m_fill < M && sat_staged(g_fill.x, g_fill.y, g_fill.z, g_fill.w))
+      sat_issue(in, desc, m_fill, g_fill.x, g_fill.y, g_fill.z, g_fill.w, &ws->stage[s], &ws->bar[s]);
     s = (s + 1 == SAT_NS) ? 0 : s + 1;
-    d = dn;
+    g_cur = g_next;
   }
   if (out.partials) {
     long long sum_targets = tally.sum_targets;

@@ -71,6 +71,12 @@ def load_library():
     L.wva_group_ctx.restype = ctxp
     L.wva_group_optimize.argtypes = [ctxp, C.POINTER(abi.System), C.POINTER(abi.Solution)]
     L.wva_group_saturation_v1.argtypes = [ctxp, C.POINTER(abi.SaturationIn), C.POINTER(abi.SaturationOut)]
+    L.wva_ingest_create.argtypes = [ctxp, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(ctxp),
+                                    C.POINTER(abi.IngestColumns), C.POINTER(abi.IngestResults)]
+    L.wva_ingest_destroy.argtypes = [ctxp]
+    L.wva_ingest_begin.argtypes = [ctxp]
+    L.wva_ingest_write.argtypes = [ctxp, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
+    L.wva_ingest_commit.argtypes = [ctxp]
     L.wva_load_system.argtypes = [ctxp, C.POINTER(abi.System)]
     L.wva_calculate.argtypes = [ctxp]
     L.wva_solve.argtypes = [ctxp]
@@ -105,7 +111,8 @@ EXPORTS = ["wva_set_option", "wva_create", "wva_destroy", "wva_strerror", "wva_l
            "wva_cost_aware_optimize", "wva_enforce", "wva_pipeline_v2", "wva_host_alloc", "wva_host_free", "wva_last_timing",
            "wva_microbench_fp64", "wva_set_optimizer", "wva_set_capacity", "wva_comm_unique_id", "wva_comm_init_rank",
            "wva_comm_shard", "wva_group_create", "wva_group_destroy", "wva_group_size", "wva_group_ctx",
-           "wva_group_optimize", "wva_group_saturation_v1"]
+           "wva_group_optimize", "wva_group_saturation_v1", "wva_ingest_create", "wva_ingest_destroy", "wva_ingest_begin",
+           "wva_ingest_write", "wva_ingest_commit"]
 
 
 def comm_unique_id() -> bytes:
@@ -391,6 +398,57 @@ class Engine:
         a, b = C.c_double(), C.c_double()
         self._check(self.lib.wva_microbench_fp64(self.ctx, C.byref(a), C.byref(b)), "wva_microbench_fp64")
         return a.value, b.value
+
+
+class Ingest:
+    """wva_ingest: the collector's columnar staging + the streaming reconcile as one CUDA graph (include/wva_b200.h).
+
+    registry: model_variant_off [M+1], variant_slot_off [V+1] (CSR model -> variant -> pod slot; slots of a variant in
+    ascending pod-name order).  `cols` / `res` are numpy views of the page-locked arenas the library owns."""
+
+    def __init__(self, engine: "Engine", model_variant_off, variant_slot_off):
+        self.engine, self.lib = engine, engine.lib
+        mvo = np.ascontiguousarray(model_variant_off, np.int32); vso = np.ascontiguousarray(variant_slot_off, np.int32)
+        M, V, S = mvo.size - 1, vso.size - 1, int(vso[-1])
+        self.M, self.V, self.S = M, V, S
+        self.h = C.c_void_p()
+        cst, rst = abi.IngestColumns(), abi.IngestResults()
+        engine._check(self.lib.wva_ingest_create(engine.ctx, M, V, S, mvo.ctypes.data, vso.ctypes.data, C.byref(self.h),
+                                                 C.byref(cst), C.byref(rst)), "wva_ingest_create")
+
+        def view(p, n, dt):
+            if n == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dt).itemsize,)).view(dt)
+
+        self.cols = {"kv": view(cst.kv, S, np.float64), "queue": view(cst.queue, S, np.float64), "has": view(cst.has, S, np.uint8),
+                     "var_cost": view(cst.var_cost, V, np.float64), "var_current": view(cst.var_current, V, np.int32),
+                     "var_desired": view(cst.var_desired, V, np.int32), "var_pending": view(cst.var_pending, V, np.int32),
+                     "cfg_kv_threshold": view(cst.cfg_kv_threshold, M, np.float64),
+                     "cfg_queue_threshold": view(cst.cfg_queue_threshold, M, np.float64),
+                     "cfg_kv_trigger": view(cst.cfg_kv_trigger, M, np.float64),
+                     "cfg_queue_trigger": view(cst.cfg_queue_trigger, M, np.float64)}
+        self.res = {"var_target": view(rst.var_target, V, np.int32), "var_replica_count": view(rst.var_replica_count, V, np.int32),
+                    "var_non_saturated": view(rst.var_non_saturated, V, np.int32),
+                    "var_avg_spare_kv": view(rst.var_avg_spare_kv, V, np.float64),
+                    "var_avg_spare_queue": view(rst.var_avg_spare_queue, V, np.float64), "mod_flags": view(rst.mod_flags, M, np.uint8),
+                    "mod_total_replicas": view(rst.mod_total_replicas, M, np.int32), "partials": view(rst.partials, 4, np.int64)}
+
+    def begin(self):
+        self.engine._check(self.lib.wva_ingest_begin(self.h), "wva_ingest_begin")
+
+    def write(self, which: int, slot, value):
+        sl = np.ascontiguousarray(slot, np.int32); va = np.ascontiguousarray(value, np.float64)
+        self.engine._check(self.lib.wva_ingest_write(self.h, which, sl.size, sl.ctypes.data, va.ctypes.data), "wva_ingest_write")
+
+    def commit(self):
+        self.engine._check(self.lib.wva_ingest_commit(self.h), "wva_ingest_commit")
+        return self.res
+
+    def close(self):
+        if self.h:
+            self.lib.wva_ingest_destroy(self.h)
+            self.h = None
 
 
 class Group:

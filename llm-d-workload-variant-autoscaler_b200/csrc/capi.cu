@@ -505,7 +505,10 @@ int32_t wva_calculate(wva_ctx* ctx) {
         e = launch_sizer_warp<4>(ctx, ctx->sm_count * per_sm, warp_tab * 4, n_pairs, nmax, d_ovf);
       }
     } else
-    if (best_per_sm >= 1 && ctx->table_mode != 2) {
+    // Head table placement (measured, B200, 320 k pairs): N = 256 leaves 192 lanes per SM in shared memory (1.5 warps per
+    // scheduler) -> 60.6 ms, against 45.4 ms with the table in global memory / L2 and two 256-thread blocks per SM under
+    // a 128-register cap; at N = 128 (384 lanes in shared memory) and N = 64 shared memory wins (19.5 vs 21.0, 9.8 vs 10.5).
+    if (best_per_sm >= 1 && ctx->table_mode != 2 && (ctx->table_mode == 1 || best_threads * best_per_sm > 256 || n_pairs <= (unsigned long long)ctx->sm_count * 512)) {
       int blocks = ctx->sm_count * best_per_sm;
       size_t smem = per_lane * best_threads;
       switch (best_threads) {

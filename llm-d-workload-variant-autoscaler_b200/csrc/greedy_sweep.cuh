@@ -32,6 +32,8 @@ __device__ __forceinline__ int ge_type(unsigned meta) { const int t = (int)(meta
 __device__ __forceinline__ unsigned ge_flags(unsigned meta) { return (meta >> 8) & 0xffu; }
 __device__ __forceinline__ int ge_rank(unsigned meta) { return (int)(meta >> 16); }
 
+constexpr int GSW_BLOCK = 512;            // events per ring slot (8 KB)
+
 struct GSweepWs {
   // dense, indexed (server, rank): tau components and flags of every potential event
   unsigned* t_kd; unsigned* t_kv; unsigned char* fl; unsigned char* valid;
@@ -41,6 +43,7 @@ struct GSweepWs {
   GEvent* ev;
   int* stamp;        // [S] clock of the entry's last failure
   int* dyn_pos; int* dyn_stamp;   // [S] scratch of the tie-group procedure
+  unsigned long long* blk_min;    // [n_blocks + 1][n_types] smallest unit count among the events of type t at or after the block
 };
 
 // tau, run class and flags of every (server, rank); after greedy_prepare_kernel
@@ -97,6 +100,19 @@ __global__ void __launch_bounds__(256) gsw_gather_kernel(SysView s, GreedyWs w, 
   e.meta = (unsigned)(ty < 0 ? 0xff : ty) | (flags << 8) | ((unsigned)j << 16);
   e.cnt = (long long)w.r_nrep[p] * w.r_upr[p];
   g.ev[i] = e;
+  if (ty >= 0) atomicMin(&g.blk_min[(size_t)(i / GSW_BLOCK) * s.n_types + ty], (unsigned long long)e.cnt);
+}
+
+// suffix minima over the blocks (one thread per type)
+__global__ void __launch_bounds__(64) gsw_sufmin_kernel(GSweepWs g, int n_blocks, int n_types) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_types) return;
+  unsigned long long m = ~0ull;
+  for (int b = n_blocks - 1; b >= 0; b--) {
+    const unsigned long long v = g.blk_min[(size_t)b * n_types + t];
+    m = v < m ? v : m;
+    g.blk_min[(size_t)b * n_types + t] = m;
+  }
 }
 
 // MULTI: the event leads a re-inserted run and its tie group holds another re-inserted leader.  Bounded walks; when a
@@ -131,7 +147,6 @@ __global__ void __launch_bounds__(256) gsw_multi_kernel(GSweepWs g, int n) {
   if (multi || open) g.ev[i].meta = m | ((unsigned)GE_MULTI << 8);
 }
 
-constexpr int GSW_BLOCK = 512;            // events per ring slot (8 KB)
 constexpr int GSW_SLOTS = 4;
 constexpr int GSW_ALIVE_WORDS = 40 * 1024; // alive bits for up to 1 310 720 entries in shared memory (160 KB)
 constexpr int GSW_AVAIL = 64;              // capacity types (WVA_MAX_TYPES)
@@ -259,7 +274,19 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
   int issued = 0;               // blocks of the current stream whose copies have been issued
   int cur_block = -1;
   int pos = 0;
+  int checked_blk = -1;
   while (pos < n_ev) {
+    // Policy None: once no remaining event of any type can fit (capacities only shrink, greedy.go:143-145, and
+    // bestEffort is a no-op), every entry still in the queue ends unallocated whatever the order: stop.
+    if (policy == 0 && pos / GSW_BLOCK != checked_blk) {
+      checked_blk = pos / GSW_BLOCK;
+      bool can = false;
+      for (int t = lane; t < s.n_types; t += 32) {
+        const unsigned long long mn = g.blk_min[(size_t)checked_blk * s.n_types + t];
+        can = can || (mn != ~0ull && (unsigned long long)avail[t] >= mn && avail[t] >= 0);
+      }
+      if (!__any_sync(full, can)) break;
+    }
     const int rel = pos - origin;
     const int b = rel / GSW_BLOCK;
     if (b != cur_block) {
@@ -337,8 +364,19 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
       const unsigned e_meta = __shfl_sync(full, me.meta, first);
       const long long e_cnt = __shfl_sync(full, me.cnt, first);
       if (ge_flags(e_meta) & GE_MULTI) {
-        const int np = gsw_tie_group(w, g, avail, alive, z, pos + first, n_ev);
-        if (np >= 0) { jump = np; break; }
+        // Several re-inserted leaders share this tau statically.  Their order only matters when another one is ALIVE:
+        // if the re-inserted part of the group ends inside this batch and holds no other alive leader, this one is
+        // processed in place; otherwise the tie-group procedure orders the alive leaders by insertion time.
+        const unsigned tm = __ballot_sync(full, valid && (fl & GE_TIE) && !(fl & GE_CLS1));
+        const unsigned after = first >= 31 ? 0u : (tm >> (first + 1));
+        const int run = __ffs(~after) - 1;                          // lanes of the part after `first` (contiguous)
+        const bool ends_here = first + 1 + run < nvalid;
+        const unsigned span = run >= 31 ? 0xffffffffu : (((1u << run) - 1u) << (first + 1));
+        const unsigned others = __ballot_sync(full, al && (fl & GE_LEADER)) & span;
+        if (!ends_here || others) {
+          const int np = gsw_tie_group(w, g, avail, alive, z, pos + first, n_ev);
+          if (np >= 0) { jump = np; break; }
+        }
       }
       gsw_process(w, g, avail, alive, z, e_srv, e_meta, e_cnt);
       cur = first + 1;
@@ -376,6 +414,8 @@ static inline int32_t run_solve_greedy_sweep(const SysView& s, const CandView& c
   const size_t e_tkd = etake(P * 4), e_tkv = etake(P * 4), e_fl = etake(P), e_va = etake(P), e_ia = etake(P * 4), e_ib = etake(P * 4),
                e_ka = etake(P * 4), e_kb = etake(P * 4), e_ne = etake(64), e_ev = etake(P * sizeof(GEvent) + 64), e_st = etake(S * 4),
                e_dp = etake(S * 4), e_ds = etake(S * 4);
+  const size_t n_blocks_max = P / GSW_BLOCK + 2;
+  const size_t e_bm = etake(n_blocks_max * (size_t)(s.n_types > 0 ? s.n_types : 1) * 8);
   GreedyWs w;
   size_t tmp = 0;
   void* d_tmp = nullptr;
@@ -389,6 +429,7 @@ static inline int32_t run_solve_greedy_sweep(const SysView& s, const CandView& c
   g.idxA = (unsigned*)(ex + e_ia); g.idxB = (unsigned*)(ex + e_ib); g.keyA = (unsigned*)(ex + e_ka); g.keyB = (unsigned*)(ex + e_kb);
   g.n_events = (int*)(ex + e_ne); g.ev = (GEvent*)(ex + e_ev); g.stamp = (int*)(ex + e_st); g.dyn_pos = (int*)(ex + e_dp);
   g.dyn_stamp = (int*)(ex + e_ds);
+  g.blk_min = (unsigned long long*)(ex + e_bm);
   if (cudaFuncSetAttribute(gsw_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSW_SMEM) != cudaSuccess) return WVA_ERR_CUDA;
   const unsigned sb = (unsigned)((S + 127) / 128);
   greedy_prepare_kernel<<<sb, 128, 0, stream>>>(s, c, w);
@@ -411,9 +452,12 @@ static inline int32_t run_solve_greedy_sweep(const SysView& s, const CandView& c
       unsigned* sw = cur; cur = alt; alt = sw;
       *launches += 2;
     }
+    const int n_blocks = n / GSW_BLOCK + 1;
+    if (cudaMemsetAsync(g.blk_min, 0xff, (size_t)n_blocks * (size_t)(s.n_types > 0 ? s.n_types : 1) * 8, stream) != cudaSuccess) return WVA_ERR_CUDA;
     gsw_gather_kernel<<<cb, 256, 0, stream>>>(s, w, g, cur, n);
     gsw_multi_kernel<<<cb, 256, 0, stream>>>(g, n);
-    *launches += 2;
+    if (s.n_types > 0) gsw_sufmin_kernel<<<(s.n_types + 63) / 64, 64, 0, stream>>>(g, n_blocks, s.n_types);
+    *launches += 3;
   }
   gsw_sweep_kernel<<<1, 32, GSW_SMEM, stream>>>(s, w, g, delayed, policy);
   greedy_finalize_kernel<<<(unsigned)((S + 255) / 256), 256, 0, stream>>>(s, c, o, w);

@@ -57,23 +57,21 @@ __device__ __forceinline__ double div_small_int(double x, int n) {
 }
 
 // ---- per-warp staging geometry -----------------------------------------------------------------------------------------
-constexpr int SAT_WARPS = 7;         // warps (= models in flight) per CTA; three CTAs per SM
+constexpr int SAT_WARPS = 8;         // warps (= models in flight) per CTA; three CTAs per SM
 constexpr int SAT_NS = 2;            // stages per warp
-constexpr int SAT_CAP = 256;         // replicas a stage holds (32 variants x 8 replicas)
+constexpr int SAT_CAP = 224;         // replicas a stage holds (32 variants x 7 replicas)
 constexpr int SAT_VCAP = 32;         // variants a stage holds (one per lane)
 
 struct SatDesc {                     // per model, 48 bytes (written once per batch by saturation_desc_kernel)
   int v0, v1, r0, r1;                // variants [v0, v1), replicas [r0, r1)
   double kvThr, qThr, kvTrig, qTrig; // SaturationScalingConfig of the model
 };
-struct alignas(16) SatStage {        // every member starts on a 16-byte boundary (cp.async.bulk destinations)
-  double kv[SAT_CAP + 2];
+struct alignas(16) SatStage {
+  double kv[SAT_CAP + 2];            // cp.async.bulk destinations: 16-byte aligned
   long long q[SAT_CAP + 2];
-  double cost[SAT_VCAP + 2];
+  double cost[SAT_VCAP];             // per-lane columns, filled by each lane's own cp.async
+  int lo[SAT_VCAP], cur[SAT_VCAP], des[SAT_VCAP], pen[SAT_VCAP];
   SatDesc desc;
-  int vro[SAT_VCAP + 8];
-  int cur[SAT_VCAP + 4], des[SAT_VCAP + 4], pen[SAT_VCAP + 4];
-  unsigned char hs[SAT_VCAP + 16];
 };
 struct alignas(16) SatWarpSmem {
   SatStage stage[SAT_NS];
@@ -81,9 +79,8 @@ struct alignas(16) SatWarpSmem {
   unsigned long long bar[SAT_NS];
 };
 static_assert(sizeof(SatDesc) == 48 && sizeof(SatStage) % 16 == 0 && offsetof(SatStage, q) % 16 == 0 &&
-              offsetof(SatStage, cost) % 16 == 0 && offsetof(SatStage, desc) % 16 == 0 && offsetof(SatStage, vro) % 16 == 0 &&
-              offsetof(SatStage, cur) % 16 == 0 && offsetof(SatStage, des) % 16 == 0 && offsetof(SatStage, pen) % 16 == 0 &&
-              offsetof(SatStage, hs) % 16 == 0 && offsetof(SatWarpSmem, terms) % 16 == 0, "alignment");
+              offsetof(SatStage, cost) % 16 == 0 && offsetof(SatStage, desc) % 16 == 0 && offsetof(SatWarpSmem, terms) % 16 == 0,
+              "alignment");
 constexpr size_t SAT_SMEM_BYTES = sizeof(SatWarpSmem) * SAT_WARPS;
 
 // the two dependent CSR look-ups and the config of every model, done once so that the copy-issuing lane never waits on
@@ -124,26 +121,38 @@ __device__ __forceinline__ void sat_bulk_g2s(void* dst, const void* src, unsigne
                ::"r"(sat_smem_addr(dst)), "l"(src), "r"(bytes), "r"(sat_smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ bool sat_staged(int v0, int v1, int r0, int r1) { return r1 - r0 <= SAT_CAP && v1 - v0 <= SAT_VCAP; }
-// lane 0: everything one model needs -> a stage.  Range starts are rounded down and lengths up to 16 bytes; the over-read
-// of < 16 B past an array's end stays inside the input arena, whose sub-arrays are 256-byte padded.
+__device__ __forceinline__ void sat_cp4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sat_smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sat_cp8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sat_smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sat_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sat_smem_addr(dst)), "l"(src) : "memory");
+}
+// Everything one model needs -> a stage (the whole warp calls this).  The two replica arrays — one contiguous range each,
+// 1-2 KB — go through the TMA unit: lane 0 issues two cp.async.bulk copies that complete on the stage's mbarrier (range
+// start rounded down / length up to 16 bytes; the over-read of < 16 B past an array's end stays inside the input arena,
+// whose sub-arrays are 256-byte padded).  The per-variant values are one element per lane: every lane copies its own with
+// cp.async (no registers, no scoreboard); lanes 0-2 copy the model's descriptor.  The caller commits the cp.async group.
 __device__ __forceinline__ void sat_issue(const SatIn& in, const SatDesc* desc, long long m, int v0, int v1, int r0, int r1,
                                           SatStage* st, unsigned long long* bar) {
-  const int ra = r0 & ~1, vi = v0 & ~3, vc = v0 & ~1, vh = v0 & ~15;
-  const unsigned b_rep = (unsigned)((r1 - ra + 1) & ~1) * 8u;
-  const unsigned b_vro = (unsigned)((v1 + 1 - vi + 3) & ~3) * 4u;
-  const unsigned b_v4 = (unsigned)((v1 - vi + 3) & ~3) * 4u;
-  const unsigned b_cost = (unsigned)((v1 - vc + 1) & ~1) * 8u;
-  const unsigned b_hs = in.var_has_state ? (unsigned)((v1 - vh + 15) & ~15) : 0u;
-  sat_mbar_expect_tx(bar, 2 * b_rep + b_vro + 3 * b_v4 + b_cost + b_hs + (unsigned)sizeof(SatDesc));
-  sat_bulk_g2s(&st->desc, desc + m, (unsigned)sizeof(SatDesc), bar);
-  sat_bulk_g2s(st->vro, in.variant_replica_off + vi, b_vro, bar);
-  if (b_rep) { sat_bulk_g2s(st->kv, in.rep_kv + ra, b_rep, bar); sat_bulk_g2s(st->q, in.rep_queue + ra, b_rep, bar); }
-  if (b_v4) {
-    sat_bulk_g2s(st->cur, in.var_current + vi, b_v4, bar); sat_bulk_g2s(st->des, in.var_desired + vi, b_v4, bar);
-    sat_bulk_g2s(st->pen, in.var_pending + vi, b_v4, bar);
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) {
+    const int ra = r0 & ~1;
+    const unsigned b_rep = (unsigned)((r1 - ra + 1) & ~1) * 8u;
+    sat_mbar_expect_tx(bar, 2 * b_rep);
+    if (b_rep) { sat_bulk_g2s(st->kv, in.rep_kv + ra, b_rep, bar); sat_bulk_g2s(st->q, in.rep_queue + ra, b_rep, bar); }
   }
-  if (b_cost) sat_bulk_g2s(st->cost, in.var_cost + vc, b_cost, bar);
-  if (b_hs) sat_bulk_g2s(st->hs, in.var_has_state + vh, b_hs, bar);
+  const int v = v0 + lane;
+  if (v < v1) {
+    sat_cp4(&st->lo[lane], in.variant_replica_off + v);
+    sat_cp4(&st->cur[lane], in.var_current + v);
+    sat_cp4(&st->des[lane], in.var_desired + v);
+    sat_cp4(&st->pen[lane], in.var_pending + v);
+    sat_cp8(&st->cost[lane], in.var_cost + v);
+  }
+  if (lane < 3) sat_cp16(reinterpret_cast<char*>(&st->desc) + 16 * lane, reinterpret_cast<const char*>(desc + m) + 16 * lane);
 }
 
 // order-preserving bit pattern of a float64 (-0 == +0; NaN sorts after +inf): costs are compared through it
@@ -371,8 +380,8 @@ __device__ __forceinline__ void sat_model(const SatIn& in, const double* kvp, co
 // One model out of a stage (at most 32 variants, one per lane; everything in shared memory).  Same arithmetic and
 // order as sat_model, without its chunk loops.
 template <bool DETAIL>
-__device__ __forceinline__ void sat_model_staged(const SatStage* st, const bool has_hs, const long long m, const SatOut& out,
-                                                 double2* my_terms, SatTally& tally) {
+__device__ __forceinline__ void sat_model_staged(const SatStage* st, const unsigned char* __restrict__ hs_col, const long long m,
+                                                 const SatOut& out, double2* my_terms, SatTally& tally) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int v0 = st->desc.v0, v1 = st->desc.v1;
@@ -380,16 +389,18 @@ __device__ __forceinline__ void sat_model_staged(const SatStage* st, const bool 
   const int rbase = st->desc.r0 & ~1;
   const int v = v0 + lane;
   const bool act = v < v1;
-  const int oi = (v0 & 3) + lane, oc = (v0 & 1) + lane, oh = (v0 & 15) + lane;
-  int lo = 0, hi = 0, cur = 0, des = 0, pen = 0;
+  int lo = st->desc.r1, cur = 0, des = 0, pen = 0;
   double cost = 0.0;
   bool hs = false;
   if (act) {
-    lo = st->vro[oi]; hi = st->vro[oi + 1];
-    hs = !has_hs || st->hs[oh];
-    if (hs) { cur = st->cur[oi]; des = st->des[oi]; pen = st->pen[oi]; }
-    cost = st->cost[oc];
+    lo = st->lo[lane];
+    hs = !hs_col || hs_col[v];
+    if (hs) { cur = st->cur[lane]; des = st->des[lane]; pen = st->pen[lane]; }
+    cost = st->cost[lane];
   }
+  // a variant's range ends where the next one starts; the model's last one ends at r1 (inactive lanes hold r1: empty)
+  const int hi_n = __shfl_down_sync(full, lo, 1);
+  const int hi = (lane == 31) ? st->desc.r1 : hi_n;
   const int cnt = hi - lo;
   int ns = 0;
   double sumKv = 0.0, sumQ = 0.0, maxKv = 0.0, avgKv = 0.0, avgQ = 0.0;
@@ -522,7 +533,6 @@ __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in,
   SatTally tally = {0, 0, 0, 0};
   const long long gw = (long long)blockIdx.x * SAT_WARPS + warp, tw = (long long)gridDim.x * SAT_WARPS;
   const long long M = in.n_models;
-  const bool has_hs = in.var_has_state != nullptr;
 
   if (lane == 0) {
     for (int s = 0; s < SAT_NS; s++) sat_mbar_init(&ws->bar[s], 1);
@@ -531,14 +541,15 @@ __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in,
   __syncwarp();
   // geometry (16 bytes) of the models this warp touches next: loaded a full model ahead of its use
   int4 g_cur = make_int4(0, 0, 0, 0), g_fill = make_int4(0, 0, 0, 0);
-  // prologue: the first SAT_NS models of this warp
+  // prologue: the first SAT_NS models of this warp; one cp.async group per model, empty or not
   for (int k = 0; k < SAT_NS; k++) {
     const long long mk = gw + (long long)k * tw;
     if (mk < M) {
       const int4 gk = *reinterpret_cast<const int4*>(desc + mk);
       if (k == 0) g_cur = gk;
-      if (lane == 0 && sat_staged(gk.x, gk.y, gk.z, gk.w)) sat_issue(in, desc, mk, gk.x, gk.y, gk.z, gk.w, &ws->stage[k], &ws->bar[k]);
+      if (sat_staged(gk.x, gk.y, gk.z, gk.w)) sat_issue(in, desc, mk, gk.x, gk.y, gk.z, gk.w, &ws->stage[k], &ws->bar[k]);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   unsigned par_bits = 0;          // bit s = phase parity of the next wait on stage s
   int s = 0;
@@ -547,16 +558,20 @@ __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in,
     int4 g_next = g_cur;
     if (m_next < M) g_next = *reinterpret_cast<const int4*>(desc + m_next);
     if (m_fill < M) g_fill = *reinterpret_cast<const int4*>(desc + m_fill);
+    // this model's cp.async group is the oldest of the SAT_NS pending ones
+    asm volatile("cp.async.wait_group %0;" ::"n"(SAT_NS - 1) : "memory");
     if (sat_staged(g_cur.x, g_cur.y, g_cur.z, g_cur.w)) {
       sat_mbar_wait(&ws->bar[s], (par_bits >> s) & 1u);          // a model that is not staged never arms its barrier
       par_bits ^= 1u << s;
-      sat_model_staged<DETAIL>(&ws->stage[s], has_hs, m, out, ws->terms, tally);
+      __syncwarp();                                               // the other lanes' cp.async data
+      sat_model_staged<DETAIL>(&ws->stage[s], in.var_has_state, m, out, ws->terms, tally);
     } else {
       sat_model<DETAIL, false>(in, in.rep_kv, in.rep_queue, 0, m, g_cur.x, g_cur.y, out, ws->terms, tally);
     }
     __syncwarp();                                                 // every lane is done with stage s before it is refilled
-    if (lane == 0 && m_fill < M && sat_staged(g_fill.x, g_fill.y, g_fill.z, g_fill.w))
+    if (m_fill < M && sat_staged(g_fill.x, g_fill.y, g_fill.z, g_fill.w))
       sat_issue(in, desc, m_fill, g_fill.x, g_fill.y, g_fill.z, g_fill.w, &ws->stage[s], &ws->bar[s]);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     s = (s + 1 == SAT_NS) ? 0 : s + 1;
     g_cur = g_next;
   }

@@ -11,7 +11,7 @@ d = pkg.synth.baseline_config(3, scale=scale) if N == 256 else pkg.synth.queue_s
 out = {"pairs": int(d["n_servers"] * d["n_acc"]), "N": N, "runs": []}
 with pkg.Engine(0) as e:
     e.load_system(d)
-    for table in (0, 2):
+    for table in ([int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else (0, 2)):
         for sort, gang in ((0, 0), (1, 0), (1, 1), (0, 1)):
             e.set_option(4, table); e.set_option(2, sort); e.set_option(3, gang)
             ts = []

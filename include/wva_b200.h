@@ -183,7 +183,8 @@ int64_t wva_launch_count(const wva_ctx* ctx);
                                       2: lane-per-pair, lock-step rounds (what large systems use); 3: two chains
                                       per lane (TTFT and ITL searches together); 4: every pair split into a TTFT
                                       item and an ITL item; 5: split items whose second chain evaluates the
-                                      predicted next bisection point */
+                                      predicted next bisection point; 6: pool sizer — the pending solves of 1024 pairs
+                                      per SM regrouped by chain length (what very large systems use) */
 #define WVA_OPT_LENGTH_SORT 2      /* 1: the lane sizer visits the work items in probe-sorted order
                                       (csrc/sizer_probe.cuh); 0: natural (server, accelerator) order; -1 (default):
                                       sorted where it was measured to pay (130-1500 pairs per SM).  Order
@@ -194,9 +195,11 @@ int64_t wva_launch_count(const wva_ctx* ctx);
 #define WVA_OPT_TABLE_MODE 4       /* lane sizer head table: 0 (default) shared memory when >= 64 lanes per SM fit, else
                                       global memory; 1 force shared memory (when it fits at all); 2 force global memory
                                       (two 256-thread blocks per SM under a 128-register cap).  Placement only */
-#define WVA_OPT_GREEDY_MODE 5      /* limited-capacity allocator: 0 (default) the static-order event sweep
-                                      (csrc/greedy_sweep.cuh) wherever it applies; 1 the literal queue (sorted array +
-                                      re-insertion heap, csrc/greedy_solve.cuh).  Same result either way */
+#define WVA_OPT_GREEDY_MODE 5      /* limited-capacity allocator: 1 the literal queue (sorted array + re-insertion heap,
+                                      csrc/greedy_solve.cuh); 2 the static-order event sweep (csrc/greedy_sweep.cuh)
+                                      wherever it applies; 0 (default) by measured cost: the sweep under policy None
+                                      (it stops once nothing can fit any more), the queue under the best-effort
+                                      policies.  Same result either way */
 int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value);
 
 /* ---- multi-GPU: model-sharded over one NCCL communicator ----------------- */

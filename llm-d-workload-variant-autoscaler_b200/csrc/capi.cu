@@ -7,6 +7,7 @@
 #include "sizer_kernel.cuh"
 #include "sizer_warp_kernel.cuh"
 #include "sizer_lane_kernel.cuh"
+#include "sizer_pool_kernel.cuh"
 #include "sizer_probe.cuh"
 #include "solve_kernels.cuh"
 #include "grid_kernel.cuh"
@@ -102,7 +103,7 @@ struct wva_ctx {
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
   int policy = 0;
-  DevBuf sys_arena, cand_arena, sol_arena, scratch, gtab, greedy_ws, split_ws, order_ws;
+  DevBuf sys_arena, cand_arena, sol_arena, scratch, gtab, greedy_ws, split_ws, order_ws, pool_ws;
   PinBuf stage_in, stage_out;
   SysView sys = {};
   CandView cand = {};
@@ -209,7 +210,7 @@ int32_t wva_destroy(wva_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->sys_arena.release(); ctx->cand_arena.release(); ctx->sol_arena.release(); ctx->scratch.release();
-  ctx->gtab.release(); ctx->greedy_ws.release(); ctx->split_ws.release(); ctx->order_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->sat.desc.release(); ctx->io_in.release(); ctx->io_out.release();
+  ctx->gtab.release(); ctx->pool_ws.release(); ctx->greedy_ws.release(); ctx->split_ws.release(); ctx->order_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->sat.desc.release(); ctx->io_in.release(); ctx->io_out.release();
   ctx->stage_in.release(); ctx->stage_out.release(); ctx->io_stage_in.release(); ctx->io_stage_out.release();
   comm_release(ctx); ctx->comm_ws.release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -369,7 +370,9 @@ static cudaError_t launch_sizer(wva_ctx* ctx, int blocks, size_t smem, unsigned 
     // 1.5-15 waves and longest-first ordering shortens the tail: -18 % at 24 k pairs, -30 % at 48 k, -15 % at 100-130 k);
     // below, every lane holds one item and the probe is pure overhead; far above, the gain (6 % at 320 k pairs, 2 % at
     // N = 256) no longer covers the probe's variance
-    const bool by_size = n_pairs > (unsigned long long)ctx->sm_count * 130 && n_pairs <= (unsigned long long)ctx->sm_count * 1500;
+    // r2, table in global memory, 3.2 M pairs at N = 256: 402 ms natural order, 371 ms sorted + gang refill
+    const bool by_size = n_pairs > (unsigned long long)ctx->sm_count * 130 &&
+                         (n_pairs <= (unsigned long long)ctx->sm_count * 1500 || !SMEM);
     const bool do_sort = ctx->length_sort < 0 ? by_size : ctx->length_sort != 0;
     const bool do_gang = ctx->gang_refill < 0 ? by_size : ctx->gang_refill != 0;
     if (do_sort && n_items >= 64 && n_items < (1ull << 31)) {
@@ -422,12 +425,12 @@ int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
   if (!ctx) return WVA_ERR_ARG;
   if (option == WVA_OPT_FORCE_LANE_SIZER) {
     ctx->force_lane_sizer = value != 0;
-    if (value >= 1 && value <= 5) ctx->lane_sizer_mode = value;
+    if (value >= 1 && value <= 6) ctx->lane_sizer_mode = value;
     return WVA_OK;
   }
   if (option == WVA_OPT_LENGTH_SORT) { ctx->length_sort = value < 0 ? -1 : (value != 0); return WVA_OK; }
   if (option == WVA_OPT_GANG_REFILL) { ctx->gang_refill = value < 0 ? -1 : (value != 0); return WVA_OK; }
-  if (option == WVA_OPT_GREEDY_MODE) { if (value < 0 || value > 1) return WVA_ERR_ARG; ctx->greedy_mode = value; return WVA_OK; }
+  if (option == WVA_OPT_GREEDY_MODE) { if (value < 0 || value > 2) return WVA_ERR_ARG; ctx->greedy_mode = value; return WVA_OK; }
   if (option == WVA_OPT_TABLE_MODE) { if (value < 0 || value > 2) return WVA_ERR_ARG; ctx->table_mode = value; return WVA_OK; }
   return WVA_ERR_ARG;
 }
@@ -483,6 +486,25 @@ int32_t wva_calculate(wva_ctx* ctx) {
     if (!ctx->force_lane_sizer)
       ctx->lane_sizer_mode = (n_pairs <= (unsigned long long)ctx->sm_count * 180) ? 4
                            : (n_pairs <= (unsigned long long)ctx->sm_count * 380) ? 5 : 2;
+    // large systems: the pool sizer (sizer_pool_kernel.cuh) regroups the pending solves of 1024 pairs per SM by
+    // length every time a warp goes back for work (88-92 % live lane-steps instead of 49-62 %)
+    const bool pool_auto = !ctx->force_lane_sizer && n_pairs > (unsigned long long)ctx->sm_count * 4096 && nmax <= 4096;
+    if (pool_auto || (ctx->force_lane_sizer && ctx->lane_sizer_mode == 6)) {
+      const int P = POOL_PMAX;
+      const int row_stride = (nmax + 31) & ~31;
+      const size_t pool_bytes = (size_t)ctx->sm_count * P * sizeof(PoolEntry);
+      const size_t rows_bytes = (size_t)ctx->sm_count * P * (size_t)row_stride * 4;
+      CK(ctx->pool_ws.reserve(pool_bytes + rows_bytes + 512));
+      PoolEntry* pool = (PoolEntry*)ctx->pool_ws.p;
+      float* rows = (float*)((char*)ctx->pool_ws.p + ((pool_bytes + 255) & ~(size_t)255));
+      CK(cudaFuncSetAttribute(sizer_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoolSmem)));
+      sizer_pool_kernel<<<ctx->sm_count, POOL_THREADS, sizeof(PoolSmem), ctx->stream>>>(sys_v, cand_v, n_pairs, nmax, P, pool, rows,
+                                                                                        row_stride, ctx->d_ctr, d_ovf);
+      ctx->launches++;
+      cudaError_t pe = cudaGetLastError();
+      if (pe != cudaSuccess) { ctx->last_error = std::string("pool sizer launch: ") + cudaGetErrorString(pe); return WVA_ERR_CUDA; }
+      goto sizer_done;
+    }
     const unsigned long long n_items = (ctx->lane_sizer_mode >= 4) ? 2 * n_pairs : n_pairs;
     const unsigned long long lanes_needed = (n_items + ctx->sm_count - 1) / ctx->sm_count;
     if (best_per_sm >= 1 && lanes_needed <= 256 && lanes_needed < (unsigned long long)best_threads * best_per_sm) {
@@ -524,6 +546,7 @@ int32_t wva_calculate(wva_ctx* ctx) {
     }
     if (e != cudaSuccess) { ctx->last_error = std::string("sizer launch: ") + cudaGetErrorString(e); return WVA_ERR_CUDA; }
   }
+sizer_done:
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   SizerCounters hc;
   CK(cudaMemcpyAsync(&hc, ctx->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
@@ -561,7 +584,9 @@ static int32_t solve_view(wva_ctx* ctx, const SysView& sv, const CandView& cv, c
     } else {
       long long gstats[2] = {0, 0};
       // the static-order sweep (greedy_sweep.cuh) wherever it applies; the literal queue otherwise or on request
-      const bool sweep = ctx->greedy_mode != 1 && greedy_sweep_covers(sv);
+      // measured (100 k servers x 32, capacity 60 %): policy None 31 ms (sweep) vs 67 ms (queue); best-effort policies
+      // 400 ms vs 300 ms
+      const bool sweep = greedy_sweep_covers(sv) && (ctx->greedy_mode == 2 || (ctx->greedy_mode == 0 && ctx->policy == WVA_POLICY_NONE));
       int32_t rc = sweep ? run_solve_greedy_sweep(sv, cv, ov, ctx->delayed, ctx->policy, &ctx->greedy_ws.p,
                                                   &ctx->greedy_ws.cap, ctx->stream, &ctx->launches, gstats)
                          : run_solve_greedy(sv, cv, ov, ctx->delayed, ctx->policy, &ctx->greedy_ws.p,

@@ -28,6 +28,7 @@ struct WarpTable {   // one table per warp in shared memory: (mu_n, ~1/mu_n) as 
   const double2* t;
   __device__ __forceinline__ void load(int n, double& mu, double& r) const { double2 v = t[n]; mu = v.x; r = v.y; }
   __device__ __forceinline__ double mu_at(int n) const { return t[n].x; }
+  __device__ __forceinline__ void prepare(int) const {}
 };
 struct LaneTable {   // one float32 column per lane ([n][thread], bank = lane); 1/mu refined on the fly
   const float* t;
@@ -36,6 +37,31 @@ struct LaneTable {   // one float32 column per lane ([n][thread], bank = lane); 
     float m32 = t[(size_t)n * stride]; mu = (double)m32; r = rcp_f32den(m32, mu);
   }
   __device__ __forceinline__ double mu_at(int n) const { return (double)t[(size_t)n * stride]; }
+  __device__ __forceinline__ void prepare(int) const {}
+};
+// Rows in global memory, one per pool slot, and any 32 of them solved together (sizer_pool_kernel.cuh): every 32 head
+// states the warp stages the next 32 entries of its 32 rows into a shared tile — row by row, each a coalesced 128-byte
+// load, stored transposed ([state][lane], padded: conflict-free) — and the lanes then read their own column.
+struct TileTable {
+  const float* rows;      // base of the CTA's rows
+  int row_stride;         // floats per row (a multiple of 32)
+  int slot;               // this lane's row (any valid row for an idle lane)
+  float* tile;            // the warp's [32][33] tile in shared memory
+  __device__ __forceinline__ void prepare(int n) const {
+    if (n & 31) return;
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+#pragma unroll 8
+    for (int r = 0; r < 32; r++) {
+      const int sr = __shfl_sync(0xffffffffu, slot, r);
+      tile[lane * 33 + r] = __ldcg(rows + (size_t)sr * row_stride + n + lane);
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void load(int n, double& mu, double& r) const {
+    float m32 = tile[(n & 31) * 33 + (threadIdx.x & 31)]; mu = (double)m32; r = rcp_f32den(m32, mu);
+  }
+  __device__ __forceinline__ double mu_at(int n) const { return (double)tile[(n & 31) * 33 + (threadIdx.x & 31)]; }
 };
 
 // high word of v * 2^-54 for a normal v >= 2^-900: the exponent field moves, nothing rounds
@@ -200,6 +226,7 @@ __device__ __forceinline__ void lockstep_solve_inl(const PairModel& m, const Tab
   bool all_done = false;
   while (n < NH && !all_done) {                       // head: table entries n .. n+cnt-1
     const int cnt = min(CH, NH - n);
+    tab.prepare(n);
     const double mu0 = tab.mu_at(n);
 #pragma unroll
     for (int c = 0; c < NC; c++) { a[c].mn = 0x7fffffff; a[c].mx = 0; }
@@ -280,6 +307,7 @@ __device__ __forceinline__ void lockstep_solve_inl(const PairModel& m, const Tab
   n = 0;
   while (n < NH && !all_done) {                       // head (i = n+1 <= N-1)
     const int cnt = min(CH, NH - n);
+    tab.prepare(n);
     const double mu0 = tab.mu_at(n);
 #pragma unroll
     for (int c = 0; c < NC; c++) { b[c].mn = 0x7fffffff; b[c].mx = 0; }

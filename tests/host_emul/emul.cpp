@@ -287,6 +287,43 @@ extern "C" int emul_trace_split(const wva_system* sys, int32_t* trace, int W) {
   return 0;
 }
 
+// Analysis helper: per WHOLE pair, the number of states of each chain solve of Size() + the two Analyze solves, in order
+// (trace[pair * W] = count, then the lengths) — input of tools/proto/lockstep_sim.py.
+extern "C" int emul_trace_pair(const wva_system* sys, int32_t* trace, int W, float* ratio) {
+  SysView s = make_view(sys);
+  CandView o = {};
+  std::vector<float> tab;
+  for (int srv = 0; srv < s.n_servers; srv++)
+    for (int acc = 0; acc < s.n_acc; acc++) {
+      int32_t* t = trace + (size_t)(srv * s.n_acc + acc) * W;
+      t[0] = 0;
+      SizerLane z; int lim = 0;
+      if (sizer_setup(z, s, o, srv, acc, 1 << 20, &lim, false) == SETUP_DONE) continue;
+      tab.assign((size_t)z.m.N, 0.0f);
+      model_fill_table(z.m, tab.data(), 1, 0, 1);
+      model_finish(z.m, tab.data(), 1);
+      std::vector<unsigned char> st_none(1);
+      o.state = nullptr;
+      // candidates are not written: a scratch view
+      static thread_local std::vector<unsigned char> b1; static thread_local std::vector<int> b4; static thread_local std::vector<float> bf;
+      b1.assign((size_t)s.n_servers * s.n_acc, 0); b4.assign((size_t)s.n_servers * s.n_acc, 0); bf.assign((size_t)s.n_servers * s.n_acc, 0.f);
+      o.state = b1.data(); o.num_replicas = b4.data(); o.batch_size = b4.data(); o.cost = bf.data(); o.value = bf.data();
+      o.itl = bf.data(); o.ttft = bf.data(); o.rho = bf.data(); o.max_arrv_rate = bf.data(); o.n_solves = nullptr;
+      bool live = sizer_begin(z, s, o);
+      while (live) {
+        SolveStats st{};
+        while (!chain_step(z.c, z.m, st)) {}
+        if (z.c.phase == CH_OVERFLOW) break;
+        if (t[0] + 1 < W) {
+          t[++t[0]] = z.c.states;
+          if (ratio) ratio[(size_t)(srv * s.n_acc + acc) * W + t[0]] = (float)((double)z.cur_x / z.m.mu_last);
+        }
+        live = sizer_on_solve(z, s, o, st);
+      }
+    }
+  return 0;
+}
+
 extern "C" {
 
 // System.Calculate through the lane state machine, one lane at a time.

@@ -18,7 +18,7 @@ for pol in ("None", "PriorityExhaustive", "PriorityRoundRobin", "RoundRobin"):
     for delayed in (False, True):
         row = {}
         ref = None
-        for mode, name in ((0, "sweep"), (1, "queue")):
+        for mode, name in ((2, "sweep"), (1, "queue")):
             e.set_option(5, mode)
             e.set_optimizer(False, delayed, pol)
             ts = []

@@ -39,29 +39,50 @@ struct LaneTable {   // one float32 column per lane ([n][thread], bank = lane); 
   __device__ __forceinline__ double mu_at(int n) const { return (double)t[(size_t)n * stride]; }
   __device__ __forceinline__ void prepare(int) const {}
 };
-// Rows in global memory, one per pool slot, and any 32 of them solved together (sizer_pool_kernel.cuh): every 32 head
-// states the warp stages the next 32 entries of its 32 rows into a shared tile — row by row, each a coalesced 128-byte
-// load, stored transposed ([state][lane], padded: conflict-free) — and the lanes then read their own column.
+// Rows in global memory, one per pool slot, and any 32 of them solved together (sizer_pool_kernel.cuh): the warp keeps
+// two shared tiles of 32 head states x 32 lanes ([state][lane], padded: conflict-free).  Tile k+1 is fetched with
+// cp.async (row by row: each row a coalesced 128-byte access, no registers, no scoreboard) while the lanes work on
+// tile k, so the only exposed latency is the first tile of a pass.
 struct TileTable {
   const float* rows;      // base of the CTA's rows
-  int row_stride;         // floats per row (a multiple of 32)
+  int row_stride;         // floats per row (a multiple of 32, >= N)
   int slot;               // this lane's row (any valid row for an idle lane)
-  float* tile;            // the warp's [32][33] tile in shared memory
-  __device__ __forceinline__ void prepare(int n) const {
-    if (n & 31) return;
+  float* tile;            // the warp's two [32][33] tiles in shared memory
+  int n_head;             // head entries (N - 1): tiles beyond are never fetched
+  __device__ __forceinline__ void fetch(int n0) const {
     const int lane = threadIdx.x & 31;
-    __syncwarp();
+    float* t = tile + ((n0 >> 5) & 1) * (32 * 33);
+    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(t + lane * 33);
 #pragma unroll 8
     for (int r = 0; r < 32; r++) {
       const int sr = __shfl_sync(0xffffffffu, slot, r);
-      tile[lane * 33 + r] = __ldcg(rows + (size_t)sr * row_stride + n + lane);
+      const float* src = rows + (size_t)sr * row_stride + n0 + lane;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 4u * r), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void prepare(int n) const {
+    if (n & 31) return;
+    if (n == 0) {                                               // first tile of a pass
+      asm volatile("cp.async.wait_group 0;" ::: "memory");      // a tile still in flight from a pass that ended early
+      __syncwarp();
+      fetch(0);
+    }
+    if (n + 32 < n_head) {                                      // next tile in flight while this one is used
+      __syncwarp();                                             // (its buffer was last read two tiles ago)
+      fetch(n + 32);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncwarp();
   }
   __device__ __forceinline__ void load(int n, double& mu, double& r) const {
-    float m32 = tile[(n & 31) * 33 + (threadIdx.x & 31)]; mu = (double)m32; r = rcp_f32den(m32, mu);
+    float m32 = tile[((n >> 5) & 1) * (32 * 33) + (n & 31) * 33 + (threadIdx.x & 31)]; mu = (double)m32; r = rcp_f32den(m32, mu);
   }
-  __device__ __forceinline__ double mu_at(int n) const { return (double)tile[(n & 31) * 33 + (threadIdx.x & 31)]; }
+  __device__ __forceinline__ double mu_at(int n) const {
+    return (double)tile[((n >> 5) & 1) * (32 * 33) + (n & 31) * 33 + (threadIdx.x & 31)];
+  }
 };
 
 // high word of v * 2^-54 for a normal v >= 2^-900: the exponent field moves, nothing rounds

@@ -539,41 +539,41 @@ __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in,
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  // geometry (16 bytes) of the models this warp touches next: loaded a full model ahead of its use
-  int4 g_cur = make_int4(0, 0, 0, 0), g_fill = make_int4(0, 0, 0, 0);
-  // prologue: the first SAT_NS models of this warp; one cp.async group per model, empty or not
-  for (int k = 0; k < SAT_NS; k++) {
-    const long long mk = gw + (long long)k * tw;
-    if (mk < M) {
-      const int4 gk = *reinterpret_cast<const int4*>(desc + mk);
-      if (k == 0) g_cur = gk;
-      if (sat_staged(gk.x, gk.y, gk.z, gk.w)) sat_issue(in, desc, mk, gk.x, gk.y, gk.z, gk.w, &ws->stage[k], &ws->bar[k]);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  unsigned par_bits = 0;          // bit s = phase parity of the next wait on stage s
-  int s = 0;
-  for (long long m = gw; m < M; m += tw) {
-    const long long m_next = m + tw, m_fill = m + (long long)SAT_NS * tw;
-    int4 g_next = g_cur;
-    if (m_next < M) g_next = *reinterpret_cast<const int4*>(desc + m_next);
-    if (m_fill < M) g_fill = *reinterpret_cast<const int4*>(desc + m_fill);
-    // this model's cp.async group is the oldest of the SAT_NS pending ones
-    asm volatile("cp.async.wait_group %0;" ::"n"(SAT_NS - 1) : "memory");
-    if (sat_staged(g_cur.x, g_cur.y, g_cur.z, g_cur.w)) {
-      sat_mbar_wait(&ws->bar[s], (par_bits >> s) & 1u);          // a model that is not staged never arms its barrier
-      par_bits ^= 1u << s;
+  // Geometry (16 bytes: variants [x, y), replicas [z, w)) of the models this warp touches next, carried in registers
+  // from one loop trip to the next so that no descriptor load is consumed in the trip that issues it:
+  //   d0 the model analysed now, d1 the next one, d2 the one whose copies are issued at the end of this trip (SAT_NS = 2
+  //   models ahead), d3 loaded now for the next trip.
+  static_assert(SAT_NS == 2, "the loop below is unrolled for two stages");
+  const int4 none = make_int4(0, 0, 0, 0);
+  auto geom = [&](long long mm) { return mm < M ? __ldg(reinterpret_cast<const int4*>(desc + mm)) : none; };
+  int4 d0 = geom(gw), d1 = geom(gw + tw), d2 = geom(gw + 2 * tw);
+  // prologue: the first two models; one cp.async group per model, empty or not
+  if (gw < M && sat_staged(d0.x, d0.y, d0.z, d0.w)) sat_issue(in, desc, gw, d0.x, d0.y, d0.z, d0.w, &ws->stage[0], &ws->bar[0]);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (gw + tw < M && sat_staged(d1.x, d1.y, d1.z, d1.w)) sat_issue(in, desc, gw + tw, d1.x, d1.y, d1.z, d1.w, &ws->stage[1], &ws->bar[1]);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  unsigned par0 = 0, par1 = 0;    // phase parity of the next wait on each stage
+  // one model out of stage S (a compile-time constant: the stage addresses fold into the instructions)
+  auto step = [&](const int S, unsigned& par, long long m) {
+    const int4 d3 = geom(m + 3 * tw);
+    asm volatile("cp.async.wait_group %0;" ::"n"(SAT_NS - 1) : "memory");   // this model's group is the oldest pending one
+    if (sat_staged(d0.x, d0.y, d0.z, d0.w)) {
+      sat_mbar_wait(&ws->bar[S], par);                           // a model that is not staged never arms its barrier
+      par ^= 1u;
       __syncwarp();                                               // the other lanes' cp.async data
-      sat_model_staged<DETAIL>(&ws->stage[s], in.var_has_state, m, out, ws->terms, tally);
+      sat_model_staged<DETAIL>(&ws->stage[S], in.var_has_state, m, out, ws->terms, tally);
     } else {
-      sat_model<DETAIL, false>(in, in.rep_kv, in.rep_queue, 0, m, g_cur.x, g_cur.y, out, ws->terms, tally);
+      sat_model<DETAIL, false>(in, in.rep_kv, in.rep_queue, 0, m, d0.x, d0.y, out, ws->terms, tally);
     }
-    __syncwarp();                                                 // every lane is done with stage s before it is refilled
-    if (m_fill < M && sat_staged(g_fill.x, g_fill.y, g_fill.z, g_fill.w))
-      sat_issue(in, desc, m_fill, g_fill.x, g_fill.y, g_fill.z, g_fill.w, &ws->stage[s], &ws->bar[s]);
+    __syncwarp();                                                 // every lane is done with stage S before it is refilled
+    const long long m_fill = m + 2 * tw;
+    if (m_fill < M && sat_staged(d2.x, d2.y, d2.z, d2.w)) sat_issue(in, desc, m_fill, d2.x, d2.y, d2.z, d2.w, &ws->stage[S], &ws->bar[S]);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    s = (s + 1 == SAT_NS) ? 0 : s + 1;
-    g_cur = g_next;
+    d0 = d1; d1 = d2; d2 = d3;
+  };
+  for (long long m = gw; m < M; m += 2 * tw) {
+    step(0, par0, m);
+    if (m + tw < M) step(1, par1, m + tw);
   }
   if (out.partials) {
     long long sum_targets = tally.sum_targets;

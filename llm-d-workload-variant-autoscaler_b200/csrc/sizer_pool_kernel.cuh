@@ -38,7 +38,7 @@ struct PoolSmem {
   unsigned short free_list[POOL_PMAX];
   int head[POOL_NCLS], tail[POOL_NCLS];
   int n_free, in_pool, exhausted, lock;
-  float tiles[POOL_THREADS / 32][32 * 33];
+  float tiles[POOL_THREADS / 32][2 * 32 * 33];
 };
 
 __device__ __forceinline__ void pool_lock(int* lock) {
@@ -202,29 +202,29 @@ sizer_pool_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
         }
         bool live = false;
         if (need_table) {
+          // BuildModel (queueanalyzer.go:95-124) into the slot's row; the monotone region and the rate range are taken
+          // from the values as they are produced (model_finish's scan from the top stops at the LAST descent)
           float* row = rows + (size_t)new_slot * row_stride;
-          for (int n = 0; n < z.m.N; n++) __stcg(row + n, serv_rate(z.m, n + 1));
-          // model_finish reads the row back: through L2 as well
-          {
-            PairModel& m = z.m;
-            m.tab = row; m.stride = 1;
-            const float r0 = __ldcg(row), rl = __ldcg(row + (m.N - 1));
-            const float lmin = f_mul(r0, WVA_EPSILON), lmax = f_mul(rl, f_sub(1.0f, WVA_EPSILON));   // queueanalyzer.go:107-108
-            const float rmin = f_mul(lmin, 1000.0f);
-            m.rate_max = f_mul(lmax, 1000.0f);
-            m.lambda_min = f_div(rmin, 1000.0f);                                                       // :189-190
-            m.lambda_max = f_div(m.rate_max, 1000.0f);
-            int mono = 0;
-            float nxt = rl;
-            for (int n = m.N - 2; n >= 0; n--) {
-              const float cur = __ldcg(row + n);
-              if (!(cur <= nxt)) { mono = n + 1; break; }
-              nxt = cur;
-            }
-            m.mono = mono;
-            m.mu_last = (double)rl;
-            m.r_last = rcp_f32den(rl, m.mu_last);
+          PairModel& m = z.m;
+          m.tab = row; m.stride = 1;
+          float r0 = 0.0f, prev = 0.0f;
+          int mono = 0;
+          for (int n = 0; n < m.N; n++) {
+            const float cur = serv_rate(m, n + 1);
+            __stcg(row + n, cur);
+            if (n == 0) r0 = cur;
+            else if (!(prev <= cur)) mono = n;
+            prev = cur;
           }
+          const float rl = prev;
+          const float lmin = f_mul(r0, WVA_EPSILON), lmax = f_mul(rl, f_sub(1.0f, WVA_EPSILON));   // queueanalyzer.go:107-108
+          const float rmin = f_mul(lmin, 1000.0f);
+          m.rate_max = f_mul(lmax, 1000.0f);
+          m.lambda_min = f_div(rmin, 1000.0f);                                                       // :189-190
+          m.lambda_max = f_div(m.rate_max, 1000.0f);
+          m.mono = mono;
+          m.mu_last = (double)rl;
+          m.r_last = rcp_f32den(rl, m.mu_last);
           live = sizer_begin(z, s, out);
           if (!live) my_solves += z.solves;
         }
@@ -251,7 +251,7 @@ sizer_pool_kernel(SysView s, CandView out, unsigned long long n_pairs, int nmax,
     SolveStats st;
     if (uniform) {
       if (!live) { pm.m.N = nref; pm.m.K = nref + nref * WVA_QUEUE_TO_BATCH; pm.m.mono = 0; pm.m.mu_last = 1.0; pm.m.r_last = 1.0; }
-      TileTable tt; tt.rows = rows; tt.row_stride = row_stride; tt.slot = live ? my_slot : 0; tt.tile = tile;
+      TileTable tt; tt.rows = rows; tt.row_stride = row_stride; tt.slot = live ? my_slot : 0; tt.tile = tile; tt.n_head = nref - 1;
       lockstep_solve(pm.m, tt, x, live, st, sv, bad);
     }
     if (live) {

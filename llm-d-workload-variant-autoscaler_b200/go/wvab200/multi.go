@@ -43,19 +43,19 @@ func (g *Group) Size() int { return int(C.wva_group_size(g.g)) }
 // Ctx returns the context of device i (timings, options); it stays owned by the group.
 func (g *Group) Ctx(i int) *Ctx { return &Ctx{c: C.wva_group_ctx(g.g, C.int32_t(i))} }
 
-// OptimizeGroup = pkg/manager.Manager.Optimize (manager.go:21-27) over every GPU of the group.  flatten() and
-// solutionFromSoA() are the helpers of wvab200.go (SystemSpec -> index-keyed SoA on sorted names, and back).
-func (m *Manager) OptimizeGroup(g *Group) (*config.AllocationSolution, error) {
+// OptimizeGroup = pkg/manager.Manager.Optimize (manager.go:21-27) over every GPU of the group: the body of
+// (*Manager).Optimize in wvab200.go with its three calls wva_load_system / wva_calculate / wva_solve /
+// wva_get_solution replaced by the one call below (sys and sol are the wva_system / wva_solution that Optimize builds).
+func optimizeGroup(g *Group, sys *C.wva_system, sol *C.wva_solution) error {
 	runtime.LockOSThread()
 	defer runtime.UnlockOSThread()
-	sys, keep := flatten(m.spec)
-	defer runtime.KeepAlive(keep)
-	out, sol := allocSolution(int(sys.n_servers), int(sys.n_types))
-	if rc := C.wva_group_optimize(g.g, &sys, &sol); rc != C.WVA_OK {
-		return nil, fmt.Errorf("wva_group_optimize: %s", C.GoString(C.wva_strerror(rc)))
+	if rc := C.wva_group_optimize(g.g, sys, sol); rc != C.WVA_OK {
+		return fmt.Errorf("wva_group_optimize: %s", C.GoString(C.wva_strerror(rc)))
 	}
-	return solutionFromSoA(m.spec, out), nil
+	return nil
 }
+
+var _ *config.AllocationSolution // (the solution type Optimize returns)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Batched V1 saturation: every model of a reconcile cycle in ONE launch.  The reference's engine loops over model
@@ -88,19 +88,19 @@ func (a *SaturationAnalyzer) AnalyzeBatch(ctx context.Context, models []ModelInp
 	mvo = append(mvo, 0)
 	vro = append(vro, 0)
 	for mi, m := range models {
-		b := groupByVariant(m.Replicas) // wvab200.go: variant names sorted, replica indices per variant
-		names[mi] = b.names
+		b := groupByVariant(m.Replicas) // wvab200.go: variant names sorted, metrics per variant in slice order
+		names[mi] = b.variants
 		st := map[string]interfaces.VariantReplicaState{}
 		for _, s := range m.States {
 			st[s.VariantName] = s
 		}
-		for vi, name := range b.names {
-			for _, ri := range b.replicas[vi] {
-				kv = append(kv, C.double(m.Replicas[ri].KvCacheUsage))
-				q = append(q, C.int64_t(m.Replicas[ri].QueueLength))
+		for _, name := range b.variants {
+			for _, r := range b.metrics[name] {
+				kv = append(kv, C.double(r.KvCacheUsage))
+				q = append(q, C.int64_t(r.QueueLength))
 			}
 			vro = append(vro, C.int32_t(len(kv)))
-			cost = append(cost, C.double(m.Replicas[b.replicas[vi][0]].Cost))
+			cost = append(cost, C.double(b.metrics[name][0].Cost))
 			s, ok := st[name]
 			cur = append(cur, C.int32_t(s.CurrentReplicas))
 			des = append(des, C.int32_t(s.DesiredReplicas))

@@ -1,7 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider -k "calculate or lane_kernels or config3 or saturation or config4 or ingest" > gpurun_out/s7_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s7_pytest.log
-WVA_SIZER_DEBUG=1 timeout 600 python tools/perf_sizer_full.py 1.0 > gpurun_out/s7_sizer.json 2> gpurun_out/s7_sizer.err
-timeout 600 python tools/perf_sat.py > gpurun_out/s7_sat.json 2> gpurun_out/s7_sat.err
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:sizer_pool_kernel -c 1 -o gpurun_out/s7_pool_prof -f python tools/perf_sizer_full.py 0.05 > gpurun_out/s7_ncu.log 2>&1
-tail -3 gpurun_out/s7_pytest.log; cat gpurun_out/s7_sizer.json; cat gpurun_out/s7_sizer.err | tail -12; cat gpurun_out/s7_sat.json
+timeout 2400 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/s8_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s8_pytest.log
+timeout 600 python tools/cfg5_ingest.py > gpurun_out/s8_cfg5.json 2> gpurun_out/s8_cfg5.err
+timeout 900 python bench.py > gpurun_out/s8_bench.json 2> gpurun_out/s8_bench.err; echo "bench rc=$?" >> gpurun_out/s8_bench.err
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s8_smoke.log 2>&1
+tail -3 gpurun_out/s8_pytest.log; cat gpurun_out/s8_cfg5.json; tail -3 gpurun_out/s8_cfg5.err; tail -c 300 gpurun_out/s8_bench.err; cat gpurun_out/s8_smoke.log | tail -2
+python - <<PY
+import json
+d=json.load(open('gpurun_out/s8_bench.json'))
+for k in ('value','ms_per_step','solver_wall_ms','greedy','e2e','saturation','roofline_hbm','cpu_baseline','clocks'):
+    print(k, json.dumps(d.get(k))[:500])
+print('fp64', json.dumps(d['roofline']['fp64'])[:300])
+PY

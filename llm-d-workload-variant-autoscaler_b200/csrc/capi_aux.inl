@@ -80,6 +80,9 @@ extern "C" int32_t wva_grid_run(wva_ctx* ctx, int32_t R, int32_t full) {
   ctx->timing.chain_solves = (int64_t)hc.solves;
   ctx->timing.chain_states = (int64_t)hc.states;
   ctx->timing.overflow_pairs = (int64_t)hc.overflow;
+  if (getenv("WVA_SIZER_DEBUG"))
+    fprintf(stderr, "grid: live %llu, lock-step slots first round %llu, later rounds %llu, rounds %llu\n", hc.states, hc.slots0,
+            hc.slots_rest, hc.rounds);
   if (hc.limit_hit) { ctx->last_error = "grid: a pair needs a larger max batch size than the launch was built for"; return WVA_ERR_LIMIT; }
   g.ran = true;
   return WVA_OK;

@@ -23,7 +23,8 @@ struct GridOut {
 
 struct GridCounters {
   unsigned long long next_pair, solves, states, overflow;
-  int limit_hit;
+  int limit_hit, pad_;
+  unsigned long long slots0, slots_rest, rounds;   // 32 x longest chain of the round: first round of a pair / later rounds
 };
 
 // per-pair preparation shared by all lanes of the warp; false -> every level is "not ok"
@@ -54,7 +55,7 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double2* tab = smem_grid + (size_t)warp * nmax;
   float* tabf = (float*)(smem_grid + (size_t)WARPS * nmax) + (size_t)warp * nmax;
-  unsigned long long my_solves = 0, my_states = 0;
+  unsigned long long my_solves = 0, my_states = 0, my_s0 = 0, my_sr = 0, my_rounds = 0;
 
   while (true) {
     unsigned long long pair = 0;
@@ -90,6 +91,7 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
     model_finish(m, tabf, 1);
     const float lambda_tps = f_mul(m.lambda_max, f_sub(1.0f, WVA_STABILITY_SAFETY));
     int front = 0x7fffffff;
+    bool first_round = true;
 
     for (int r0 = 0; r0 < R; r0 += 32) {
       const int r = r0 + lane + 1;
@@ -113,6 +115,12 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
       bool bad = false, ovf = false;
       lockstep_solve(m, WarpTable{tab}, lambda, admitted, st, sv, bad);
       if (admitted) { my_solves++; my_states += (unsigned long long)sv; }
+      {
+        int mxs = admitted ? sv : 0;
+        for (int o = 16; o; o >>= 1) mxs = max(mxs, __shfl_xor_sync(full, mxs, o));
+        if (lane == 0) { if (first_round) my_s0 += 32ull * mxs; else my_sr += 32ull * mxs; my_rounds++; }
+        first_round = false;
+      }
       if (admitted && bad) {
         // outside the exponent window: redo this level alone through the per-lane state machine
         // (IEEE divisions); a true float64 overflow stays flagged (only the sizer has the rescale path)
@@ -156,7 +164,10 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
     my_solves += __shfl_down_sync(full, my_solves, o);
     my_states += __shfl_down_sync(full, my_states, o);
   }
-  if (lane == 0) { atomicAdd(&ctr->solves, my_solves); atomicAdd(&ctr->states, my_states); }
+  if (lane == 0) {
+    atomicAdd(&ctr->solves, my_solves); atomicAdd(&ctr->states, my_states);
+    atomicAdd(&ctr->slots0, my_s0); atomicAdd(&ctr->slots_rest, my_sr); atomicAdd(&ctr->rounds, my_rounds);
+  }
 }
 
 }  // namespace wva

@@ -38,6 +38,7 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")     # no "NCCL version ..." banner on stdout: rank 0 prints ONE JSON line
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

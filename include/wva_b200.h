@@ -200,6 +200,9 @@ int64_t wva_launch_count(const wva_ctx* ctx);
                                       wherever it applies; 0 (default) by measured cost: the sweep under policy None
                                       (it stops once nothing can fit any more), the queue under the best-effort
                                       policies.  Same result either way */
+#define WVA_OPT_GRID_DEFER 6       /* replica grid: 0 (default) the near-saturation levels of every pair (lambda / mu_N
+                                      > 0.6: the long chains) are deferred to a pass sorted by chain length when the
+                                      system has >= 20 000 pairs; 1 never; 2 always.  Scheduling only */
 int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value);
 
 /* ---- multi-GPU: model-sharded over one NCCL communicator ----------------- */

@@ -70,7 +70,7 @@ struct Layout {
 struct GridState {   // results of the last wva_grid_run, resident in HBM
   int R = 0;
   bool full = false, ran = false;
-  DevBuf buf;
+  DevBuf buf, defer;
   GridOut view = {};
   GridCounters* ctr = nullptr;
 };
@@ -99,6 +99,7 @@ struct wva_ctx {
   int length_sort = -1;             // lane sizer pulls items through the probe-sorted permutation (sizer_probe.cuh); -1 = by size
   int table_mode = 0;        // WVA_OPT_TABLE_MODE
   int greedy_mode = 0;       // WVA_OPT_GREEDY_MODE
+  int grid_defer = 0;        // WVA_OPT_GRID_DEFER
   int lane_sizer_mode = 2;   // 1 flattened, 2 lock-step (default), 3 lock-step with two chains per lane (slower: measured)
   int A = 0, T = 0, M = 0, S = 0;
   uint8_t unlimited = 1, delayed = 0;
@@ -210,7 +211,7 @@ int32_t wva_destroy(wva_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->sys_arena.release(); ctx->cand_arena.release(); ctx->sol_arena.release(); ctx->scratch.release();
-  ctx->gtab.release(); ctx->pool_ws.release(); ctx->greedy_ws.release(); ctx->split_ws.release(); ctx->order_ws.release(); ctx->grid.buf.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->sat.desc.release(); ctx->io_in.release(); ctx->io_out.release();
+  ctx->gtab.release(); ctx->pool_ws.release(); ctx->greedy_ws.release(); ctx->split_ws.release(); ctx->order_ws.release(); ctx->grid.buf.release(); ctx->grid.defer.release(); ctx->sat.in.release(); ctx->sat.out.release(); ctx->sat.desc.release(); ctx->io_in.release(); ctx->io_out.release();
   ctx->stage_in.release(); ctx->stage_out.release(); ctx->io_stage_in.release(); ctx->io_stage_out.release();
   comm_release(ctx); ctx->comm_ws.release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -430,6 +431,7 @@ int32_t wva_set_option(wva_ctx* ctx, int32_t option, int32_t value) {
   }
   if (option == WVA_OPT_LENGTH_SORT) { ctx->length_sort = value < 0 ? -1 : (value != 0); return WVA_OK; }
   if (option == WVA_OPT_GANG_REFILL) { ctx->gang_refill = value < 0 ? -1 : (value != 0); return WVA_OK; }
+  if (option == WVA_OPT_GRID_DEFER) { if (value < 0 || value > 2) return WVA_ERR_ARG; ctx->grid_defer = value; return WVA_OK; }
   if (option == WVA_OPT_GREEDY_MODE) { if (value < 0 || value > 2) return WVA_ERR_ARG; ctx->greedy_mode = value; return WVA_OK; }
   if (option == WVA_OPT_TABLE_MODE) { if (value < 0 || value > 2) return WVA_ERR_ARG; ctx->table_mode = value; return WVA_OK; }
   return WVA_ERR_ARG;

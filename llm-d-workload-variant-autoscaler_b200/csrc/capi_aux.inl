@@ -5,11 +5,11 @@
 // ------------------------------------------------------------------ replica grid
 template <int WARPS>
 static cudaError_t launch_grid(wva_ctx* ctx, int blocks, size_t smem, int R, const GridOut& o, unsigned long long n_pairs,
-                               int nmax, GridCounters* ctr) {
+                               int nmax, GridCounters* ctr, const GridDefer& df) {
   auto k = grid_kernel<WARPS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<blocks, WARPS * 32, smem, ctx->stream>>>(shard_sys(ctx), R, o, n_pairs, nmax, ctr);
+  k<<<blocks, WARPS * 32, smem, ctx->stream>>>(shard_sys(ctx), R, o, n_pairs, nmax, ctr, df);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -60,17 +60,59 @@ extern "C" int32_t wva_grid_run(wva_ctx* ctx, int32_t R, int32_t full) {
     // per-warp head table: (mu, 1/mu) float64 pairs + the float32 copy = 20 B per state
     const size_t per_warp = (size_t)nmax * 20;
     if (per_warp + 1024 > 200 * 1024) { ctx->last_error = "grid: max batch size above 10188"; return WVA_ERR_LIMIT; }
+    // ---- deferral of the near-saturation levels (grid_kernel.cuh): large systems only
+    GridDefer df = {};
+    unsigned long long* d_next = nullptr;
+    unsigned long long* items_alt = nullptr; unsigned char* cls_alt = nullptr; void* d_sort_tmp = nullptr; size_t sort_tmp = 0;
+    const int row_stride = (nmax + 31) & ~31;
+    {
+      const size_t rows_bytes = P * (size_t)row_stride * 4;
+      const bool want = ctx->grid_defer == 2 || (ctx->grid_defer == 0 && P >= 20000);
+      if (want && R <= 65535 && P < 0x7fffffffull && rows_bytes <= ((size_t)16 << 30)) {
+        const unsigned long long cap = (unsigned long long)std::min((size_t)P * (size_t)R, (size_t)P * 16 + 1024);
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (unsigned char*)nullptr, (unsigned char*)nullptr, (unsigned long long*)nullptr,
+                                        (unsigned long long*)nullptr, (int)std::min<unsigned long long>(cap, 0x7fffffffull), 0, 8, ctx->stream);
+        Layout D;
+        const size_t o_cnt = D.take(256), o_rows = D.take(rows_bytes), o_side = D.take(P * sizeof(GridSide)), o_it = D.take(cap * 8),
+                     o_it2 = D.take(cap * 8), o_cl = D.take(cap), o_cl2 = D.take(cap), o_tmp = D.take(sort_tmp + 256);
+        if (cap < 0x7fffffffull && g.defer.reserve(D.off + 256) == cudaSuccess) {
+          char* dd = (char*)g.defer.p;
+          CK(cudaMemsetAsync(dd + o_cnt, 0, 256, ctx->stream));
+          df.n_items = (unsigned long long*)(dd + o_cnt); d_next = df.n_items + 1;
+          df.rows = (float*)(dd + o_rows); df.side = (GridSide*)(dd + o_side);
+          df.items = (unsigned long long*)(dd + o_it); items_alt = (unsigned long long*)(dd + o_it2);
+          df.cls = (unsigned char*)(dd + o_cl); cls_alt = (unsigned char*)(dd + o_cl2); d_sort_tmp = dd + o_tmp;
+          df.cap = cap; df.row_stride = row_stride; df.thr = 0.6f;
+        }
+      }
+    }
     cudaError_t e;
     if (per_warp * 8 <= 64 * 1024) {
       int per_sm = (int)((200 * 1024) / (per_warp * 8 + 1024)); if (per_sm > 6) per_sm = 6; if (per_sm < 1) per_sm = 1;
-      e = launch_grid<8>(ctx, ctx->sm_count * per_sm, per_warp * 8, R, g.view, P, nmax, g.ctr);
+      e = launch_grid<8>(ctx, ctx->sm_count * per_sm, per_warp * 8, R, g.view, P, nmax, g.ctr, df);
     } else if (per_warp * 4 + 1024 <= 200 * 1024) {
       int per_sm = (int)((200 * 1024) / (per_warp * 4 + 1024)); if (per_sm > 8) per_sm = 8; if (per_sm < 1) per_sm = 1;
-      e = launch_grid<4>(ctx, ctx->sm_count * per_sm, per_warp * 4, R, g.view, P, nmax, g.ctr);
+      e = launch_grid<4>(ctx, ctx->sm_count * per_sm, per_warp * 4, R, g.view, P, nmax, g.ctr, df);
     } else {
-      e = launch_grid<1>(ctx, ctx->sm_count * 4, per_warp, R, g.view, P, nmax, g.ctr);
+      e = launch_grid<1>(ctx, ctx->sm_count * 4, per_warp, R, g.view, P, nmax, g.ctr, df);
     }
     if (e != cudaSuccess) { ctx->last_error = std::string("grid launch: ") + cudaGetErrorString(e); return WVA_ERR_CUDA; }
+    if (df.rows) {
+      unsigned long long n_items = 0;
+      CK(cudaMemcpyAsync(&n_items, df.n_items, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (n_items > df.cap) n_items = df.cap;          // reservations past the capacity were solved in place
+      if (n_items > 0) {
+        size_t tb = sort_tmp;
+        CK(cub::DeviceRadixSort::SortPairsDescending(d_sort_tmp, tb, df.cls, cls_alt, df.items, items_alt, (int)n_items, 0, 8, ctx->stream));
+        CK(cudaFuncSetAttribute(grid_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 32 * 33 * 4));
+        grid_deferred_kernel<<<ctx->sm_count * 2, 256, 8 * 2 * 32 * 33 * 4, ctx->stream>>>(R, g.view, df, items_alt, n_items, g.ctr, d_next);
+        ctx->launches += 2;
+      }
+      grid_frontier_fix_kernel<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(g.view.frontier, (unsigned long long)P);
+      ctx->launches++;
+      CK(cudaGetLastError());
+    }
   }
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   GridCounters hc;
@@ -81,8 +123,8 @@ extern "C" int32_t wva_grid_run(wva_ctx* ctx, int32_t R, int32_t full) {
   ctx->timing.chain_states = (int64_t)hc.states;
   ctx->timing.overflow_pairs = (int64_t)hc.overflow;
   if (getenv("WVA_SIZER_DEBUG"))
-    fprintf(stderr, "grid: live %llu, lock-step slots first round %llu, later rounds %llu, rounds %llu\n", hc.states, hc.slots0,
-            hc.slots_rest, hc.rounds);
+    fprintf(stderr, "grid: live %llu, lock-step slots first round %llu, later rounds %llu, deferred pass %llu, rounds %llu\n",
+            hc.states, hc.slots0, hc.slots_rest, hc.slots_def, hc.rounds);
   if (hc.limit_hit) { ctx->last_error = "grid: a pair needs a larger max batch size than the launch was built for"; return WVA_ERR_LIMIT; }
   g.ran = true;
   return WVA_OK;

@@ -25,7 +25,38 @@ struct GridCounters {
   unsigned long long next_pair, solves, states, overflow;
   int limit_hit, pad_;
   unsigned long long slots0, slots_rest, rounds;   // 32 x longest chain of the round: first round of a pair / later rounds
+  unsigned long long slots_def;                   // the same for the deferred pass
 };
+
+// Deferral of the near-saturation levels (large systems).  A pair's chain length is a steep function of lambda / mu_N
+// (early exit E4): the one or two lowest admitted levels of a pair run thousands of states next to ~50 for the rest, so a
+// warp that takes 32 consecutive levels spends its first round waiting for one lane.  With deferral the pair's warp skips
+// the levels whose ratio exceeds `thr`, saves the pair's head table (one row) and model, and appends (pair, r, class)
+// to a global list; the list is radix-sorted by length class and grid_deferred_kernel solves it 32 items — of 32
+// different pairs, similar lengths — at a time through TileTable.  Same per-level arithmetic, same outputs.
+struct GridSide {            // what an evaluation needs of its pair
+  PairModel m;
+  float total_rate, slo_ttft, slo_itl, slo_tps, lambda_tps;
+  int pad_[3];
+};
+struct GridDefer {
+  float* rows;               // [n_pairs][row_stride] head tables, nullptr = no deferral
+  GridSide* side;            // [n_pairs]
+  unsigned long long* items; // (pair << 16) | r
+  unsigned char* cls;        // length class of the item (sort key)
+  unsigned long long* n_items;
+  unsigned long long cap;
+  int row_stride;
+  float thr;
+};
+__device__ __forceinline__ int grid_class(const PairModel& m, float ratio) {
+  if (!(ratio > 1e-6f)) ratio = 1e-6f;
+  if (ratio > 0.999999f) ratio = 0.999999f;
+  float est = (float)m.N + 37.4f / -__logf(ratio);
+  if (est > (float)m.K) est = (float)m.K;
+  const int c = (int)(__log2f(fmaxf(est, 32.0f) * (1.0f / 32.0f)) * 8.0f);
+  return c < 0 ? 0 : (c > 255 ? 255 : c);
+}
 
 // per-pair preparation shared by all lanes of the warp; false -> every level is "not ok"
 __device__ __forceinline__ bool grid_setup(PairModel& m, const SysView& s, int srv, int acc, int n_limit,
@@ -49,7 +80,7 @@ __device__ __forceinline__ bool grid_setup(PairModel& m, const SysView& s, int s
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax, GridCounters* ctr) {
+grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax, GridCounters* ctr, GridDefer df) {
   extern __shared__ double2 smem_grid[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -91,6 +122,9 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
     model_finish(m, tabf, 1);
     const float lambda_tps = f_mul(m.lambda_max, f_sub(1.0f, WVA_STABILITY_SAFETY));
     int front = 0x7fffffff;
+    const bool deferring = df.rows != nullptr && pair < 0xffffffffull;
+    bool saved = false;                                   // the pair's row and model are written when its first level is deferred
+    const float mu_last_f = (float)m.mu_last;
     bool first_round = true;
 
     for (int r0 = 0; r0 < R; r0 += 32) {
@@ -110,18 +144,49 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
         continue;
       }
       const float lambda = f_div(rate, 1000.0f);
+      bool defer = false;
+      if (deferring) {
+        const float ratio = lambda / mu_last_f;
+        const bool want = admitted && ratio > df.thr;
+        const unsigned wm = __ballot_sync(full, want);
+        if (wm) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(df.n_items, (unsigned long long)__popc(wm));
+          base = __shfl_sync(full, base, 0);
+          if (base + __popc(wm) <= df.cap) {              // room in the list: these levels leave the warp
+            defer = want;
+            if (want) {
+              const unsigned long long k = base + __popc(wm & ((1u << lane) - 1u));
+              df.items[k] = (pair << 16) | (unsigned long long)r;
+              df.cls[k] = (unsigned char)grid_class(m, ratio);
+            }
+            if (!saved) {
+              saved = true;
+              float* row = df.rows + (size_t)pair * df.row_stride;
+              for (int n = lane; n < m.N; n += 32) row[n] = tabf[n];
+              if (lane == 0) {
+                GridSide sd;
+                sd.m = m; sd.m.tab = row; sd.m.stride = 1;
+                sd.total_rate = total_rate; sd.slo_ttft = slo_ttft; sd.slo_itl = slo_itl; sd.slo_tps = slo_tps; sd.lambda_tps = lambda_tps;
+                df.side[pair] = sd;
+              }
+            }
+          }
+        }
+      }
+      const bool solve_here = admitted && !defer;
       SolveStats st;
       int sv = 0;
       bool bad = false, ovf = false;
-      lockstep_solve(m, WarpTable{tab}, lambda, admitted, st, sv, bad);
-      if (admitted) { my_solves++; my_states += (unsigned long long)sv; }
+      if (__any_sync(full, solve_here)) lockstep_solve(m, WarpTable{tab}, lambda, solve_here, st, sv, bad);
+      if (solve_here) { my_solves++; my_states += (unsigned long long)sv; }
       {
-        int mxs = admitted ? sv : 0;
+        int mxs = solve_here ? sv : 0;
         for (int o = 16; o; o >>= 1) mxs = max(mxs, __shfl_xor_sync(full, mxs, o));
         if (lane == 0) { if (first_round) my_s0 += 32ull * mxs; else my_sr += 32ull * mxs; my_rounds++; }
         first_round = false;
       }
-      if (admitted && bad) {
+      if (solve_here && bad) {
         // outside the exponent window: redo this level alone through the per-lane state machine
         // (IEEE divisions); a true float64 overflow stays flagged (only the sizer has the rescale path)
         Chain c;
@@ -131,7 +196,7 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
         ovf = c.phase == CH_OVERFLOW;
         if (ovf) atomicAdd(&ctr->overflow, 1ull);
       }
-      if (in_range) {
+      if (in_range && !defer) {
         const size_t o = obase + (size_t)(r - 1);
         if (!admitted || ovf) {
           if (out.ok) out.ok[o] = 0;
@@ -157,7 +222,8 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
       }
     }
     for (int o = 16; o; o >>= 1) front = min(front, __shfl_down_sync(full, front, o));
-    if (out.frontier && lane == 0) out.frontier[pair] = (front == 0x7fffffff) ? 0 : front;
+    // with deferral the deferred pass still lowers the frontier (atomicMin); grid_frontier_fix maps "none" to 0
+    if (out.frontier && lane == 0) out.frontier[pair] = deferring ? front : ((front == 0x7fffffff) ? 0 : front);
     __syncwarp();
   }
   for (int o = 16; o; o >>= 1) {
@@ -168,6 +234,98 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
     atomicAdd(&ctr->solves, my_solves); atomicAdd(&ctr->states, my_states);
     atomicAdd(&ctr->slots0, my_s0); atomicAdd(&ctr->slots_rest, my_sr); atomicAdd(&ctr->rounds, my_rounds);
   }
+}
+
+// The deferred levels, sorted by length class: lane per (pair, level), 32 different pairs per warp.
+__global__ void __launch_bounds__(256, 2)
+grid_deferred_kernel(int R, GridOut out, GridDefer df, const unsigned long long* __restrict__ items, unsigned long long n_items,
+                     GridCounters* ctr, unsigned long long* next_item) {
+  extern __shared__ __align__(16) float grid_tiles[];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tile = grid_tiles + (size_t)warp * (2 * 32 * 33);
+  unsigned long long my_solves = 0, my_states = 0, my_slots = 0, my_rounds = 0;
+  while (true) {
+    unsigned long long i0 = 0;
+    if (lane == 0) i0 = atomicAdd(next_item, 32ull);
+    i0 = __shfl_sync(full, i0, 0);
+    if (i0 >= n_items) break;
+    const bool live = i0 + lane < n_items;
+    unsigned long long it = live ? items[i0 + lane] : items[i0];
+    const unsigned long long pair = it >> 16;
+    const int r = (int)(it & 0xffffu);
+    const GridSide* sp = df.side + pair;
+    PairModel m = sp->m;
+    const float total_rate = sp->total_rate, slo_ttft = sp->slo_ttft, slo_itl = sp->slo_itl, slo_tps = sp->slo_tps,
+                lambda_tps = sp->lambda_tps;
+    const float rate = f_div(total_rate, (float)r);
+    const float lambda = f_div(rate, 1000.0f);
+    const int nref = __shfl_sync(full, m.N, 0);
+    const bool uniform = __all_sync(full, m.N == nref);
+    SolveStats st;
+    int sv = 0;
+    bool bad = false, ovf = false;
+    if (uniform) {
+      TileTable tt; tt.rows = df.rows; tt.row_stride = df.row_stride; tt.slot = (int)pair; tt.tile = tile; tt.n_head = nref - 1;
+      lockstep_solve(m, tt, lambda, live, st, sv, bad);
+    } else if (live) {
+      Chain c;
+      chain_start(c, lambda);
+      c.tail_ok = d_bits(c.lamg) <= d_bits(m.mu_last);
+      while (!chain_step(c, m, st)) {}
+      bad = false; ovf = c.phase == CH_OVERFLOW; sv = c.states;
+    }
+    if (live && bad) {
+      Chain c;
+      chain_start(c, lambda);
+      c.tail_ok = d_bits(c.lamg) <= d_bits(m.mu_last);
+      while (!chain_step(c, m, st)) {}
+      ovf = c.phase == CH_OVERFLOW;
+    }
+    if (live) {
+      my_solves++; my_states += (unsigned long long)sv;
+      if (ovf) atomicAdd(&ctr->overflow, 1ull);
+      const size_t o = (size_t)pair * (size_t)R + (size_t)(r - 1);
+      if (ovf) {
+        if (out.ok) out.ok[o] = 0;
+        if (out.ttft) out.ttft[o] = 0.0f;
+        if (out.itl) out.itl[o] = 0.0f;
+        if (out.rho) out.rho[o] = 0.0f;
+        if (out.tput) out.tput[o] = 0.0f;
+      } else {
+        float pf, dec, avg_ttft;
+        eval_values(m, st, &avg_ttft, &dec, &pf);
+        float rho = f_div(st.avgNumInServers, (float)m.N);
+        rho = fminf(fmaxf(rho, 0.0f), 1.0f);
+        if (out.ok) out.ok[o] = 1;
+        if (out.ttft) out.ttft[o] = f_add(st.avgWaitTime, pf);
+        if (out.itl) out.itl[o] = dec;
+        if (out.rho) out.rho[o] = rho;
+        if (out.tput) out.tput[o] = f_mul(st.throughput, 1000.0f);
+        const bool meets = (slo_ttft <= 0.0f || avg_ttft <= slo_ttft) && (slo_itl <= 0.0f || dec <= slo_itl) &&
+                           (slo_tps <= 0.0f || lambda <= lambda_tps);
+        if (meets && out.frontier) atomicMin(&out.frontier[pair], r);
+      }
+    }
+    {
+      int mxs = live ? sv : 0;
+      for (int o = 16; o; o >>= 1) mxs = max(mxs, __shfl_xor_sync(full, mxs, o));
+      if (lane == 0) { my_slots += 32ull * mxs; my_rounds++; }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    my_solves += __shfl_down_sync(full, my_solves, o);
+    my_states += __shfl_down_sync(full, my_states, o);
+  }
+  if (lane == 0) {
+    atomicAdd(&ctr->solves, my_solves); atomicAdd(&ctr->states, my_states);
+    atomicAdd(&ctr->slots_def, my_slots); atomicAdd(&ctr->rounds, my_rounds);
+  }
+}
+
+__global__ void __launch_bounds__(256) grid_frontier_fix_kernel(int* frontier, unsigned long long n) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && frontier[i] == 0x7fffffff) frontier[i] = 0;
 }
 
 }  // namespace wva

@@ -443,6 +443,29 @@ def test_grid_matches_oracle(pkg, engine, oracle, S, A, N, R, stream):
     assert np.array_equal(engine.grid_fetch_frontier(), o["frontier"])
 
 
+@pytest.mark.parametrize("N,R", [(32, 64), (256, 256)])
+def test_grid_deferred_levels_match_oracle(pkg, engine, oracle, N, R):
+    """WVA_OPT_GRID_DEFER = 2: the near-saturation levels of every pair leave the pair's warp and are solved in a pass
+    sorted by chain length (grid_deferred_kernel, TileTable over per-pair rows); every output and the frontier stay
+    bit-identical to the oracle's grid — and to the undeferred kernel's."""
+    sysd = pkg.synth.queue_system(40, 8, N, stream=21, R=R)
+    sysd["srv_max_batch"][::5] = max(1, N // 2)        # two batch sizes: mixed N in the deferred pass
+    engine.load_system(sysd)
+    o = oracle.analyze_grid(sysd, R)
+    for mode in (2, 1):
+        engine.set_option(6, mode)
+        try:
+            g = engine.analyze_grid(R)
+            engine.grid_run(R, full=False)
+            fr = engine.grid_fetch_frontier()
+        finally:
+            engine.set_option(6, 0)
+        assert np.array_equal(g["ok"], o["ok"]) and np.array_equal(g["frontier"], o["frontier"]), mode
+        assert np.array_equal(fr, o["frontier"]), mode
+        for k in ("ttft", "itl", "rho", "tput"):
+            assert _bit_equal(g[k], o[k]), (k, mode)
+
+
 def test_grid_monotone_in_replicas(pkg, engine):
     """Size-independent property at BASELINE config 2 shape: more replicas never raise ITL/TTFT/rho."""
     sysd = pkg.synth.baseline_config(2, scale=0.05)

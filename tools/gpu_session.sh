@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-WVA_SIZER_DEBUG=1 timeout 300 python tools/perf_grid.py 0.1 > gpurun_out/s10_grid.json 2> gpurun_out/s10_grid.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/s10_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/s10_bench_under_ncu.log 2>&1
-cat gpurun_out/s10_grid.json; cat gpurun_out/s10_grid.err | tail -8; wc -l gpurun_out/s10_launches.csv
+timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider -k "grid or greedy or config2" > gpurun_out/s11_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s11_pytest.log
+WVA_SIZER_DEBUG=1 timeout 300 python tools/perf_grid.py 1.0 > gpurun_out/s11_grid.json 2> gpurun_out/s11_grid.err
+WVA_SIZER_DEBUG=1 timeout 300 python tools/perf_greedy.py > gpurun_out/s11_greedy.json 2> gpurun_out/s11_greedy.err
+tail -3 gpurun_out/s11_pytest.log; cat gpurun_out/s11_grid.json; tail -4 gpurun_out/s11_grid.err; head -c 600 gpurun_out/s11_greedy.json; grep "greedy sweep" gpurun_out/s11_greedy.err | head -4

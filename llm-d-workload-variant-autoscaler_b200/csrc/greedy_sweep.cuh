@@ -463,8 +463,13 @@ static inline int32_t run_solve_greedy_sweep(const SysView& s, const CandView& c
   greedy_finalize_kernel<<<(unsigned)((S + 255) / 256), 256, 0, stream>>>(s, c, o, w);
   *launches += 2;
   if (stats_out) {
-    if (cudaMemcpyAsync(stats_out, w.stats, 16, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
+    long long h[8];
+    if (cudaMemcpyAsync(h, w.stats, 64, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
     if (cudaStreamSynchronize(stream) != cudaSuccess) return WVA_ERR_CUDA;
+    stats_out[0] = h[0]; stats_out[1] = h[1];
+    if (getenv("WVA_SIZER_DEBUG"))
+      fprintf(stderr, "greedy sweep: alive events %lld, batches %lld, rounds %lld, sequential events %lld, tie-group calls %lld, stopped at %lld of %lld\n",
+              h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
   }
   return cudaGetLastError() == cudaSuccess ? WVA_OK : WVA_ERR_CUDA;
 }

@@ -79,7 +79,7 @@ __device__ __forceinline__ bool grid_setup(PairModel& m, const SysView& s, int s
 }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1)
 grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax, GridCounters* ctr, GridDefer df) {
   extern __shared__ double2 smem_grid[];
   const unsigned full = 0xffffffffu;
@@ -127,97 +127,117 @@ grid_kernel(SysView s, int R, GridOut out, unsigned long long n_pairs, int nmax,
     const float mu_last_f = (float)m.mu_last;
     bool first_round = true;
 
-    for (int r0 = 0; r0 < R; r0 += 32) {
-      const int r = r0 + lane + 1;
-      const bool in_range = r <= R;
-      const float rate = f_div(total_rate, (float)r);
-      const bool admitted = in_range && analyze_admits(m, rate);      // queueanalyzer.go:128-136
-      if (!__any_sync(full, admitted)) {
-        if (in_range) {
-          const size_t o = obase + (size_t)(r - 1);
-          if (out.ok) out.ok[o] = 0;
-          if (out.ttft) out.ttft[o] = 0.0f;
-          if (out.itl) out.itl[o] = 0.0f;
-          if (out.rho) out.rho[o] = 0.0f;
-          if (out.tput) out.tput[o] = 0.0f;
-        }
+    // Two levels per lane and round (r0 + lane + 1 and r0 + 32 + lane + 1): the two chains of a lane share every table
+    // load and give the FP64 pipe two independent dependency chains; half as many rounds (the chains of a round are ~20
+    // states long on average, so the per-round work is a large part of the cost).
+    for (int r0 = 0; r0 < R; r0 += 64) {
+      int r[2]; bool in_range[2], admitted[2], defer[2], here[2], ovf[2];
+      float rate[2], lambda[2];
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        r[c] = r0 + 32 * c + lane + 1;
+        in_range[c] = r[c] <= R;
+        rate[c] = f_div(total_rate, (float)r[c]);
+        admitted[c] = in_range[c] && analyze_admits(m, rate[c]);      // queueanalyzer.go:128-136
+        lambda[c] = f_div(rate[c], 1000.0f);
+        defer[c] = false; ovf[c] = false;
+      }
+      if (!__any_sync(full, admitted[0] || admitted[1])) {
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+          if (in_range[c]) {
+            const size_t o = obase + (size_t)(r[c] - 1);
+            if (out.ok) out.ok[o] = 0;
+            if (out.ttft) out.ttft[o] = 0.0f;
+            if (out.itl) out.itl[o] = 0.0f;
+            if (out.rho) out.rho[o] = 0.0f;
+            if (out.tput) out.tput[o] = 0.0f;
+          }
         continue;
       }
-      const float lambda = f_div(rate, 1000.0f);
-      bool defer = false;
       if (deferring) {
-        const float ratio = lambda / mu_last_f;
-        const bool want = admitted && ratio > df.thr;
-        const unsigned wm = __ballot_sync(full, want);
-        if (wm) {
-          unsigned long long base = 0;
-          if (lane == 0) base = atomicAdd(df.n_items, (unsigned long long)__popc(wm));
-          base = __shfl_sync(full, base, 0);
-          if (base + __popc(wm) <= df.cap) {              // room in the list: these levels leave the warp
-            defer = want;
-            if (want) {
-              const unsigned long long k = base + __popc(wm & ((1u << lane) - 1u));
-              df.items[k] = (pair << 16) | (unsigned long long)r;
-              df.cls[k] = (unsigned char)grid_class(m, ratio);
-            }
-            if (!saved) {
-              saved = true;
-              float* row = df.rows + (size_t)pair * df.row_stride;
-              for (int n = lane; n < m.N; n += 32) row[n] = tabf[n];
-              if (lane == 0) {
-                GridSide sd;
-                sd.m = m; sd.m.tab = row; sd.m.stride = 1;
-                sd.total_rate = total_rate; sd.slo_ttft = slo_ttft; sd.slo_itl = slo_itl; sd.slo_tps = slo_tps; sd.lambda_tps = lambda_tps;
-                df.side[pair] = sd;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const float ratio = lambda[c] / mu_last_f;
+          const bool want = admitted[c] && ratio > df.thr;
+          const unsigned wm = __ballot_sync(full, want);
+          if (wm) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(df.n_items, (unsigned long long)__popc(wm));
+            base = __shfl_sync(full, base, 0);
+            if (base + __popc(wm) <= df.cap) {              // room in the list: these levels leave the warp
+              defer[c] = want;
+              if (want) {
+                const unsigned long long k = base + __popc(wm & ((1u << lane) - 1u));
+                df.items[k] = (pair << 16) | (unsigned long long)r[c];
+                df.cls[k] = (unsigned char)grid_class(m, ratio);
+              }
+              if (!saved) {
+                saved = true;
+                float* row = df.rows + (size_t)pair * df.row_stride;
+                for (int n = lane; n < m.N; n += 32) row[n] = tabf[n];
+                if (lane == 0) {
+                  GridSide sd;
+                  sd.m = m; sd.m.tab = row; sd.m.stride = 1;
+                  sd.total_rate = total_rate; sd.slo_ttft = slo_ttft; sd.slo_itl = slo_itl; sd.slo_tps = slo_tps; sd.lambda_tps = lambda_tps;
+                  df.side[pair] = sd;
+                }
               }
             }
           }
         }
       }
-      const bool solve_here = admitted && !defer;
-      SolveStats st;
+      here[0] = admitted[0] && !defer[0]; here[1] = admitted[1] && !defer[1];
+      SolveStats st[2];
       int sv = 0;
-      bool bad = false, ovf = false;
-      if (__any_sync(full, solve_here)) lockstep_solve(m, WarpTable{tab}, lambda, solve_here, st, sv, bad);
-      if (solve_here) { my_solves++; my_states += (unsigned long long)sv; }
+      bool bad = false;
+      if (__any_sync(full, here[0] || here[1])) lockstep_solve_inl<2, WarpTable>(m, WarpTable{tab}, lambda, here, st, sv, bad);
+      if (here[0] || here[1]) { my_solves += (here[0] ? 1 : 0) + (here[1] ? 1 : 0); my_states += (unsigned long long)sv; }
       {
-        int mxs = solve_here ? sv : 0;
+        int mxs = (here[0] || here[1]) ? sv : 0;
         for (int o = 16; o; o >>= 1) mxs = max(mxs, __shfl_xor_sync(full, mxs, o));
         if (lane == 0) { if (first_round) my_s0 += 32ull * mxs; else my_sr += 32ull * mxs; my_rounds++; }
         first_round = false;
       }
-      if (solve_here && bad) {
-        // outside the exponent window: redo this level alone through the per-lane state machine
+      if (bad) {
+        // a chain of this lane left the exponent window: redo its levels one by one through the per-lane state machine
         // (IEEE divisions); a true float64 overflow stays flagged (only the sizer has the rescale path)
-        Chain c;
-        chain_start(c, lambda);
-        c.tail_ok = d_bits(c.lamg) <= d_bits(m.mu_last);
-        while (!chain_step(c, m, st)) {}
-        ovf = c.phase == CH_OVERFLOW;
-        if (ovf) atomicAdd(&ctr->overflow, 1ull);
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+          if (here[c]) {
+            Chain ch;
+            chain_start(ch, lambda[c]);
+            ch.tail_ok = d_bits(ch.lamg) <= d_bits(m.mu_last);
+            while (!chain_step(ch, m, st[c])) {}
+            ovf[c] = ch.phase == CH_OVERFLOW;
+            if (ovf[c]) atomicAdd(&ctr->overflow, 1ull);
+          }
       }
-      if (in_range && !defer) {
-        const size_t o = obase + (size_t)(r - 1);
-        if (!admitted || ovf) {
-          if (out.ok) out.ok[o] = 0;
-          if (out.ttft) out.ttft[o] = 0.0f;
-          if (out.itl) out.itl[o] = 0.0f;
-          if (out.rho) out.rho[o] = 0.0f;
-          if (out.tput) out.tput[o] = 0.0f;
-        } else {
-          // Analyze: queueanalyzer.go:143-166
-          float pf, dec, avg_ttft;
-          eval_values(m, st, &avg_ttft, &dec, &pf);
-          float rho = f_div(st.avgNumInServers, (float)m.N);
-          rho = fminf(fmaxf(rho, 0.0f), 1.0f);
-          if (out.ok) out.ok[o] = 1;
-          if (out.ttft) out.ttft[o] = f_add(st.avgWaitTime, pf);   // allocation.go:148
-          if (out.itl) out.itl[o] = dec;
-          if (out.rho) out.rho[o] = rho;
-          if (out.tput) out.tput[o] = f_mul(st.throughput, 1000.0f);
-          bool meets = (slo_ttft <= 0.0f || avg_ttft <= slo_ttft) && (slo_itl <= 0.0f || dec <= slo_itl) &&
-                       (slo_tps <= 0.0f || lambda <= lambda_tps);
-          if (meets && r < front) front = r;
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        if (in_range[c] && !defer[c]) {
+          const size_t o = obase + (size_t)(r[c] - 1);
+          if (!admitted[c] || ovf[c]) {
+            if (out.ok) out.ok[o] = 0;
+            if (out.ttft) out.ttft[o] = 0.0f;
+            if (out.itl) out.itl[o] = 0.0f;
+            if (out.rho) out.rho[o] = 0.0f;
+            if (out.tput) out.tput[o] = 0.0f;
+          } else {
+            // Analyze: queueanalyzer.go:143-166
+            float pf, dec, avg_ttft;
+            eval_values(m, st[c], &avg_ttft, &dec, &pf);
+            float rho = f_div(st[c].avgNumInServers, (float)m.N);
+            rho = fminf(fmaxf(rho, 0.0f), 1.0f);
+            if (out.ok) out.ok[o] = 1;
+            if (out.ttft) out.ttft[o] = f_add(st[c].avgWaitTime, pf);   // allocation.go:148
+            if (out.itl) out.itl[o] = dec;
+            if (out.rho) out.rho[o] = rho;
+            if (out.tput) out.tput[o] = f_mul(st[c].throughput, 1000.0f);
+            const bool meets = (slo_ttft <= 0.0f || avg_ttft <= slo_ttft) && (slo_itl <= 0.0f || dec <= slo_itl) &&
+                               (slo_tps <= 0.0f || lambda[c] <= lambda_tps);
+            if (meets && r[c] < front) front = r[c];
+          }
         }
       }
     }

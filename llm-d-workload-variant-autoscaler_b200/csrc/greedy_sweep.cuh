@@ -103,15 +103,21 @@ __global__ void __launch_bounds__(256) gsw_gather_kernel(SysView s, GreedyWs w, 
   if (ty >= 0) atomicMin(&g.blk_min[(size_t)(i / GSW_BLOCK) * s.n_types + ty], (unsigned long long)e.cnt);
 }
 
-// suffix minima over the blocks (one thread per type)
-__global__ void __launch_bounds__(64) gsw_sufmin_kernel(GSweepWs g, int n_blocks, int n_types) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// suffix minima over the blocks: one warp per type, 32 blocks per step (warp suffix scan + carry)
+__global__ void __launch_bounds__(32) gsw_sufmin_kernel(GSweepWs g, int n_blocks, int n_types) {
+  const int t = blockIdx.x, lane = threadIdx.x;
   if (t >= n_types) return;
-  unsigned long long m = ~0ull;
-  for (int b = n_blocks - 1; b >= 0; b--) {
-    const unsigned long long v = g.blk_min[(size_t)b * n_types + t];
-    m = v < m ? v : m;
-    g.blk_min[(size_t)b * n_types + t] = m;
+  unsigned long long carry = ~0ull;
+  for (int hi = n_blocks; hi > 0; hi -= 32) {
+    const int b = hi - 1 - lane;                         // lane 0 holds the LAST block of the step
+    unsigned long long v = b >= 0 ? g.blk_min[(size_t)b * n_types + t] : ~0ull;
+    for (int o = 1; o < 32; o <<= 1) {                   // inclusive scan towards higher lanes = towards lower blocks
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o && u < v) v = u;
+    }
+    if (carry < v) v = carry;
+    if (b >= 0) g.blk_min[(size_t)b * n_types + t] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
   }
 }
 
@@ -267,6 +273,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
   __syncwarp();
   GSweepState z = {0, 0, 0};
   int group_un0 = 0;
+  long long n_batches = 0, n_rounds = 0, n_seq = 0, n_tie = 0;
 
   // event stream: blocks of GSW_BLOCK records copied asynchronously into a ring of GSW_SLOTS slots; while block b is
   // read, blocks b+1 .. b+GSW_SLOTS-1 are in flight.  One commit group per block (empty past the end of the list).
@@ -308,6 +315,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
       __syncwarp();
       cur_block = b;
     }
+    n_batches++;
     const GEvent* blk = ring + (size_t)(b % GSW_SLOTS) * GSW_BLOCK;
     const int in_blk = rel % GSW_BLOCK;
     const int nvalid = min(min(32, GSW_BLOCK - in_blk), n_ev - pos);
@@ -318,9 +326,64 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
     const int type = ge_type(me.meta);
     const unsigned peers = __match_any_sync(full, me.srv);
     unsigned npm = delayed ? 0u : __ballot_sync(full, valid && (fl & GE_NEWPRIO));
+    // ---- fast path: no alive leader of a multi-leader tie group and no priority boundary in the batch.
+    // Only a lane that fits (or has no accelerator) under the capacities at the START of the batch can take (or be
+    // dropped): capacities only shrink.  Those candidates are visited in lane order with the whole state in registers —
+    // every lane keeps the capacity left for ITS type and its alive flag, a take is two shuffles and two predicated
+    // updates — and everything else alive is a failure, processed once for the whole batch.  Exactly the sequential
+    // semantics: lane L sees the takes of the lanes before it and nothing else.
+    {
+      bool al = valid && gsw_alive(alive, me.srv);
+      long long myavail = (al && type >= 0) ? avail[type] : 0;
+      const unsigned multi_alive = __ballot_sync(full, al && (fl & GE_MULTI));
+      if (!multi_alive && !npm) {
+        unsigned cand = __ballot_sync(full, al && (type < 0 || myavail >= me.cnt));
+        unsigned took = 0;
+        while (cand) {
+          const int F = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const unsigned okm = __ballot_sync(full, lane == F && al && (type < 0 || myavail >= me.cnt));
+          if (!okm) continue;                        // killed by an earlier lane of its entry, or no longer fits: it fails
+          const int tF = __shfl_sync(full, type, F);
+          const long long cF = __shfl_sync(full, me.cnt, F);
+          if (tF >= 0 && type == tF) myavail -= cF;
+          if (lane > F && ((peers >> F) & 1u)) al = false;   // later events of the same entry are dead
+          took |= 1u << F;
+          n_seq++;
+        }
+        const bool taker = (took >> lane) & 1u;
+        if (taker) {                                 // greedy.go:143-145 (or dropped, :126-136): every taker writes its own decision
+          if (type >= 0) {
+            w.kind[me.srv] = 1; w.sel_rank[me.srv] = ge_rank(me.meta);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&avail[type]), (unsigned long long)(-me.cnt));
+          }
+          atomicAnd(&alive[me.srv >> 5], ~(1u << (me.srv & 31)));
+        }
+        const bool failing = al && !taker;
+        const unsigned fm = __ballot_sync(full, failing);
+        if (fm) {
+          const int rank = __popc(fm & lt);
+          if (failing && (fm & peers & ~lt & ~(1u << lane)) == 0) g.stamp[me.srv] = z.clock + rank + 1;   // the entry's latest failure
+          const bool lastc = failing && (fl & GE_LAST);                                                     // :152-156
+          const unsigned lm = __ballot_sync(full, lastc);
+          if (lastc) {
+            w.unalloc[z.n_un + __popc(lm & lt)] = me.srv;
+            atomicAnd(&alive[me.srv >> 5], ~(1u << (me.srv & 31)));
+          }
+          z.n_un += __popc(lm);
+          z.clock += __popc(fm);
+        }
+        z.n_active += __popc(fm) + __popc(took);
+        n_rounds++;
+        __syncwarp();
+        pos += nvalid;
+        continue;
+      }
+    }
     int cur = 0;                                   // lanes below `cur` are done
     int jump = -1;
     while (cur < nvalid) {
+      n_rounds++;
       // Outcome of every remaining lane under the CURRENT capacities and alive bits.  Up to the first lane that takes,
       // is dropped, leads a multi-leader tie group or starts a priority group, every alive lane simply fails — and a
       // failure changes neither the capacities nor (unless it is the entry's last candidate) the alive bits, so all
@@ -374,10 +437,12 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
         const unsigned span = run >= 31 ? 0xffffffffu : (((1u << run) - 1u) << (first + 1));
         const unsigned others = __ballot_sync(full, al && (fl & GE_LEADER)) & span;
         if (!ends_here || others) {
+          n_tie++;
           const int np = gsw_tie_group(w, g, avail, alive, z, pos + first, n_ev);
           if (np >= 0) { jump = np; break; }
         }
       }
+      n_seq++;
       gsw_process(w, g, avail, alive, z, e_srv, e_meta, e_cnt);
       cur = first + 1;
     }
@@ -395,7 +460,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
   __syncwarp();
   // the last group's (or, delayed, the whole list's) best effort
   if (z.n_un > group_un0) g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy);
-  if (lane == 0) { w.stats[0] = 0; w.stats[1] = z.n_active; }
+  if (lane == 0) { w.stats[0] = 0; w.stats[1] = z.n_active; w.stats[2] = n_batches; w.stats[3] = n_rounds; w.stats[4] = n_seq; w.stats[5] = n_tie; w.stats[6] = pos; w.stats[7] = n_ev; }
 }
 
 // host driver of the static-order sweep.  Returns WVA_ERR_LIMIT (nothing launched) when the system is outside what this
@@ -456,7 +521,7 @@ static inline int32_t run_solve_greedy_sweep(const SysView& s, const CandView& c
     if (cudaMemsetAsync(g.blk_min, 0xff, (size_t)n_blocks * (size_t)(s.n_types > 0 ? s.n_types : 1) * 8, stream) != cudaSuccess) return WVA_ERR_CUDA;
     gsw_gather_kernel<<<cb, 256, 0, stream>>>(s, w, g, cur, n);
     gsw_multi_kernel<<<cb, 256, 0, stream>>>(g, n);
-    if (s.n_types > 0) gsw_sufmin_kernel<<<(s.n_types + 63) / 64, 64, 0, stream>>>(g, n_blocks, s.n_types);
+    if (s.n_types > 0) gsw_sufmin_kernel<<<s.n_types, 32, 0, stream>>>(g, n_blocks, s.n_types);
     *launches += 3;
   }
   gsw_sweep_kernel<<<1, 32, GSW_SMEM, stream>>>(s, w, g, delayed, policy);

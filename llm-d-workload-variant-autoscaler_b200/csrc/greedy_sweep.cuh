@@ -324,8 +324,14 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
     if (valid) me = blk[in_blk + lane];
     const unsigned fl = ge_flags(me.meta);
     const int type = ge_type(me.meta);
-    const unsigned peers = __match_any_sync(full, me.srv);
     unsigned npm = delayed ? 0u : __ballot_sync(full, valid && (fl & GE_NEWPRIO));
+    // most events of the stream belong to entries that already left the queue: a batch without an alive event (and
+    // without a priority boundary) costs one shared-memory look-up and a vote
+    const bool al0 = valid && gsw_alive(alive, me.srv);
+    const unsigned am0 = __ballot_sync(full, al0);
+    if (!am0 && !npm) { pos += nvalid; continue; }
+    // lanes of the same entry (only needed when two or more events of the batch are alive)
+    const unsigned peers = (am0 & (am0 - 1)) ? __match_any_sync(full, me.srv) : (1u << lane);
     // ---- fast path: no alive leader of a multi-leader tie group and no priority boundary in the batch.
     // Only a lane that fits (or has no accelerator) under the capacities at the START of the batch can take (or be
     // dropped): capacities only shrink.  Those candidates are visited in lane order with the whole state in registers —
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
     // updates — and everything else alive is a failure, processed once for the whole batch.  Exactly the sequential
     // semantics: lane L sees the takes of the lanes before it and nothing else.
     {
-      bool al = valid && gsw_alive(alive, me.srv);
+      bool al = al0;
       long long myavail = (al && type >= 0) ? avail[type] : 0;
       const unsigned multi_alive = __ballot_sync(full, al && (fl & GE_MULTI));
       if (!multi_alive && !npm) {
@@ -347,7 +353,8 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
           const int tF = __shfl_sync(full, type, F);
           const long long cF = __shfl_sync(full, me.cnt, F);
           if (tF >= 0 && type == tF) myavail -= cF;
-          if (lane > F && ((peers >> F) & 1u)) al = false;   // later events of the same entry are dead
+          if (lane > F && ((peers >> F) & 1u)) al = false;   // later events of the same entry are dead ...
+          cand &= ~__shfl_sync(full, peers, F);              // ... and no longer candidates
           took |= 1u << F;
           n_seq++;
         }

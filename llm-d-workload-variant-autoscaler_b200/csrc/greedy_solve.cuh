@@ -238,8 +238,42 @@ __device__ __forceinline__ GRec g_load_rec(const GreedyWs& w, size_t p, int j, i
   return r;
 }
 
+// Optional shared-memory staging for bestEffort: the first G_STAGE_A records (type, replicas, units per replica) of 32
+// servers of the list are fetched with all loads in flight, instead of one dependent round trip per server.
+struct GStage { long long* upr; int* type; int* nrep; };
+__device__ __forceinline__ void g_stage_fill(const GreedyWs& w, const GStage& st, int my_srv, int my_n, int kn, int A) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  for (int k0 = 0; k0 < 32; k0 += 8) {              // 8 servers' records in flight: loads first, stores after (the
+    int t[8], nr[8]; long long u[8];                  // compiler cannot move a load above a store through generic pointers)
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int srv = __shfl_sync(full, my_srv, k0 + q);
+      const int nc = __shfl_sync(full, my_n, k0 + q);
+      t[q] = -1; nr[q] = 0; u[q] = 0;
+      if (k0 + q < kn && lane < nc && lane < G_STAGE_A) {
+        const size_t p = (size_t)srv * A + lane;
+        t[q] = w.r_type[p]; nr[q] = w.r_nrep[p]; u[q] = w.r_upr[p];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (lane < G_STAGE_A) { st.type[(k0 + q) * G_STAGE_A + lane] = t[q]; st.nrep[(k0 + q) * G_STAGE_A + lane] = nr[q]; st.upr[(k0 + q) * G_STAGE_A + lane] = u[q]; }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ GRec g_staged_rec(const GreedyWs& w, const GStage& st, int k, size_t p, int j, int A) {
+  if (st.upr && j < G_STAGE_A) {
+    GRec r; r.kd = 0; r.kv = 0;
+    r.type = st.type[k * G_STAGE_A + j]; r.nrep = st.nrep[k * G_STAGE_A + j]; r.upr = st.upr[k * G_STAGE_A + j];
+    return r;
+  }
+  return g_load_rec(w, p, j, A);
+}
+
 // allocateMaximally (greedy.go:194-223): servers in list order; the lanes test a server's candidates in parallel
-__device__ void g_allocate_maximally(const SysView& s, const GreedyWs& w, long long* avail, const int* list, int n) {
+__device__ void g_allocate_maximally(const SysView& s, const GreedyWs& w, long long* avail, const int* list, int n, const GStage& st) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int A = s.n_acc;
@@ -247,13 +281,14 @@ __device__ void g_allocate_maximally(const SysView& s, const GreedyWs& w, long l
     const int my_srv = (k0 + lane < n) ? list[k0 + lane] : -1;
     const int my_n = my_srv >= 0 ? w.ncand[my_srv] : 0;
     const int kn = min(32, n - k0);
+    if (st.upr) g_stage_fill(w, st, my_srv, my_n, kn, A);
     for (int k = 0; k < kn; k++) {
       const int srv = __shfl_sync(full, my_srv, k);
       const int nc = __shfl_sync(full, my_n, k);
       const size_t p = (size_t)srv * A;
       for (int j0 = 0; j0 < nc; j0 += 32) {
         const int j = j0 + lane;
-        const GRec r = g_load_rec(w, p, j, A);
+        const GRec r = g_staged_rec(w, st, k, p, j, A);
         long long maxr = 0;
         if (j < nc && r.type >= 0 && r.upr > 0) {
           maxr = avail[r.type] / r.upr;
@@ -277,7 +312,7 @@ __device__ void g_allocate_maximally(const SysView& s, const GreedyWs& w, long l
 // Round 1 picks each server's accelerator (the first candidate with room for one replica AT THAT MOMENT) and is
 // therefore sequential over the servers, with the candidates of a server tested by the lanes; the later rounds
 // only touch the tickets, 32 per round trip.
-__device__ void g_allocate_equally(const SysView& s, const GreedyWs& w, long long* avail, const int* list, int n) {
+__device__ void g_allocate_equally(const SysView& s, const GreedyWs& w, long long* avail, const int* list, int n, const GStage& st) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int A = s.n_acc;
@@ -286,13 +321,14 @@ __device__ void g_allocate_equally(const SysView& s, const GreedyWs& w, long lon
     const int my_srv = (k0 + lane < n) ? list[k0 + lane] : -1;
     const int my_n = my_srv >= 0 ? w.ncand[my_srv] : 0;
     const int kn = min(32, n - k0);
+    if (st.upr) g_stage_fill(w, st, my_srv, my_n, kn, A);
     for (int k = 0; k < kn; k++) {
       const int srv = __shfl_sync(full, my_srv, k);
       const int nc = __shfl_sync(full, my_n, k);
       const size_t p = (size_t)srv * A;
       for (int j0 = 0; j0 < nc; j0 += 32) {
         const int j = j0 + lane;
-        const GRec r = g_load_rec(w, p, j, A);
+        const GRec r = g_staged_rec(w, st, k, p, j, A);
         const bool room = j < nc && r.type >= 0 && r.upr > 0 && avail[r.type] >= r.upr;
         const unsigned m = __ballot_sync(full, room);
         if (m) {
@@ -346,11 +382,12 @@ __device__ void g_allocate_equally(const SysView& s, const GreedyWs& w, long lon
 }
 
 // bestEffort (greedy.go:169-192)
-__device__ void g_best_effort(const SysView& s, const GreedyWs& w, long long* avail, const int* list, int n, int policy) {
+__device__ void g_best_effort(const SysView& s, const GreedyWs& w, long long* avail, const int* list, int n, int policy,
+                              const GStage& st = GStage{nullptr, nullptr, nullptr}) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   __syncwarp();   // the list was written by lane 0
-  if (policy == 1) g_allocate_maximally(s, w, avail, list, n);
+  if (policy == 1) g_allocate_maximally(s, w, avail, list, n, st);
   else if (policy == 2) {
     int i = 0;
     while (i < n) {   // makePriorityGroups (greedy.go:321-341): runs of equal priority in list order
@@ -364,10 +401,10 @@ __device__ void g_best_effort(const SysView& s, const GreedyWs& w, long long* av
         j += 32;
       }
       if (j > n) j = n;
-      g_allocate_equally(s, w, avail, list + i, j - i);
+      g_allocate_equally(s, w, avail, list + i, j - i, st);
       i = j;
     }
-  } else if (policy == 3) g_allocate_equally(s, w, avail, list, n);
+  } else if (policy == 3) g_allocate_equally(s, w, avail, list, n, st);
 }
 
 #ifdef WVA_GREEDY_PROFILE
@@ -613,7 +650,7 @@ static inline int32_t greedy_layout(size_t S, size_t A, size_t T, size_t extra, 
                o_hkh = take(S * 8), o_hkl = take(S * 8), o_hcn = take(S * 8), o_hs = take(S * 4), o_hc = take(S * 4), o_ht = take(S * 4),
                o_un = take(S * 4), o_kind = take(S), o_sr = take(S * 4), o_sn = take(S * 4),
                o_ts = take(S * 4), o_tt = take(S * 4), o_tr = take(S * 4), o_tw = take(S * 4), o_tn = take(S * 4), o_tu = take(S * 8),
-               o_av = take(T * 8 + 8), o_st = take(64);
+               o_av = take(T * 8 + 8), o_st = take(128);
   size_t tmp = 0, tb = 0;
   cub::CountingInputIterator<int> cnt(0);
   const size_t n_sel = S * A > S ? S * A : S;

@@ -154,9 +154,13 @@ __global__ void __launch_bounds__(256) gsw_multi_kernel(GSweepWs g, int n) {
 }
 
 constexpr int GSW_SLOTS = 4;
-constexpr int GSW_ALIVE_WORDS = 40 * 1024; // alive bits for up to 1 310 720 entries in shared memory (160 KB)
+constexpr int GSW_ALIVE_WORDS = 36 * 1024; // alive bits for up to 1 179 648 entries in shared memory (144 KB)
+constexpr int GSW_TIE_CAP = 1024;          // events of a tie group staged in shared memory at a time
+constexpr int GSW_DYN_CAP = 4096;          // alive leaders of a tie group ordered in shared memory (more: global-memory path)
+constexpr int GSW_RUN_SLOTS = 8;           // runs of a tie group in flight (32 events each, in the staging area)
 constexpr int GSW_AVAIL = 64;              // capacity types (WVA_MAX_TYPES)
-constexpr size_t GSW_SMEM = (size_t)GSW_BLOCK * GSW_SLOTS * sizeof(GEvent) + (size_t)GSW_ALIVE_WORDS * 4 + GSW_AVAIL * 8;
+constexpr size_t GSW_SMEM = (size_t)GSW_BLOCK * GSW_SLOTS * sizeof(GEvent) + (size_t)GSW_ALIVE_WORDS * 4 + GSW_AVAIL * 8 +
+                            (size_t)GSW_TIE_CAP * sizeof(GEvent) + (size_t)GSW_DYN_CAP * 8;
 
 __device__ __forceinline__ void gsw_cp16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
@@ -165,7 +169,7 @@ __device__ __forceinline__ void gsw_commit() { asm volatile("cp.async.commit_gro
 template <int N> __device__ __forceinline__ void gsw_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Sweep state: plain values (kept in registers: nothing here has its address taken across a call)
-struct GSweepState { int n_un, clock; long long n_active; };
+struct GSweepState { int n_un, clock; long long n_active; long long d_fb, d_nact, d_maxact, d_fbev; };
 
 __device__ __forceinline__ bool gsw_alive(const unsigned* alive, int srv) { return (alive[srv >> 5] >> (srv & 31)) & 1u; }
 __device__ __forceinline__ void gsw_kill(unsigned* alive, int srv) {
@@ -258,11 +262,140 @@ __device__ __forceinline__ int gsw_tie_group(const GreedyWs& w, const GSweepWs& 
   return end_pos;
 }
 
+// The same with the event list streamed through shared memory.  (1) The part is scanned in chunks of GSW_TIE_CAP events
+// (cp.async, a whole chunk in flight) and its alive leaders collected; (2) their stamps are fetched lane-parallel and the
+// leaders sorted latest insertion first (bitonic, shared memory); (3) the runs are processed in that order, 32 events per
+// step, each run prefetched GSW_RUN_SLOTS - 1 runs ahead.  Returns -2 (nothing changed) when the part holds more than
+// GSW_DYN_CAP alive leaders: the caller then takes the global-memory path above.
+__device__ __forceinline__ int gsw_tie_group_staged(const GreedyWs& w, const GSweepWs& g, long long* avail, unsigned* alive,
+                                                    GSweepState& z, int i0, int n_ev, GEvent* tev, int2* dyn) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  __threadfence_block();           // the stamps written by other lanes of this warp are read below
+  __syncwarp();
+  int scanned = 0, n_part = 0, n_act = 0, chunk = 256;
+  bool ended = false;
+  while (!ended) {
+    const int cnt = min(chunk, n_ev - (i0 + scanned));
+    if (cnt <= 0) break;
+    for (int k = lane; k < cnt; k += 32) gsw_cp16(tev + k, g.ev + i0 + scanned + k);
+    gsw_commit();
+    gsw_wait<0>();
+    __syncwarp();
+    for (int base = 0; base < cnt && !ended; base += 32) {
+      const int k = base + lane;
+      const bool v = k < cnt;
+      unsigned m = 0; int sv = 0;
+      if (v) { m = tev[k].meta; sv = tev[k].srv; }
+      const unsigned f = ge_flags(m);
+      const bool in_part = v && (scanned + k == 0 || (f & GE_TIE)) && !(f & GE_CLS1);
+      const unsigned stop = __ballot_sync(full, !in_part);
+      const int nin = stop ? __ffs(stop) - 1 : 32;
+      const bool is_cand = lane < nin && (f & GE_LEADER) && gsw_alive(alive, sv);
+      const unsigned cm = __ballot_sync(full, is_cand);
+      if (n_act + __popc(cm) > GSW_DYN_CAP) return -2;
+      if (is_cand) dyn[n_act + __popc(cm & ((1u << lane) - 1u))] = make_int2(sv, i0 + scanned + k);
+      n_act += __popc(cm);
+      n_part = scanned + base + nin;
+      if (nin < 32) ended = true;
+    }
+    __syncwarp();                  // the chunk is overwritten next
+    scanned += cnt;
+    chunk = GSW_TIE_CAP;
+  }
+  const int end_pos = i0 + n_part;
+  z.d_nact += n_act; if (n_act > z.d_maxact) z.d_maxact = n_act;
+  if (scanned > GSW_TIE_CAP) { z.d_fb++; z.d_fbev += n_part; }
+  if (n_act <= 1) return -1;
+  // (2) stamps (distinct clock values > 0), then descending order; the padding (-1) sorts last
+  int n2 = 32;
+  while (n2 < n_act) n2 <<= 1;
+  __syncwarp();
+#pragma unroll 4
+  for (int q = lane; q < n2; q += 32) dyn[q].x = q < n_act ? *((volatile int*)&g.stamp[dyn[q].x]) : -1;
+  __syncwarp();
+  for (int k = 2; k <= n2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n2; i += 32) {
+        const int l = i ^ j;
+        if (l > i) {
+          const int2 a = dyn[i], b = dyn[l];
+          if (((i & k) == 0) ? (a.x < b.x) : (a.x > b.x)) { dyn[i] = b; dyn[l] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  // (3) the runs.  Slot (it % GSW_RUN_SLOTS) of the staging area holds the first 32 events of run `it`.
+  auto issue = [&](int it) {
+    if (it < n_act) {
+      const int p = dyn[it].y + lane;
+      if (p < end_pos) gsw_cp16(tev + (it % GSW_RUN_SLOTS) * 32 + lane, g.ev + p);
+    }
+    gsw_commit();
+  };
+  for (int it = 0; it < GSW_RUN_SLOTS - 1; it++) issue(it);
+  for (int it = 0; it < n_act; it++) {
+    issue(it + GSW_RUN_SLOTS - 1);
+    gsw_wait<GSW_RUN_SLOTS - 1>();
+    __syncwarp();
+    // the leader's run, 32 events per step: the events before the first one that fits (or has no accelerator) fail —
+    // each failure re-inserts the entry in front of the queue (same tau, latest insertion) — and the run ends there, at
+    // the entry's last candidate, or at the end of its events in this tie group (gsw_process, event by event)
+    const int k0 = dyn[it].y;
+    int srv0 = 0;
+    bool done = false;
+    for (int base = k0; base < end_pos && !done; base += 32) {
+      const int k = base + lane;
+      GEvent e; e.srv = -1; e.meta = 0; e.cnt = 0;
+      if (k < end_pos) e = base == k0 ? tev[(it % GSW_RUN_SLOTS) * 32 + lane] : g.ev[k];
+      if (base == k0) srv0 = __shfl_sync(full, e.srv, 0);
+      const unsigned f = ge_flags(e.meta);
+      const bool inrun = k < end_pos && (k == k0 || (e.srv == srv0 && (f & GE_TIE)));
+      const unsigned stopm = __ballot_sync(full, !inrun);
+      const int nrun = stopm ? __ffs(stopm) - 1 : 32;
+      const int type = ge_type(e.meta);
+      const bool mine = lane < nrun;
+      const unsigned tm = __ballot_sync(full, mine && (type < 0 || avail[type < 0 ? 0 : type] >= e.cnt));
+      const int F = tm ? __ffs(tm) - 1 : nrun;       // lanes below F fail
+      const unsigned lastm = __ballot_sync(full, mine && lane < F && (f & GE_LAST));
+      __syncwarp();
+      z.n_active += F + (tm ? 1 : 0);
+      z.clock += F;
+      if (tm) {
+        if (lane == F) {
+          if (type >= 0) { avail[type] -= e.cnt; w.kind[srv0] = 1; w.sel_rank[srv0] = ge_rank(e.meta); }   // greedy.go:143-145
+          alive[srv0 >> 5] &= ~(1u << (srv0 & 31));                                                           // (or dropped, :126-136)
+        }
+        done = true;
+      } else if (lastm) {                            // :152-156
+        if (lane == 0) { w.unalloc[z.n_un] = srv0; alive[srv0 >> 5] &= ~(1u << (srv0 & 31)); }
+        z.n_un++;
+        done = true;
+      } else {
+        if (lane == 0 && F > 0) g.stamp[srv0] = z.clock;
+        if (nrun < 32) done = true;
+      }
+      __syncwarp();
+    }
+  }
+  gsw_wait<0>();
+  __syncwarp();
+  return end_pos;
+}
+
 __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w, GSweepWs g, int delayed, int policy) {
   extern __shared__ __align__(16) unsigned char gsw_smem[];
   GEvent* ring = reinterpret_cast<GEvent*>(gsw_smem);
   unsigned* alive = reinterpret_cast<unsigned*>(gsw_smem + (size_t)GSW_BLOCK * GSW_SLOTS * sizeof(GEvent));
   long long* avail = reinterpret_cast<long long*>(alive + GSW_ALIVE_WORDS);
+  GEvent* tie_ev = reinterpret_cast<GEvent*>(avail + GSW_AVAIL);
+  int2* tie_dyn = reinterpret_cast<int2*>(tie_ev + GSW_TIE_CAP);
+  // bestEffort never runs inside a tie group: its staging area is the tie group's (32 x G_STAGE_A x 16 B = GSW_TIE_CAP x 16 B)
+  static_assert(32 * G_STAGE_A * 16 <= GSW_TIE_CAP * (int)sizeof(GEvent), "bestEffort staging");
+  GStage be_stage;
+  be_stage.upr = reinterpret_cast<long long*>(tie_ev);
+  be_stage.type = reinterpret_cast<int*>(be_stage.upr + 32 * G_STAGE_A);
+  be_stage.nrep = be_stage.type + 32 * G_STAGE_A;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -271,9 +404,10 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
   for (int t = lane; t < s.n_types; t += 32) avail[t] = s.type_count[t];          // greedy.go:38-39
   for (int k = lane; k < (S + 31) / 32; k += 32) alive[k] = 0xffffffffu;
   __syncwarp();
-  GSweepState z = {0, 0, 0};
+  GSweepState z = {0, 0, 0, 0, 0, 0, 0};
   int group_un0 = 0;
-  long long n_batches = 0, n_rounds = 0, n_seq = 0, n_tie = 0;
+  long long n_batches = 0, n_rounds = 0, n_seq = 0, n_tie = 0, cyc_be = 0, cyc_tie = 0, n_unalloc_be = 0;
+  const long long cyc0 = clock64();
 
   // event stream: blocks of GSW_BLOCK records copied asynchronously into a ring of GSW_SLOTS slots; while block b is
   // read, blocks b+1 .. b+GSW_SLOTS-1 are in flight.  One commit group per block (empty past the end of the list).
@@ -425,7 +559,11 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
         // a new priority group starts at lane `first`: allocate() of the previous group is complete -> its bestEffort()
         // (greedy.go:96-103) on the entries it left unallocated, in the order they were exhausted
         npm &= ~(1u << first);
-        if (z.n_un > group_un0) g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy);
+        if (z.n_un > group_un0) {
+          const long long c0 = clock64();
+          g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy, be_stage);
+          cyc_be += clock64() - c0; n_unalloc_be += z.n_un - group_un0;
+        }
         group_un0 = z.n_un;
         __syncwarp();
         continue;                                  // the lane itself is evaluated in the next round
@@ -445,7 +583,10 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
         const unsigned others = __ballot_sync(full, al && (fl & GE_LEADER)) & span;
         if (!ends_here || others) {
           n_tie++;
-          const int np = gsw_tie_group(w, g, avail, alive, z, pos + first, n_ev);
+          const long long c0 = clock64();
+          int np = gsw_tie_group_staged(w, g, avail, alive, z, pos + first, n_ev, tie_ev, tie_dyn);
+          if (np == -2) np = gsw_tie_group(w, g, avail, alive, z, pos + first, n_ev);
+          cyc_tie += clock64() - c0;
           if (np >= 0) { jump = np; break; }
         }
       }
@@ -466,7 +607,12 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
   }
   __syncwarp();
   // the last group's (or, delayed, the whole list's) best effort
-  if (z.n_un > group_un0) g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy);
+  if (z.n_un > group_un0) {
+    const long long c0 = clock64();
+    g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy, be_stage);
+    cyc_be += clock64() - c0; n_unalloc_be += z.n_un - group_un0;
+  }
+  if (lane == 0) { w.stats[8] = cyc_be; w.stats[9] = cyc_tie; w.stats[10] = clock64() - cyc0; w.stats[11] = n_unalloc_be; w.stats[12] = z.d_fb; w.stats[13] = z.d_nact; w.stats[14] = z.d_maxact; w.stats[15] = z.d_fbev; }
   if (lane == 0) { w.stats[0] = 0; w.stats[1] = z.n_active; w.stats[2] = n_batches; w.stats[3] = n_rounds; w.stats[4] = n_seq; w.stats[5] = n_tie; w.stats[6] = pos; w.stats[7] = n_ev; }
 }
 
@@ -535,13 +681,13 @@ static inline int32_t run_solve_greedy_sweep(const SysView& s, const CandView& c
   greedy_finalize_kernel<<<(unsigned)((S + 255) / 256), 256, 0, stream>>>(s, c, o, w);
   *launches += 2;
   if (stats_out) {
-    long long h[8];
-    if (cudaMemcpyAsync(h, w.stats, 64, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
+    long long h[16];
+    if (cudaMemcpyAsync(h, w.stats, 128, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
     if (cudaStreamSynchronize(stream) != cudaSuccess) return WVA_ERR_CUDA;
     stats_out[0] = h[0]; stats_out[1] = h[1];
     if (getenv("WVA_SIZER_DEBUG"))
-      fprintf(stderr, "greedy sweep: alive events %lld, batches %lld, rounds %lld, sequential events %lld, tie-group calls %lld, stopped at %lld of %lld\n",
-              h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+      fprintf(stderr, "greedy sweep: alive events %lld, batches %lld, rounds %lld, sequential events %lld, tie-group calls %lld, stopped at %lld of %lld; cycles: best effort %lld (%lld entries), tie groups %lld, kernel %lld; tie groups: %lld over the staging size (%lld events), alive leaders %lld (max %lld)\n",
+              h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[11], h[9], h[10], h[12], h[15], h[13], h[14]);
   }
   return cudaGetLastError() == cudaSuccess ? WVA_OK : WVA_ERR_CUDA;
 }

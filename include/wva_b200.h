@@ -196,10 +196,9 @@ int64_t wva_launch_count(const wva_ctx* ctx);
                                       global memory; 1 force shared memory (when it fits at all); 2 force global memory
                                       (two 256-thread blocks per SM under a 128-register cap).  Placement only */
 #define WVA_OPT_GREEDY_MODE 5      /* limited-capacity allocator: 1 the literal queue (sorted array + re-insertion heap,
-                                      csrc/greedy_solve.cuh); 2 the static-order event sweep (csrc/greedy_sweep.cuh)
-                                      wherever it applies; 0 (default) by measured cost: the sweep under policy None
-                                      (it stops once nothing can fit any more), the queue under the best-effort
-                                      policies.  Same result either way */
+                                      csrc/greedy_solve.cuh); 0 (default) and 2 the static-order event sweep
+                                      (csrc/greedy_sweep.cuh) wherever it applies (<= 1 179 648 servers, <= 64 capacity
+                                      types), the queue elsewhere.  Same result either way */
 #define WVA_OPT_GRID_DEFER 6       /* replica grid: 0 (default) the near-saturation levels of every pair (lambda / mu_N
                                       > 0.6: the long chains) are deferred to a pass sorted by chain length when the
                                       system has >= 20 000 pairs; 1 never; 2 always.  Scheduling only */

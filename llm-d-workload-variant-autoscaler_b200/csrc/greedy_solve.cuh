@@ -74,6 +74,9 @@ struct GreedyWs {   // device workspace views
   // allocateEqually tickets, [S] indexed by ticket
   int* tk_srv; int* tk_type; int* tk_rank; int* tk_want; int* tk_nrep; long long* tk_upr;
   long long* avail;  // [T] (used when the types do not fit the shared-memory copy)
+  // bestEffort filter: the capacity types (< 64) behind a server's candidates, and per type the smallest units per replica
+  // of any candidate — a server none of whose types has that much left can get nothing (greedy.go:204-213, 262-272)
+  g_u64* tmask; long long* min_upr;
   long long* stats;  // [2] heap pushes, events (entries processed) of the last sweep
 };
 
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(128) greedy_prepare_kernel(SysView s, CandView
     n++;
   }
   const bool known = s.srv_model[srv] >= 0;                              // greedy.go:126-129
+  g_u64 tmask = 0;
   for (int j = 0; j < n; j++) {
     const int a = ord[j];
     const float v = c.value[p + a];
@@ -103,8 +107,15 @@ __global__ void __launch_bounds__(128) greedy_prepare_kernel(SysView s, CandView
     const bool live = known && c.state[p + a] == ALLOC_ACC;              // greedy.go:133-136
     w.r_type[p + j] = live ? s.acc_type[a] : -1;
     w.r_nrep[p + j] = live ? c.num_replicas[p + a] : 0;
-    w.r_upr[p + j] = live ? (long long)num_instances(s, s.srv_model[srv], a) * s.acc_multiplicity[a] : 0;   // greedy.go:139
+    const long long upr = live ? (long long)num_instances(s, s.srv_model[srv], a) * s.acc_multiplicity[a] : 0;   // greedy.go:139
+    w.r_upr[p + j] = upr;
+    if (live && upr > 0) {
+      const int t = s.acc_type[a];
+      if (t >= 64) tmask = ~0ull;
+      else if (t >= 0) { if (upr < w.min_upr[t]) atomicMin(&w.min_upr[t], upr); tmask |= 1ull << t; }
+    }
   }
+  w.tmask[srv] = tmask;
   for (int j = n; j < A; j++) {   // ranks past the list are read (and masked) by the 32-wide record loads of the sweep
     w.r_kd[p + j] = 0; w.r_kv[p + j] = 0; w.r_type[p + j] = -1; w.r_nrep[p + j] = 0; w.r_upr[p + j] = 0;
   }
@@ -241,18 +252,19 @@ __device__ __forceinline__ GRec g_load_rec(const GreedyWs& w, size_t p, int j, i
 // Optional shared-memory staging for bestEffort: the first G_STAGE_A records (type, replicas, units per replica) of 32
 // servers of the list are fetched with all loads in flight, instead of one dependent round trip per server.
 struct GStage { long long* upr; int* type; int* nrep; };
-__device__ __forceinline__ void g_stage_fill(const GreedyWs& w, const GStage& st, int my_srv, int my_n, int kn, int A) {
+__device__ __forceinline__ void g_stage_fill(const GreedyWs& w, const GStage& st, int my_srv, int my_n, unsigned passm, int A) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   __syncwarp();
   for (int k0 = 0; k0 < 32; k0 += 8) {              // 8 servers' records in flight: loads first, stores after (the
+    if (!((passm >> k0) & 0xffu)) continue;
     int t[8], nr[8]; long long u[8];                  // compiler cannot move a load above a store through generic pointers)
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const int srv = __shfl_sync(full, my_srv, k0 + q);
       const int nc = __shfl_sync(full, my_n, k0 + q);
       t[q] = -1; nr[q] = 0; u[q] = 0;
-      if (k0 + q < kn && lane < nc && lane < G_STAGE_A) {
+      if (((passm >> (k0 + q)) & 1u) && lane < nc && lane < G_STAGE_A) {
         const size_t p = (size_t)srv * A + lane;
         t[q] = w.r_type[p]; nr[q] = w.r_nrep[p]; u[q] = w.r_upr[p];
       }
@@ -272,17 +284,35 @@ __device__ __forceinline__ GRec g_staged_rec(const GreedyWs& w, const GStage& st
   return g_load_rec(w, p, j, A);
 }
 
+// the capacity types that can still place one replica of SOME candidate (bit t: available[t] >= min_upr[t])
+__device__ __forceinline__ g_u64 g_live_types(const long long* avail, int n_types, long long mu_lo, long long mu_hi) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (n_types > 64) return ~0ull;
+  const unsigned lo = __ballot_sync(full, lane < n_types && avail[lane] >= mu_lo);
+  const unsigned hi = __ballot_sync(full, lane + 32 < n_types && avail[(lane + 32) < n_types ? lane + 32 : 0] >= mu_hi);
+  return (g_u64)lo | ((g_u64)hi << 32);
+}
+
 // allocateMaximally (greedy.go:194-223): servers in list order; the lanes test a server's candidates in parallel
 __device__ void g_allocate_maximally(const SysView& s, const GreedyWs& w, long long* avail, const int* list, int n, const GStage& st) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int A = s.n_acc;
+  const long long mu_lo = lane < s.n_types ? w.min_upr[lane] : 0, mu_hi = (lane + 32 < s.n_types && lane + 32 < 64) ? w.min_upr[lane + 32] : 0;
+  int nxt_srv = lane < n ? list[lane] : -1;
   for (int k0 = 0; k0 < n; k0 += 32) {
-    const int my_srv = (k0 + lane < n) ? list[k0 + lane] : -1;
-    const int my_n = my_srv >= 0 ? w.ncand[my_srv] : 0;
-    const int kn = min(32, n - k0);
-    if (st.upr) g_stage_fill(w, st, my_srv, my_n, kn, A);
-    for (int k = 0; k < kn; k++) {
+    const int my_srv = nxt_srv;
+    nxt_srv = (k0 + 32 + lane < n) ? list[k0 + 32 + lane] : -1;
+    // only a server with a candidate on a type that still has room for one replica of something can get anything
+    const g_u64 ltypes = g_live_types(avail, s.n_types, mu_lo, mu_hi);
+    unsigned passm = __ballot_sync(full, my_srv >= 0 && ltypes != 0 && (w.tmask[my_srv] & ltypes) != 0);
+    if (!passm) continue;
+    const int my_n = ((passm >> lane) & 1u) ? w.ncand[my_srv] : 0;
+    if (st.upr) g_stage_fill(w, st, my_srv, my_n, passm, A);
+    while (passm) {
+      const int k = __ffs(passm) - 1;
+      passm &= passm - 1;
       const int srv = __shfl_sync(full, my_srv, k);
       const int nc = __shfl_sync(full, my_n, k);
       const size_t p = (size_t)srv * A;
@@ -317,12 +347,20 @@ __device__ void g_allocate_equally(const SysView& s, const GreedyWs& w, long lon
   const int lane = threadIdx.x & 31;
   const int A = s.n_acc;
   int n_tk = 0, live = 0;
+  const long long mu_lo = lane < s.n_types ? w.min_upr[lane] : 0, mu_hi = (lane + 32 < s.n_types && lane + 32 < 64) ? w.min_upr[lane + 32] : 0;
+  int nxt_srv = lane < n ? list[lane] : -1;
   for (int k0 = 0; k0 < n; k0 += 32) {
-    const int my_srv = (k0 + lane < n) ? list[k0 + lane] : -1;
-    const int my_n = my_srv >= 0 ? w.ncand[my_srv] : 0;
-    const int kn = min(32, n - k0);
-    if (st.upr) g_stage_fill(w, st, my_srv, my_n, kn, A);
-    for (int k = 0; k < kn; k++) {
+    const int my_srv = nxt_srv;
+    nxt_srv = (k0 + 32 + lane < n) ? list[k0 + 32 + lane] : -1;
+    // only a server with a candidate on a type that still has room for one replica of something can get anything
+    const g_u64 ltypes = g_live_types(avail, s.n_types, mu_lo, mu_hi);
+    unsigned passm = __ballot_sync(full, my_srv >= 0 && ltypes != 0 && (w.tmask[my_srv] & ltypes) != 0);
+    if (!passm) continue;
+    const int my_n = ((passm >> lane) & 1u) ? w.ncand[my_srv] : 0;
+    if (st.upr) g_stage_fill(w, st, my_srv, my_n, passm, A);
+    while (passm) {
+      const int k = __ffs(passm) - 1;
+      passm &= passm - 1;
       const int srv = __shfl_sync(full, my_srv, k);
       const int nc = __shfl_sync(full, my_n, k);
       const size_t p = (size_t)srv * A;
@@ -650,7 +688,7 @@ static inline int32_t greedy_layout(size_t S, size_t A, size_t T, size_t extra, 
                o_hkh = take(S * 8), o_hkl = take(S * 8), o_hcn = take(S * 8), o_hs = take(S * 4), o_hc = take(S * 4), o_ht = take(S * 4),
                o_un = take(S * 4), o_kind = take(S), o_sr = take(S * 4), o_sn = take(S * 4),
                o_ts = take(S * 4), o_tt = take(S * 4), o_tr = take(S * 4), o_tw = take(S * 4), o_tn = take(S * 4), o_tu = take(S * 8),
-               o_av = take(T * 8 + 8), o_st = take(128);
+               o_av = take(T * 8 + 8), o_st = take(256), o_tm = take(S * 8), o_mu = take(64 * 8);
   size_t tmp = 0, tb = 0;
   cub::CountingInputIterator<int> cnt(0);
   const size_t n_sel = S * A > S ? S * A : S;
@@ -678,6 +716,7 @@ static inline int32_t greedy_layout(size_t S, size_t A, size_t T, size_t extra, 
   w.unalloc = (int*)(d + o_un); w.kind = (unsigned char*)(d + o_kind); w.sel_rank = (int*)(d + o_sr); w.sel_nrep = (int*)(d + o_sn);
   w.tk_srv = (int*)(d + o_ts); w.tk_type = (int*)(d + o_tt); w.tk_rank = (int*)(d + o_tr); w.tk_want = (int*)(d + o_tw);
   w.tk_nrep = (int*)(d + o_tn); w.tk_upr = (long long*)(d + o_tu);
+  w.tmask = (g_u64*)(d + o_tm); w.min_upr = (long long*)(d + o_mu);
   w.avail = (long long*)(d + o_av);
   w.stats = (long long*)(d + o_st);
   tmp_bytes = tmp;
@@ -703,6 +742,7 @@ static inline int32_t run_solve_greedy(const SysView& s, const CandView& c, cons
     return WVA_ERR_CUDA;
   void* d_tmp = d_tmp0;
   const unsigned nb = (unsigned)((S + 255) / 256);
+  if (cudaMemsetAsync(w.min_upr, 0x7f, 64 * 8, stream) != cudaSuccess) return WVA_ERR_CUDA;
   greedy_prepare_kernel<<<(unsigned)((S + 127) / 128), 128, 0, stream>>>(s, c, w);
   size_t t2 = tmp;
   if (cub::DeviceSelect::Flagged(d_tmp, t2, cnt, w.flag, w.e_srv, w.n_entries, (int)S, stream) != cudaSuccess) return WVA_ERR_CUDA;

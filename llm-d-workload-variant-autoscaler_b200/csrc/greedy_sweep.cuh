@@ -416,18 +416,53 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
   int cur_block = -1;
   int pos = 0;
   int checked_blk = -1;
+  bool nothing_fits = false;
+  long long n_survivors = -1;
+  long long cyc_ring = 0, cyc_dead = 0, cyc_fast = 0, cyc_slow = 0, cyc_chk = 0;
   while (pos < n_ev) {
-    // Policy None: once no remaining event of any type can fit (capacities only shrink, greedy.go:143-145, and
-    // bestEffort is a no-op), every entry still in the queue ends unallocated whatever the order: stop.
-    if (policy == 0 && pos / GSW_BLOCK != checked_blk) {
+    const long long tc0 = clock64();
+    // Once no remaining event of any type can fit (capacities only shrink, greedy.go:143-145; bestEffort only takes),
+    // every entry still in the queue ends unallocated.  Policy None (bestEffort is a no-op): stop.  The other policies:
+    // what is left of the sweep only fixes the ORDER of the unallocated list, and bestEffort gives nothing to an entry
+    // none of whose candidates sits on a type with room for one replica of anything (g_live_types) whatever its place
+    // in the list — those entries leave the queue here; the rest are swept on, in exactly the reference's order (the
+    // relative order of insertion stamps does not depend on the entries removed; the unallocated list is sorted by
+    // priority, so removing entries cannot merge two priority groups of makePriorityGroups, greedy.go:321-341).
+    if (!nothing_fits && pos / GSW_BLOCK != checked_blk) {
       checked_blk = pos / GSW_BLOCK;
       bool can = false;
       for (int t = lane; t < s.n_types; t += 32) {
         const unsigned long long mn = g.blk_min[(size_t)checked_blk * s.n_types + t];
         can = can || (mn != ~0ull && (unsigned long long)avail[t] >= mn && avail[t] >= 0);
       }
-      if (!__any_sync(full, can)) break;
+      if (!__any_sync(full, can)) {
+        if (policy == 0) break;
+        nothing_fits = true;
+        const long long mu_lo = lane < s.n_types ? w.min_upr[lane] : 0, mu_hi = (lane + 32 < s.n_types && lane + 32 < 64) ? w.min_upr[lane + 32] : 0;
+        const g_u64 ltypes = g_live_types(avail, s.n_types, mu_lo, mu_hi);
+        int survivors = 0;
+        __syncwarp();
+        for (int k0 = 0; k0 < (S + 31) / 32; k0 += 4) {              // 32 consecutive entries per step, 4 steps in flight
+          unsigned wd[4]; g_u64 tm[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int k = k0 + q, srv = k * 32 + lane;
+            wd[q] = k < (S + 31) / 32 ? alive[k] : 0u;
+            tm[q] = (((wd[q] >> lane) & 1u) && srv < S && ltypes) ? w.tmask[srv] : 0ull;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const unsigned keep = __ballot_sync(full, (tm[q] & ltypes) != 0);
+            if (wd[q] && lane == 0) alive[k0 + q] = keep;
+            survivors += __popc(keep);
+          }
+        }
+        __syncwarp();
+        n_survivors = survivors;
+        if (survivors == 0) break;
+      }
     }
+    const long long tc1 = clock64(); cyc_chk += tc1 - tc0;
     const int rel = pos - origin;
     const int b = rel / GSW_BLOCK;
     if (b != cur_block) {
@@ -449,6 +484,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
       __syncwarp();
       cur_block = b;
     }
+    const long long tc2 = clock64(); cyc_ring += tc2 - tc1;
     n_batches++;
     const GEvent* blk = ring + (size_t)(b % GSW_SLOTS) * GSW_BLOCK;
     const int in_blk = rel % GSW_BLOCK;
@@ -463,7 +499,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
     // without a priority boundary) costs one shared-memory look-up and a vote
     const bool al0 = valid && gsw_alive(alive, me.srv);
     const unsigned am0 = __ballot_sync(full, al0);
-    if (!am0 && !npm) { pos += nvalid; continue; }
+    if (!am0 && !npm) { pos += nvalid; cyc_dead += clock64() - tc2; continue; }
     // lanes of the same entry (only needed when two or more events of the batch are alive)
     const unsigned peers = (am0 & (am0 - 1)) ? __match_any_sync(full, me.srv) : (1u << lane);
     // ---- fast path: no alive leader of a multi-leader tie group and no priority boundary in the batch.
@@ -518,6 +554,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
         n_rounds++;
         __syncwarp();
         pos += nvalid;
+        cyc_fast += clock64() - tc2;
         continue;
       }
     }
@@ -604,6 +641,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
     } else {
       pos += nvalid;
     }
+    cyc_slow += clock64() - tc2;
   }
   __syncwarp();
   // the last group's (or, delayed, the whole list's) best effort
@@ -612,7 +650,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
     g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy, be_stage);
     cyc_be += clock64() - c0; n_unalloc_be += z.n_un - group_un0;
   }
-  if (lane == 0) { w.stats[8] = cyc_be; w.stats[9] = cyc_tie; w.stats[10] = clock64() - cyc0; w.stats[11] = n_unalloc_be; w.stats[12] = z.d_fb; w.stats[13] = z.d_nact; w.stats[14] = z.d_maxact; w.stats[15] = z.d_fbev; }
+  if (lane == 0) { w.stats[8] = cyc_be; w.stats[9] = cyc_tie; w.stats[10] = clock64() - cyc0; w.stats[11] = n_unalloc_be; w.stats[12] = z.d_fb; w.stats[13] = z.d_nact; w.stats[14] = z.d_maxact; w.stats[15] = z.d_fbev; w.stats[16] = cyc_chk; w.stats[17] = cyc_ring; w.stats[18] = cyc_dead; w.stats[19] = cyc_fast; w.stats[20] = cyc_slow; w.stats[21] = n_survivors; }
   if (lane == 0) { w.stats[0] = 0; w.stats[1] = z.n_active; w.stats[2] = n_batches; w.stats[3] = n_rounds; w.stats[4] = n_seq; w.stats[5] = n_tie; w.stats[6] = pos; w.stats[7] = n_ev; }
 }
 
@@ -650,6 +688,7 @@ static inline int32_t run_solve_greedy_sweep(const SysView& s, const CandView& c
   g.blk_min = (unsigned long long*)(ex + e_bm);
   if (cudaFuncSetAttribute(gsw_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSW_SMEM) != cudaSuccess) return WVA_ERR_CUDA;
   const unsigned sb = (unsigned)((S + 127) / 128);
+  if (cudaMemsetAsync(w.min_upr, 0x7f, 64 * 8, stream) != cudaSuccess) return WVA_ERR_CUDA;
   greedy_prepare_kernel<<<sb, 128, 0, stream>>>(s, c, w);
   gsw_events_kernel<<<sb, 128, 0, stream>>>(s, w, g);
   cub::CountingInputIterator<unsigned> cnt(0u);
@@ -681,13 +720,13 @@ static inline int32_t run_solve_greedy_sweep(const SysView& s, const CandView& c
   greedy_finalize_kernel<<<(unsigned)((S + 255) / 256), 256, 0, stream>>>(s, c, o, w);
   *launches += 2;
   if (stats_out) {
-    long long h[16];
-    if (cudaMemcpyAsync(h, w.stats, 128, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
+    long long h[24];
+    if (cudaMemcpyAsync(h, w.stats, 192, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
     if (cudaStreamSynchronize(stream) != cudaSuccess) return WVA_ERR_CUDA;
     stats_out[0] = h[0]; stats_out[1] = h[1];
     if (getenv("WVA_SIZER_DEBUG"))
-      fprintf(stderr, "greedy sweep: alive events %lld, batches %lld, rounds %lld, sequential events %lld, tie-group calls %lld, stopped at %lld of %lld; cycles: best effort %lld (%lld entries), tie groups %lld, kernel %lld; tie groups: %lld over the staging size (%lld events), alive leaders %lld (max %lld)\n",
-              h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[11], h[9], h[10], h[12], h[15], h[13], h[14]);
+      fprintf(stderr, "greedy sweep: alive events %lld, batches %lld, rounds %lld, sequential events %lld, tie-group calls %lld, stopped at %lld of %lld; cycles: best effort %lld (%lld entries), tie groups %lld, kernel %lld; tie groups: %lld over the staging size (%lld events), alive leaders %lld (max %lld); loop cycles: early-exit check %lld, ring %lld, dead batches %lld, fast path %lld, slow path %lld; entries swept on after nothing fits: %lld\n",
+              h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[11], h[9], h[10], h[12], h[15], h[13], h[14], h[16], h[17], h[18], h[19], h[20], h[21]);
   }
   return cudaGetLastError() == cudaSuccess ? WVA_OK : WVA_ERR_CUDA;
 }

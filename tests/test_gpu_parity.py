@@ -350,6 +350,40 @@ def test_greedy_both_formulations(pkg, engine, oracle, mode):
         engine.set_option(5, 0)
 
 
+def test_greedy_leftover_room_after_nothing_fits(pkg, engine, oracle, capfd, monkeypatch):
+    """Every server wants >= 3 replicas, so the sweep reaches the point where no remaining candidate fits while single
+    replicas still do: the event sweep then drops the entries bestEffort cannot serve and keeps sweeping the others in
+    the reference's order (greedy_sweep.cuh, `nothing_fits`).  Every best-effort policy, both formulations, against the
+    oracle; the debug line proves that the case with survivors was exercised."""
+    import re
+    monkeypatch.setenv("WVA_SIZER_DEBUG", "1")
+    d = pkg.synth.queue_system(500, 8, 16, stream=83, zero_load_frac=0.0, infeasible_frac=0.0)
+    d["srv_min_replicas"][:] = 3
+    dup = pkg.synth.queue_system(96, 6, 16, stream=84, zero_load_frac=0.0, infeasible_frac=0.0)
+    for k, v in list(dup.items()):
+        if isinstance(v, np.ndarray) and v.shape[:1] == (96,):
+            v[:] = np.concatenate([v[:8]] * 12)          # 12-fold keys: the survivors meet in tie groups
+    dup["srv_min_replicas"][:] = 2
+    survivors = []
+    for mode in (2, 1):
+        engine.set_option(5, mode)
+        try:
+            for sysd in (d, dup):
+                for frac in (0.2, 0.35, 0.5, 0.65, 0.8):
+                    for pol, delayed in (("PriorityExhaustive", False), ("PriorityExhaustive", True), ("PriorityRoundRobin", False),
+                                         ("PriorityRoundRobin", True), ("RoundRobin", False), ("RoundRobin", True)):
+                        capfd.readouterr()
+                        g, _ = _greedy_case(pkg, engine, oracle, sysd, frac, pol, delayed)
+                        err = capfd.readouterr().err
+                        if mode == 2:
+                            survivors += [int(x) for x in re.findall(r"after nothing fits: (-?\d+)", err)]
+                            if (g["state"] == 1).any() and frac < 0.8:
+                                assert "greedy sweep:" in err
+        finally:
+            engine.set_option(5, 0)
+    assert any(x > 0 for x in survivors), sorted(set(survivors))
+
+
 def test_greedy_ample_capacity_equals_unlimited(pkg, engine, oracle):
     sysd = pkg.synth.queue_system(120, 6, 16, stream=73)
     g, un = _greedy_case(pkg, engine, oracle, sysd, 10.0, "None", False)

@@ -194,6 +194,7 @@ extern "C" int32_t wva_mm1k_eval(wva_ctx* ctx, int64_t n, const float* lambda, c
 extern "C" int32_t wva_saturation_upload(wva_ctx* ctx, const wva_saturation_in* in) {
   if (!ctx || !in) return WVA_ERR_ARG;
   const long long M = in->n_models, V = in->n_variants, P = in->n_replicas;
+  if (M > 0x7fffffffLL) { ctx->last_error = "more than 2^31 - 1 models in one batch"; return WVA_ERR_LIMIT; }
   if (M < 0 || V < 0 || P < 0 || P > 0x7fffffffLL || V > 0x7fffffffLL) return WVA_ERR_ARG;
   if (!in->model_variant_off || !in->variant_replica_off) return WVA_ERR_ARG;
   if (!valid_offsets(in->model_variant_off, (size_t)M, (size_t)V) || !valid_offsets(in->variant_replica_off, (size_t)V, (size_t)P)) {

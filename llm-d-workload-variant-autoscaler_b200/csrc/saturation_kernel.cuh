@@ -75,11 +75,11 @@ struct alignas(16) SatStage {
 };
 struct alignas(16) SatWarpSmem {
   SatStage stage[SAT_NS];
-  double2 terms[32];
+  double termsKv[32], termsQ[32];   // the variants' terms of the two ordered sums, one column each
   unsigned long long bar[SAT_NS];
 };
 static_assert(sizeof(SatDesc) == 48 && sizeof(SatStage) % 16 == 0 && offsetof(SatStage, q) % 16 == 0 &&
-              offsetof(SatStage, cost) % 16 == 0 && offsetof(SatStage, desc) % 16 == 0 && offsetof(SatWarpSmem, terms) % 16 == 0,
+              offsetof(SatStage, cost) % 16 == 0 && offsetof(SatStage, desc) % 16 == 0 && offsetof(SatWarpSmem, termsKv) % 16 == 0 && offsetof(SatWarpSmem, termsQ) % 16 == 0,
               "alignment");
 constexpr size_t SAT_SMEM_BYTES = sizeof(SatWarpSmem) * SAT_WARPS;
 
@@ -162,14 +162,14 @@ __device__ __forceinline__ unsigned long long sat_sortable(double x) {
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-struct SatTally { long long n_up, n_down, n_trans, sum_targets; };
+struct SatTally { int n_up, n_down, n_trans; long long sum_targets; };   // (a warp sees < 2^31 models)
 
 // One model, one warp.  kv / q: the model's replicas, element 0 = replica index `rbase` (a stage, or the global arrays
 // with rbase = 0).  STAGED selects the plain per-lane loop (shared memory) or four independent loads in flight (global).
 template <bool DETAIL, bool STAGED>
 __device__ __forceinline__ void sat_model(const SatIn& in, const double* kvp, const long long* qp, const int rbase,
                                           const long long m, const int v0, const int v1, const SatOut& out,
-                                          double2* my_terms, SatTally& tally) {
+                                          double* termsKv, double* termsQ, SatTally& tally) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const bool has_hs = in.var_has_state != nullptr;
@@ -262,14 +262,14 @@ __device__ __forceinline__ void sat_model(const SatIn& in, const double* kvp, co
     // ns == 0 -> term +0.0, and x + 0.0 == x exactly, so all 32 slots are added unconditionally.
     const double termKv = analysed ? d_mul(avgKv, (double)ns) : 0.0, termQ = analysed ? d_mul(avgQ, (double)ns) : 0.0;
     __syncwarp();
-    my_terms[lane] = make_double2(termKv, termQ);
+    termsKv[lane] = termKv; termsQ[lane] = termQ;
     __syncwarp();
     {
-      // lanes 0-15 run the KV chain, lanes 16-31 the queue chain (each exact and sequential)
-      const double* col = reinterpret_cast<const double*>(my_terms) + (lane >> 4);
+      // lanes 0-15 run the KV chain, lanes 16-31 the queue chain (each exact and sequential; two terms per 16-byte load)
+      const double2* col = reinterpret_cast<const double2*>(lane < 16 ? termsKv : termsQ);
       double acc = (lane < 16) ? totalSpareKv : totalSpareQueue;
 #pragma unroll
-      for (int l = 0; l < 32; l++) acc = d_add(acc, col[2 * l]);
+      for (int l = 0; l < 16; l++) { const double2 t = col[l]; acc = d_add(d_add(acc, t.x), t.y); }
       const double other = shfl_xor_d(full, acc, 16);
       totalSpareKv = (lane < 16) ? acc : other;
       totalSpareQueue = (lane < 16) ? other : acc;
@@ -381,7 +381,7 @@ __device__ __forceinline__ void sat_model(const SatIn& in, const double* kvp, co
 // order as sat_model, without its chunk loops.
 template <bool DETAIL>
 __device__ __forceinline__ void sat_model_staged(const SatStage* st, const unsigned char* __restrict__ hs_col, const long long m,
-                                                 const SatOut& out, double2* my_terms, SatTally& tally) {
+                                                 const SatOut& out, double* termsKv, double* termsQ, SatTally& tally) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int v0 = st->desc.v0, v1 = st->desc.v1;
@@ -439,14 +439,14 @@ __device__ __forceinline__ void sat_model_staged(const SatStage* st, const unsig
   const bool analysed = cnt > 0;           // (inactive lanes have cnt == 0)
   // ordered accumulation (analyzer.go:86-94): a variant without metrics contributes an exact +0.0
   __syncwarp();
-  my_terms[lane] = make_double2(d_mul(avgKv, (double)ns), d_mul(avgQ, (double)ns));
+  termsKv[lane] = d_mul(avgKv, (double)ns); termsQ[lane] = d_mul(avgQ, (double)ns);
   __syncwarp();
   double totalSpareKv, totalSpareQueue;
   {
-    const double* col = reinterpret_cast<const double*>(my_terms) + (lane >> 4);
+    const double2* col = reinterpret_cast<const double2*>(lane < 16 ? termsKv : termsQ);
     double acc = 0.0;
 #pragma unroll
-    for (int l = 0; l < 32; l++) acc = d_add(acc, col[2 * l]);
+    for (int l = 0; l < 16; l++) { const double2 t = col[l]; acc = d_add(d_add(acc, t.x), t.y); }
     const double other = shfl_xor_d(full, acc, 16);
     totalSpareKv = (lane < 16) ? acc : other;
     totalSpareQueue = (lane < 16) ? other : acc;
@@ -531,49 +531,57 @@ __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SatWarpSmem* ws = reinterpret_cast<SatWarpSmem*>(sat_smem) + warp;
   SatTally tally = {0, 0, 0, 0};
-  const long long gw = (long long)blockIdx.x * SAT_WARPS + warp, tw = (long long)gridDim.x * SAT_WARPS;
-  const long long M = in.n_models;
+  // model indices fit 32 bits (the CSR offsets are int32; the host rejects larger batches)
+  const int gw = blockIdx.x * SAT_WARPS + warp, tw = gridDim.x * SAT_WARPS;
+  const int M = (int)in.n_models;
 
   if (lane == 0) {
     for (int s = 0; s < SAT_NS; s++) sat_mbar_init(&ws->bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  // Geometry (16 bytes: variants [x, y), replicas [z, w)) of the models this warp touches next, carried in registers
-  // from one loop trip to the next so that no descriptor load is consumed in the trip that issues it:
-  //   d0 the model analysed now, d1 the next one, d2 the one whose copies are issued at the end of this trip (SAT_NS = 2
-  //   models ahead), d3 loaded now for the next trip.
-  static_assert(SAT_NS == 2, "the loop below is unrolled for two stages");
+  static_assert(SAT_NS == 2, "stage = trip parity");
+  // Geometry (16 bytes: variants [x, y), replicas [z, w)) is only needed where copies are issued; the model analysed
+  // reads its own from the stage.  `gn` = the model whose copies are issued at the end of this trip (SAT_NS models ahead),
+  // loaded one trip earlier so that no descriptor load is consumed in the trip that issues it.  `staged` / `par`: one bit
+  // per stage — the stage holds a staged model / phase parity of the next wait on its barrier.  All of it lives in
+  // registers (no lambda, nothing by reference).
   const int4 none = make_int4(0, 0, 0, 0);
-  auto geom = [&](long long mm) { return mm < M ? __ldg(reinterpret_cast<const int4*>(desc + mm)) : none; };
-  int4 d0 = geom(gw), d1 = geom(gw + tw), d2 = geom(gw + 2 * tw);
-  // prologue: the first two models; one cp.async group per model, empty or not
-  if (gw < M && sat_staged(d0.x, d0.y, d0.z, d0.w)) sat_issue(in, desc, gw, d0.x, d0.y, d0.z, d0.w, &ws->stage[0], &ws->bar[0]);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  if (gw + tw < M && sat_staged(d1.x, d1.y, d1.z, d1.w)) sat_issue(in, desc, gw + tw, d1.x, d1.y, d1.z, d1.w, &ws->stage[1], &ws->bar[1]);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  unsigned par0 = 0, par1 = 0;    // phase parity of the next wait on each stage
-  // one model out of stage S (a compile-time constant: the stage addresses fold into the instructions)
-  auto step = [&](const int S, unsigned& par, long long m) {
-    const int4 d3 = geom(m + 3 * tw);
-    asm volatile("cp.async.wait_group %0;" ::"n"(SAT_NS - 1) : "memory");   // this model's group is the oldest pending one
-    if (sat_staged(d0.x, d0.y, d0.z, d0.w)) {
-      sat_mbar_wait(&ws->bar[S], par);                           // a model that is not staged never arms its barrier
-      par ^= 1u;
-      __syncwarp();                                               // the other lanes' cp.async data
-      sat_model_staged<DETAIL>(&ws->stage[S], in.var_has_state, m, out, ws->terms, tally);
-    } else {
-      sat_model<DETAIL, false>(in, in.rep_kv, in.rep_queue, 0, m, d0.x, d0.y, out, ws->terms, tally);
-    }
-    __syncwarp();                                                 // every lane is done with stage S before it is refilled
-    const long long m_fill = m + 2 * tw;
-    if (m_fill < M && sat_staged(d2.x, d2.y, d2.z, d2.w)) sat_issue(in, desc, m_fill, d2.x, d2.y, d2.z, d2.w, &ws->stage[S], &ws->bar[S]);
+  unsigned staged = 0, par = 0;
+  {
+    const int4 g0 = gw < M ? __ldg(reinterpret_cast<const int4*>(desc + gw)) : none;
+    const int4 g1 = (long long)gw + tw < M ? __ldg(reinterpret_cast<const int4*>(desc + gw + tw)) : none;
+    // prologue: the first two models; one cp.async group per model, empty or not
+    if (gw < M && sat_staged(g0.x, g0.y, g0.z, g0.w)) { sat_issue(in, desc, gw, g0.x, g0.y, g0.z, g0.w, &ws->stage[0], &ws->bar[0]); staged |= 1u; }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    d0 = d1; d1 = d2; d2 = d3;
-  };
-  for (long long m = gw; m < M; m += 2 * tw) {
-    step(0, par0, m);
-    if (m + tw < M) step(1, par1, m + tw);
+    if ((long long)gw + tw < M && sat_staged(g1.x, g1.y, g1.z, g1.w)) { sat_issue(in, desc, gw + tw, g1.x, g1.y, g1.z, g1.w, &ws->stage[1], &ws->bar[1]); staged |= 2u; }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  int4 gn = (long long)gw + 2LL * tw < M ? __ldg(reinterpret_cast<const int4*>(desc + gw + 2LL * tw)) : none;
+  int S = 0;
+  // (m + 3 tw can pass 2^31 only in the last trips: the look-ahead indices are compared in 64 bits, m itself stays int)
+  for (int m = gw; m < M; S ^= 1) {
+    SatStage* st = &ws->stage[S];
+    unsigned long long* bar = &ws->bar[S];
+    const long long mf = (long long)m + 2LL * tw;                            // the model that takes this stage next
+    const int4 g_after = mf + tw < M ? __ldg(reinterpret_cast<const int4*>(desc + mf + tw)) : none;
+    asm volatile("cp.async.wait_group %0;" ::"n"(SAT_NS - 1) : "memory");   // this model's group is the oldest pending one
+    if ((staged >> S) & 1u) {
+      sat_mbar_wait(bar, (par >> S) & 1u);                                   // a model that is not staged never arms its barrier
+      par ^= 1u << S;
+      __syncwarp();                                                          // the other lanes' cp.async data
+      sat_model_staged<DETAIL>(st, in.var_has_state, m, out, ws->termsKv, ws->termsQ, tally);
+    } else {
+      const int4 g = __ldg(reinterpret_cast<const int4*>(desc + m));
+      sat_model<DETAIL, false>(in, in.rep_kv, in.rep_queue, 0, m, g.x, g.y, out, ws->termsKv, ws->termsQ, tally);
+    }
+    __syncwarp();                                                            // every lane is done with the stage before it is refilled
+    staged &= ~(1u << S);
+    if (mf < M && sat_staged(gn.x, gn.y, gn.z, gn.w)) { sat_issue(in, desc, mf, gn.x, gn.y, gn.z, gn.w, st, bar); staged |= 1u << S; }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    gn = g_after;
+    if ((long long)m + tw >= M) break;
+    m += tw;
   }
   if (out.partials) {
     long long sum_targets = tally.sum_targets;

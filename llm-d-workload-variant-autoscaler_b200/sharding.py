@@ -111,6 +111,27 @@ def gather_candidates(cand: dict, n_servers: int, n_acc: int, rank: int, world: 
     return full
 
 
+class ShardError(RuntimeError):
+    """Raised on EVERY rank when some rank could not size its shard."""
+
+
+def _agree(err, rank: int, world: int, device=None):
+    """All-reduce (MAX) a failure flag; raise on every rank when any rank failed."""
+    bad = 1 if err is not None else 0
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        flag = torch.tensor([bad, rank if bad else -1], dtype=torch.int32, device=device if device is not None else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        bad, who = int(flag[0].item()), int(flag[1].item())
+    else:
+        who = rank
+    if bad:
+        if err is not None:
+            raise ShardError(f"rank {rank}: {err}") from err
+        raise ShardError(f"rank {who} failed to size its shard (this rank, {rank}, was fine)")
+
+
 def solve_sharded(engine, sysd: dict, rank: int, world: int, device=None, shard_fn=None, timings: dict | None = None):
     """Manager.Optimize (pkg/manager/manager.go:21-27) over `world` ranks for either capacity mode: size the rank's
     shard, all-gather the candidates, run the allocator on the merged set.  Every rank returns the global solution.
@@ -130,11 +151,18 @@ def solve_sharded(engine, sysd: dict, rank: int, world: int, device=None, shard_
     shard, idx = shard_fn(sysd, rank, world)
     assert np.array_equal(idx, shard_indices(S, rank, world))
     lap("shard")
-    engine.load_system(shard)
-    engine.calculate()
-    lap("load+calculate")
-    cand = engine.candidates()
-    lap("candidates_d2h")
+    # A rank whose shard fails to load or to size (a limit, out of memory) must not leave the others blocked in the
+    # all-gather: every rank learns the worst status first and all of them raise.
+    err, cand = None, None
+    try:
+        engine.load_system(shard)
+        engine.calculate()
+        lap("load+calculate")
+        cand = engine.candidates()
+        lap("candidates_d2h")
+    except Exception as e:                      # noqa: BLE001 — re-raised below, on every rank
+        err = e
+    _agree(err, rank, world, device)
     full = gather_candidates(cand, S, A, rank, world, device)
     lap("all_gather+merge")
     engine.load_system(sysd)

@@ -143,6 +143,51 @@ def test_sharded_limited_greedy_all_gather_gloo(pkg, oracle):
                 assert np.array_equal(a.view(np.uint8) if a.dtype.kind == "f" else a, b.view(np.uint8) if b.dtype.kind == "f" else b), (policy, r, k)
 
 
+class _FailingEngine(_OracleEngine):
+    def calculate(self):
+        raise RuntimeError("WVA_ERR_LIMIT: one pair over the limit")
+
+
+def _failing_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    pkg_synth = importlib.import_module(PKG + ".synth")
+    sharding = importlib.import_module(PKG + ".sharding")
+    from tests import oracle_lib
+    orc = oracle_lib.load()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        d = _limited_system(pkg_synth, orc, 0, False)
+        eng = _FailingEngine(orc) if rank == 1 else _OracleEngine(orc)
+        try:
+            sharding.solve_sharded(eng, d, rank, world)
+            q.put((rank, "no error"))
+        except sharding.ShardError as e:
+            q.put((rank, str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_solve_raises_on_every_rank_when_one_fails():
+    """a rank whose calculate() raises must not leave the others blocked in the all-gather."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_failing_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert "rank 1" in got[0] and "this rank, 0, was fine" in got[0]
+    assert "WVA_ERR_LIMIT" in got[1]
+
+
 def test_candidate_pack_roundtrip(pkg):
     g = np.random.default_rng(5)
     sh = pkg.sharding

@@ -281,12 +281,7 @@ extern "C" int32_t wva_saturation_run(wva_ctx* ctx, int32_t detail) {
     CK(st.desc.reserve((size_t)st.M * sizeof(SatDesc)));
     SatDesc* d_desc = (SatDesc*)st.desc.p;
     saturation_desc_kernel<<<(unsigned)((st.M + 255) / 256), 256, 0, ctx->stream>>>(st.vin, d_desc);
-    long long blocks = (long long)ctx->sm_count * 3;
-    const long long need_blocks = (st.M + SAT_WARPS - 1) / SAT_WARPS;
-    if (blocks > need_blocks) blocks = need_blocks;
-    auto k = detail ? saturation_kernel<true> : saturation_kernel<false>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SAT_SMEM_BYTES));
-    k<<<(unsigned)blocks, SAT_WARPS * 32, SAT_SMEM_BYTES, ctx->stream>>>(st.vin, w, d_desc);
+    CK(launch_saturation(detail, ctx->sm_count, st.M, st.vin, w, d_desc, ctx->stream));
     ctx->launches += 2;
     CK(cudaGetLastError());
   }

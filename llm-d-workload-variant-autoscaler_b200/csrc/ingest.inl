@@ -86,10 +86,7 @@ static cudaError_t ingest_enqueue(wva_ingest* g, cudaStream_t s) {
   if ((e = cudaMemsetAsync(g->vout.partials, 0, 64, s)) != cudaSuccess) return e;
   if (M > 0) {
     saturation_desc_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(g->vin, g->d_desc);
-    long long blocks = (long long)g->ctx->sm_count * 3;
-    const long long need = (M + SAT_WARPS - 1) / SAT_WARPS;
-    if (blocks > need) blocks = need;
-    saturation_kernel<true><<<(unsigned)blocks, SAT_WARPS * 32, SAT_SMEM_BYTES, s>>>(g->vin, g->vout, g->d_desc);
+    if ((e = launch_saturation(true, g->ctx->sm_count, M, g->vin, g->vout, g->d_desc, s)) != cudaSuccess) return e;
   }
   if ((e = cudaMemcpyAsync(g->h_out.p, g->d_out.p, g->out_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
   return cudaGetLastError();
@@ -184,7 +181,8 @@ extern "C" int32_t wva_ingest_create(wva_ctx* ctx, int64_t n_models, int64_t n_v
   w.partials = (long long*)(dob + q_part); w.var_target = (int*)(dob + q_t); w.var_replica_count = (int*)(dob + q_rc);
   w.var_non_saturated = (int*)(dob + q_ns); w.var_avg_spare_kv = (double*)(dob + q_ak); w.var_avg_spare_queue = (double*)(dob + q_aq);
   w.mod_flags = (unsigned char*)(dob + q_mf); w.mod_total_replicas = (int*)(dob + q_mt);
-  if (cudaFuncSetAttribute(saturation_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SAT_SMEM_BYTES) != cudaSuccess)
+  // (the kernel's shared-memory attribute is set before the capture as well: launch_saturation sets it again, harmlessly)
+  if (cudaFuncSetAttribute(saturation_kernel<true, SAT_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SatWarpSmem) * SAT_WARPS)) != cudaSuccess)
     return fail(WVA_ERR_CUDA);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(WVA_ERR_CUDA);
   // ---- capture the cycle once

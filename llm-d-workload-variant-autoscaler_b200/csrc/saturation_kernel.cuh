@@ -81,7 +81,7 @@ struct alignas(16) SatWarpSmem {
 static_assert(sizeof(SatDesc) == 48 && sizeof(SatStage) % 16 == 0 && offsetof(SatStage, q) % 16 == 0 &&
               offsetof(SatStage, cost) % 16 == 0 && offsetof(SatStage, desc) % 16 == 0 && offsetof(SatWarpSmem, termsKv) % 16 == 0 && offsetof(SatWarpSmem, termsQ) % 16 == 0,
               "alignment");
-constexpr size_t SAT_SMEM_BYTES = sizeof(SatWarpSmem) * SAT_WARPS;
+constexpr int SAT_WARPS_PER_SM = 24;   // resident warps per SM: 24 x 9.2 KB of stages = 221 KB of shared memory
 
 // the two dependent CSR look-ups and the config of every model, done once so that the copy-issuing lane never waits on
 // a dependent load (48 B per model: 1.4 % of the stream)
@@ -101,10 +101,10 @@ __device__ __forceinline__ unsigned sat_smem_addr(const void* p) { return (unsig
 __device__ __forceinline__ void sat_mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sat_smem_addr(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void sat_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sat_smem_addr(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void sat_mbar_expect_tx(unsigned bar_s, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void sat_mbar_wait(unsigned long long* bar, unsigned parity) {
+__device__ __forceinline__ void sat_mbar_wait(unsigned bar_s, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -113,22 +113,22 @@ __device__ __forceinline__ void sat_mbar_wait(unsigned long long* bar, unsigned 
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(sat_smem_addr(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(bar_s), "r"(parity) : "memory");
 }
 // global -> shared, `bytes` a positive multiple of 16, both addresses 16-byte aligned; completes on `bar`
-__device__ __forceinline__ void sat_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+__device__ __forceinline__ void sat_bulk_g2s(unsigned dst_s, const void* src, unsigned bytes, unsigned bar_s) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(sat_smem_addr(dst)), "l"(src), "r"(bytes), "r"(sat_smem_addr(bar)) : "memory");
+               ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar_s) : "memory");
 }
 __device__ __forceinline__ bool sat_staged(int v0, int v1, int r0, int r1) { return r1 - r0 <= SAT_CAP && v1 - v0 <= SAT_VCAP; }
-__device__ __forceinline__ void sat_cp4(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sat_smem_addr(dst)), "l"(src) : "memory");
+__device__ __forceinline__ void sat_cp4(unsigned dst_s, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_s), "l"(src) : "memory");
 }
-__device__ __forceinline__ void sat_cp8(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sat_smem_addr(dst)), "l"(src) : "memory");
+__device__ __forceinline__ void sat_cp8(unsigned dst_s, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_s), "l"(src) : "memory");
 }
-__device__ __forceinline__ void sat_cp16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sat_smem_addr(dst)), "l"(src) : "memory");
+__device__ __forceinline__ void sat_cp16(unsigned dst_s, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
 }
 // Everything one model needs -> a stage (the whole warp calls this).  The two replica arrays — one contiguous range each,
 // 1-2 KB — go through the TMA unit: lane 0 issues two cp.async.bulk copies that complete on the stage's mbarrier (range
@@ -136,23 +136,28 @@ __device__ __forceinline__ void sat_cp16(void* dst, const void* src) {
 // whose sub-arrays are 256-byte padded).  The per-variant values are one element per lane: every lane copies its own with
 // cp.async (no registers, no scoreboard); lanes 0-2 copy the model's descriptor.  The caller commits the cp.async group.
 __device__ __forceinline__ void sat_issue(const SatIn& in, const SatDesc* desc, long long m, int v0, int v1, int r0, int r1,
-                                          SatStage* st, unsigned long long* bar) {
+                                          unsigned st_s, unsigned bar_s) {
+  // st_s / bar_s: shared-space addresses of the stage and of its barrier (computed once per kernel, not per copy)
   const int lane = threadIdx.x & 31;
   if (lane == 0) {
     const int ra = r0 & ~1;
     const unsigned b_rep = (unsigned)((r1 - ra + 1) & ~1) * 8u;
-    sat_mbar_expect_tx(bar, 2 * b_rep);
-    if (b_rep) { sat_bulk_g2s(st->kv, in.rep_kv + ra, b_rep, bar); sat_bulk_g2s(st->q, in.rep_queue + ra, b_rep, bar); }
+    sat_mbar_expect_tx(bar_s, 2 * b_rep);
+    if (b_rep) {
+      sat_bulk_g2s(st_s + (unsigned)offsetof(SatStage, kv), in.rep_kv + ra, b_rep, bar_s);
+      sat_bulk_g2s(st_s + (unsigned)offsetof(SatStage, q), in.rep_queue + ra, b_rep, bar_s);
+    }
   }
   const int v = v0 + lane;
   if (v < v1) {
-    sat_cp4(&st->lo[lane], in.variant_replica_off + v);
-    sat_cp4(&st->cur[lane], in.var_current + v);
-    sat_cp4(&st->des[lane], in.var_desired + v);
-    sat_cp4(&st->pen[lane], in.var_pending + v);
-    sat_cp8(&st->cost[lane], in.var_cost + v);
+    const unsigned l4 = st_s + 4u * lane;
+    sat_cp4(l4 + (unsigned)offsetof(SatStage, lo), in.variant_replica_off + v);
+    sat_cp4(l4 + (unsigned)offsetof(SatStage, cur), in.var_current + v);
+    sat_cp4(l4 + (unsigned)offsetof(SatStage, des), in.var_desired + v);
+    sat_cp4(l4 + (unsigned)offsetof(SatStage, pen), in.var_pending + v);
+    sat_cp8(st_s + 8u * lane + (unsigned)offsetof(SatStage, cost), in.var_cost + v);
   }
-  if (lane < 3) sat_cp16(reinterpret_cast<char*>(&st->desc) + 16 * lane, reinterpret_cast<const char*>(desc + m) + 16 * lane);
+  if (lane < 3) sat_cp16(st_s + (unsigned)offsetof(SatStage, desc) + 16u * lane, reinterpret_cast<const char*>(desc + m) + 16 * lane);
 }
 
 // order-preserving bit pattern of a float64 (-0 == +0; NaN sorts after +inf): costs are compared through it
@@ -524,17 +529,18 @@ __device__ __forceinline__ void sat_model_staged(const SatStage* st, const unsig
   }
 }
 
-template <bool DETAIL>
-__global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in, SatOut out, const SatDesc* __restrict__ desc) {
+template <bool DETAIL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, SAT_WARPS_PER_SM / WARPS) saturation_kernel(SatIn in, SatOut out, const SatDesc* __restrict__ desc) {
   extern __shared__ __align__(16) unsigned char sat_smem[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SatWarpSmem* ws = reinterpret_cast<SatWarpSmem*>(sat_smem) + warp;
   SatTally tally = {0, 0, 0, 0};
   // model indices fit 32 bits (the CSR offsets are int32; the host rejects larger batches)
-  const int gw = blockIdx.x * SAT_WARPS + warp, tw = gridDim.x * SAT_WARPS;
+  const int gw = blockIdx.x * WARPS + warp, tw = gridDim.x * WARPS;
   const int M = (int)in.n_models;
 
+  const unsigned ws_s = sat_smem_addr(ws);       // shared-space address of this warp's area
   if (lane == 0) {
     for (int s = 0; s < SAT_NS; s++) sat_mbar_init(&ws->bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -552,9 +558,9 @@ __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in,
     const int4 g0 = gw < M ? __ldg(reinterpret_cast<const int4*>(desc + gw)) : none;
     const int4 g1 = (long long)gw + tw < M ? __ldg(reinterpret_cast<const int4*>(desc + gw + tw)) : none;
     // prologue: the first two models; one cp.async group per model, empty or not
-    if (gw < M && sat_staged(g0.x, g0.y, g0.z, g0.w)) { sat_issue(in, desc, gw, g0.x, g0.y, g0.z, g0.w, &ws->stage[0], &ws->bar[0]); staged |= 1u; }
+    if (gw < M && sat_staged(g0.x, g0.y, g0.z, g0.w)) { sat_issue(in, desc, gw, g0.x, g0.y, g0.z, g0.w, ws_s, ws_s + (unsigned)offsetof(SatWarpSmem, bar)); staged |= 1u; }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    if ((long long)gw + tw < M && sat_staged(g1.x, g1.y, g1.z, g1.w)) { sat_issue(in, desc, gw + tw, g1.x, g1.y, g1.z, g1.w, &ws->stage[1], &ws->bar[1]); staged |= 2u; }
+    if ((long long)gw + tw < M && sat_staged(g1.x, g1.y, g1.z, g1.w)) { sat_issue(in, desc, gw + tw, g1.x, g1.y, g1.z, g1.w, ws_s + (unsigned)sizeof(SatStage), ws_s + (unsigned)offsetof(SatWarpSmem, bar) + 8u); staged |= 2u; }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   int4 gn = (long long)gw + 2LL * tw < M ? __ldg(reinterpret_cast<const int4*>(desc + gw + 2LL * tw)) : none;
@@ -562,12 +568,12 @@ __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in,
   // (m + 3 tw can pass 2^31 only in the last trips: the look-ahead indices are compared in 64 bits, m itself stays int)
   for (int m = gw; m < M; S ^= 1) {
     SatStage* st = &ws->stage[S];
-    unsigned long long* bar = &ws->bar[S];
+    const unsigned st_s = ws_s + (unsigned)S * (unsigned)sizeof(SatStage), bar_s = ws_s + (unsigned)offsetof(SatWarpSmem, bar) + 8u * S;
     const long long mf = (long long)m + 2LL * tw;                            // the model that takes this stage next
     const int4 g_after = mf + tw < M ? __ldg(reinterpret_cast<const int4*>(desc + mf + tw)) : none;
     asm volatile("cp.async.wait_group %0;" ::"n"(SAT_NS - 1) : "memory");   // this model's group is the oldest pending one
     if ((staged >> S) & 1u) {
-      sat_mbar_wait(bar, (par >> S) & 1u);                                   // a model that is not staged never arms its barrier
+      sat_mbar_wait(bar_s, (par >> S) & 1u);                                   // a model that is not staged never arms its barrier
       par ^= 1u << S;
       __syncwarp();                                                          // the other lanes' cp.async data
       sat_model_staged<DETAIL>(st, in.var_has_state, m, out, ws->termsKv, ws->termsQ, tally);
@@ -577,7 +583,7 @@ __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in,
     }
     __syncwarp();                                                            // every lane is done with the stage before it is refilled
     staged &= ~(1u << S);
-    if (mf < M && sat_staged(gn.x, gn.y, gn.z, gn.w)) { sat_issue(in, desc, mf, gn.x, gn.y, gn.z, gn.w, st, bar); staged |= 1u << S; }
+    if (mf < M && sat_staged(gn.x, gn.y, gn.z, gn.w)) { sat_issue(in, desc, mf, gn.x, gn.y, gn.z, gn.w, st_s, bar_s); staged |= 1u << S; }
     asm volatile("cp.async.commit_group;" ::: "memory");
     gn = g_after;
     if ((long long)m + tw >= M) break;
@@ -593,6 +599,21 @@ __global__ void __launch_bounds__(SAT_WARPS * 32, 3) saturation_kernel(SatIn in,
       if (sum_targets) atomicAdd((unsigned long long*)&out.partials[3], (unsigned long long)sum_targets);
     }
   }
+}
+
+// persistent launch: SAT_WARPS_PER_SM warps per SM in 256-thread blocks, each warp its own two-stage pipeline
+// (one warp per block — block-uniform addresses — was tried and is slower: 1.18 ms vs 0.85 ms on configs[3])
+static inline cudaError_t launch_saturation(bool detail, int sm_count, long long M, const SatIn& vin, const SatOut& w, const SatDesc* d_desc,
+                                            cudaStream_t stream) {
+  long long blocks = (long long)sm_count * (SAT_WARPS_PER_SM / SAT_WARPS);
+  const long long need = (M + SAT_WARPS - 1) / SAT_WARPS;
+  if (blocks > need) blocks = need;
+  const size_t smem = sizeof(SatWarpSmem) * SAT_WARPS;
+  auto k = detail ? saturation_kernel<true, SAT_WARPS> : saturation_kernel<false, SAT_WARPS>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<(unsigned)blocks, SAT_WARPS * 32, smem, stream>>>(vin, w, d_desc);
+  return cudaGetLastError();
 }
 
 }  // namespace wva

@@ -164,7 +164,8 @@ typedef struct wva_timing {
   int64_t overflow_pairs;  /* pairs that took the float64 overflow-rescale slow path  */
   float exchange_ms;       /* NCCL exchange of the last wva_solve / wva_saturation_run on a ctx with a communicator
                               (all-gather of the candidate arena or of the solution, all-reduce of the partials) */
-  int32_t reserved0;
+  int32_t sizer_kernel;    /* which sizer the last wva_calculate ran: 1 warp per pair, 2 lane per pair (head table in
+                              shared memory), 3 lane per pair (table in global memory), 4 pool sizer; 0 nothing to size */
   int64_t greedy_heap_pushes; /* entries the last limited wva_solve pushed into the re-insertion heap (greedy.go:143-163) */
   int64_t greedy_events;      /* head entries the last limited wva_solve processed (greedy.go:112-165 loop trips)    */
 } wva_timing;

@@ -73,7 +73,7 @@ class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("calculate_ms", C.c_float), ("solve_ms", C.c_float),
                 ("grid_ms", C.c_float), ("saturation_ms", C.c_float), ("limit_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("chain_solves", C.c_int64), ("chain_states", C.c_int64),
-                ("overflow_pairs", C.c_int64), ("exchange_ms", C.c_float), ("reserved0", C.c_int32),
+                ("overflow_pairs", C.c_int64), ("exchange_ms", C.c_float), ("sizer_kernel", C.c_int32),
                 ("greedy_heap_pushes", C.c_int64), ("greedy_events", C.c_int64)]
 
 

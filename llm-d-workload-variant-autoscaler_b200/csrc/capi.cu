@@ -490,7 +490,9 @@ int32_t wva_calculate(wva_ctx* ctx) {
                            : (n_pairs <= (unsigned long long)ctx->sm_count * 380) ? 5 : 2;
     // large systems: the pool sizer (sizer_pool_kernel.cuh) regroups the pending solves of 1024 pairs per SM by
     // length every time a warp goes back for work (88-92 % live lane-steps instead of 49-62 %)
-    const bool pool_auto = !ctx->force_lane_sizer && n_pairs > (unsigned long long)ctx->sm_count * 4096 && nmax <= 4096;
+    // measured (B200, N = 256, pairs -> pool / lane ms): 96 k 16.0 / 16.5, 200 k 25.4 / 28.2, 400 k 40.7 / 52.6, 800 k 73.9 / 98.6,
+    // 1.6 M 140 / 190, 3.2 M 271 / 372
+    const bool pool_auto = !ctx->force_lane_sizer && n_pairs > (unsigned long long)ctx->sm_count * 640 && nmax <= 4096;
     if (pool_auto || (ctx->force_lane_sizer && ctx->lane_sizer_mode == 6)) {
       const int P = POOL_PMAX;
       const int row_stride = (nmax + 31) & ~31;
@@ -505,6 +507,7 @@ int32_t wva_calculate(wva_ctx* ctx) {
       ctx->launches++;
       cudaError_t pe = cudaGetLastError();
       if (pe != cudaSuccess) { ctx->last_error = std::string("pool sizer launch: ") + cudaGetErrorString(pe); return WVA_ERR_CUDA; }
+      ctx->timing.sizer_kernel = 4;
       goto sizer_done;
     }
     const unsigned long long n_items = (ctx->lane_sizer_mode >= 4) ? 2 * n_pairs : n_pairs;
@@ -524,9 +527,11 @@ int32_t wva_calculate(wva_ctx* ctx) {
       if (warp_tab * 8 <= 48 * 1024) {
         int per_sm = (int)(SMEM_PER_SM / (warp_tab * 8 + 1024)); if (per_sm > 6) per_sm = 6; if (per_sm < 1) per_sm = 1;
         e = launch_sizer_warp<8>(ctx, ctx->sm_count * per_sm, warp_tab * 8, n_pairs, nmax, d_ovf);
+        ctx->timing.sizer_kernel = 1;
       } else {
         int per_sm = (int)(SMEM_PER_SM / (warp_tab * 4 + 1024)); if (per_sm > 8) per_sm = 8; if (per_sm < 1) per_sm = 1;
         e = launch_sizer_warp<4>(ctx, ctx->sm_count * per_sm, warp_tab * 4, n_pairs, nmax, d_ovf);
+        ctx->timing.sizer_kernel = 1;
       }
     } else
     // Head table placement (measured, B200, 320 k pairs): N = 256 leaves 192 lanes per SM in shared memory (1.5 warps per
@@ -535,6 +540,7 @@ int32_t wva_calculate(wva_ctx* ctx) {
     if (best_per_sm >= 1 && ctx->table_mode != 2 && (ctx->table_mode == 1 || best_threads * best_per_sm > 256 || n_pairs <= (unsigned long long)ctx->sm_count * 512)) {
       int blocks = ctx->sm_count * best_per_sm;
       size_t smem = per_lane * best_threads;
+      ctx->timing.sizer_kernel = 2;
       switch (best_threads) {
         case 256: e = launch_sizer<256, true>(ctx, blocks, smem, n_pairs, nmax, nullptr, d_ovf); break;
         case 192: e = launch_sizer<192, true>(ctx, blocks, smem, n_pairs, nmax, nullptr, d_ovf); break;
@@ -543,6 +549,7 @@ int32_t wva_calculate(wva_ctx* ctx) {
       }
     } else {
       int blk = ctx->sm_count * 2;
+      ctx->timing.sizer_kernel = 3;
       CK(ctx->gtab.reserve((size_t)blk * 256 * per_lane));
       e = launch_sizer<256, false>(ctx, blk, 0, n_pairs, nmax, (float*)ctx->gtab.p, d_ovf);
     }

@@ -1,7 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu -p no:cacheprovider -x -k "saturation or ingest or golden" > gpurun_out/s27_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s27_pytest.log
-tail -2 gpurun_out/s27_pytest.log
-timeout 300 python tools/perf_sat.py 1000000 12 2> gpurun_out/s27_sat.err | cut -c1-230
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:saturation_kernel -s 3 -c 1 -f -o gpurun_out/r2_sat python tools/perf_sat.py 1000000 4 > gpurun_out/s27_ncu.log 2>&1
-ls -la gpurun_out/r2_sat.ncu-rep
+for sc in 0.03 0.0625 0.125 0.25 0.5; do timeout 300 python tools/perf_sizer_full.py $sc 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['pairs'], {k:(round(min(v['ms']),2), v['same']) for k,v in d.items() if isinstance(v,dict)})"; done

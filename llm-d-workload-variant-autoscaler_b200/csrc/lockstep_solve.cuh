@@ -221,7 +221,11 @@ __device__ __forceinline__ void p2_chunk(P2 (&b)[NC], const double (&lam)[NC], c
 // __noinline__ wrapper below so that one copy of the unrolled loops stays in the instruction cache.
 template <int NC, class Tab>
 __device__ __forceinline__ void lockstep_solve_inl(const PairModel& m, const Tab& tab, const float* lambda,
-                                                   const bool* active, SolveStats* st, int& states, bool& bad) {
+                                                   const bool* active, SolveStats* st, int& states_out, bool& bad_out) {
+  // (kept in registers here: the reference parameters live in the caller's local memory when this is not inlined, and a
+  //  load-add-store per chunk on them was 10 % of the pool sizer's stall samples)
+  int states;
+  bool bad;
   constexpr int CH = 16 / NC;                          // states per unrolled chunk (per chain)
   const unsigned full = 0xffffffffu;
   const int K = m.K, N = m.N, NH = N - 1;
@@ -430,6 +434,8 @@ __device__ __forceinline__ void lockstep_solve_inl(const PairModel& m, const Tab
     float w = f_sub(s.avgRespTime, s.avgServTime);
     s.avgWaitTime = (w < 0.0f) ? 0.0f : w;
   }
+  states_out = states;
+  bad_out = bad;
 }
 
 template <int NC, class Tab>

@@ -14,7 +14,7 @@
 #include "saturation_kernel.cuh"
 #include "limiter_kernel.cuh"
 #include "pipeline_v2_kernel.cuh"
-#include "greedy_kernel.cuh"
+#include "overflow_slow_kernel.cuh"
 #include "greedy_solve.cuh"
 #include "greedy_sweep.cuh"
 #include "mm1k_kernel.cuh"

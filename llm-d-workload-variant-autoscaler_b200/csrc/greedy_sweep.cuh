@@ -153,6 +153,13 @@ __global__ void __launch_bounds__(256) gsw_multi_kernel(GSweepWs g, int n) {
   if (multi || open) g.ev[i].meta = m | ((unsigned)GE_MULTI << 8);
 }
 
+// cycle counters of the sweep's phases (debug line of run_solve_greedy_sweep): compiled in with -DWVA_SWEEP_PROFILE only —
+// the reads themselves cost ~10 % of the kernel
+#ifdef WVA_SWEEP_PROFILE
+#define GSW_CLK() clock64()
+#else
+#define GSW_CLK() 0ll
+#endif
 constexpr int GSW_SLOTS = 4;
 constexpr int GSW_ALIVE_WORDS = 36 * 1024; // alive bits for up to 1 179 648 entries in shared memory (144 KB)
 constexpr int GSW_TIE_CAP = 1024;          // events of a tie group staged in shared memory at a time
@@ -401,13 +408,13 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
   const unsigned lt = (1u << lane) - 1u;
   const int n_ev = *g.n_events;
   const int S = s.n_servers;
-  for (int t = lane; t < s.n_types; t += 32) avail[t] = s.type_count[t];          // greedy.go:38-39
+  for (int t = lane; t < GSW_AVAIL; t += 32) avail[t] = t < s.n_types ? s.type_count[t] : 0;   // greedy.go:38-39
   for (int k = lane; k < (S + 31) / 32; k += 32) alive[k] = 0xffffffffu;
   __syncwarp();
   GSweepState z = {0, 0, 0, 0, 0, 0, 0};
   int group_un0 = 0;
   long long n_batches = 0, n_rounds = 0, n_seq = 0, n_tie = 0, cyc_be = 0, cyc_tie = 0, n_unalloc_be = 0;
-  const long long cyc0 = clock64();
+  const long long cyc0 = GSW_CLK();
 
   // event stream: blocks of GSW_BLOCK records copied asynchronously into a ring of GSW_SLOTS slots; while block b is
   // read, blocks b+1 .. b+GSW_SLOTS-1 are in flight.  One commit group per block (empty past the end of the list).
@@ -417,10 +424,12 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
   int pos = 0;
   int checked_blk = -1;
   bool nothing_fits = false;
-  long long n_survivors = -1;
+  int pf_blk = -1;
+  unsigned long long pf0 = ~0ull, pf1 = ~0ull;
+  long long n_survivors = -1, n_skip128 = 0;
   long long cyc_ring = 0, cyc_dead = 0, cyc_fast = 0, cyc_slow = 0, cyc_chk = 0;
   while (pos < n_ev) {
-    const long long tc0 = clock64();
+    const long long tc0 = GSW_CLK();
     // Once no remaining event of any type can fit (capacities only shrink, greedy.go:143-145; bestEffort only takes),
     // every entry still in the queue ends unallocated.  Policy None (bestEffort is a no-op): stop.  The other policies:
     // what is left of the sweep only fixes the ORDER of the unallocated list, and bestEffort gives nothing to an entry
@@ -430,11 +439,22 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
     // priority, so removing entries cannot merge two priority groups of makePriorityGroups, greedy.go:321-341).
     if (!nothing_fits && pos / GSW_BLOCK != checked_blk) {
       checked_blk = pos / GSW_BLOCK;
-      bool can = false;
-      for (int t = lane; t < s.n_types; t += 32) {
-        const unsigned long long mn = g.blk_min[(size_t)checked_blk * s.n_types + t];
-        can = can || (mn != ~0ull && (unsigned long long)avail[t] >= mn && avail[t] >= 0);
+      // (the row of the NEXT block is fetched now and used at the next check: no load is consumed where it is issued;
+      //  n_types <= GSW_AVAIL = 64: two values per lane)
+      const int T = s.n_types;
+      unsigned long long m0, m1;
+      if (pf_blk == checked_blk) { m0 = pf0; m1 = pf1; }
+      else {
+        m0 = lane < T ? g.blk_min[(size_t)checked_blk * T + lane] : ~0ull;
+        m1 = lane + 32 < T ? g.blk_min[(size_t)checked_blk * T + lane + 32] : ~0ull;
       }
+      pf_blk = checked_blk + 1;
+      if (pf_blk <= n_ev / GSW_BLOCK) {
+        pf0 = lane < T ? g.blk_min[(size_t)pf_blk * T + lane] : ~0ull;
+        pf1 = lane + 32 < T ? g.blk_min[(size_t)pf_blk * T + lane + 32] : ~0ull;
+      } else pf_blk = -1;
+      const bool can = (m0 != ~0ull && avail[lane] >= 0 && (unsigned long long)avail[lane] >= m0) ||
+                       (m1 != ~0ull && avail[lane + 32] >= 0 && (unsigned long long)avail[lane + 32] >= m1);
       if (!__any_sync(full, can)) {
         if (policy == 0) break;
         nothing_fits = true;
@@ -462,7 +482,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
         if (survivors == 0) break;
       }
     }
-    const long long tc1 = clock64(); cyc_chk += tc1 - tc0;
+    const long long tc1 = GSW_CLK(); cyc_chk += tc1 - tc0;
     const int rel = pos - origin;
     const int b = rel / GSW_BLOCK;
     if (b != cur_block) {
@@ -484,10 +504,21 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
       __syncwarp();
       cur_block = b;
     }
-    const long long tc2 = clock64(); cyc_ring += tc2 - tc1;
+    const long long tc2 = GSW_CLK(); cyc_ring += tc2 - tc1;
     n_batches++;
     const GEvent* blk = ring + (size_t)(b % GSW_SLOTS) * GSW_BLOCK;
     const int in_blk = rel % GSW_BLOCK;
+    // most events of the stream belong to entries that already left the queue: 128 of them are checked at once (their
+    // entry's alive bit, a priority boundary), and skipped together when nothing is left of them
+    if ((in_blk & 127) == 0 && in_blk + 128 <= GSW_BLOCK && pos + 128 <= n_ev) {
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int2 hd = *reinterpret_cast<const int2*>(&blk[in_blk + 32 * q + lane]);        // srv, meta
+        any = any || gsw_alive(alive, hd.x) || (!delayed && (ge_flags((unsigned)hd.y) & GE_NEWPRIO));
+      }
+      if (!__any_sync(full, any)) { pos += 128; n_batches += 3; n_skip128++; cyc_dead += GSW_CLK() - tc2; continue; }
+    }
     const int nvalid = min(min(32, GSW_BLOCK - in_blk), n_ev - pos);
     const bool valid = lane < nvalid;
     GEvent me; me.srv = -1; me.meta = 0; me.cnt = 0;
@@ -499,7 +530,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
     // without a priority boundary) costs one shared-memory look-up and a vote
     const bool al0 = valid && gsw_alive(alive, me.srv);
     const unsigned am0 = __ballot_sync(full, al0);
-    if (!am0 && !npm) { pos += nvalid; cyc_dead += clock64() - tc2; continue; }
+    if (!am0 && !npm) { pos += nvalid; cyc_dead += GSW_CLK() - tc2; continue; }
     // lanes of the same entry (only needed when two or more events of the batch are alive)
     const unsigned peers = (am0 & (am0 - 1)) ? __match_any_sync(full, me.srv) : (1u << lane);
     // ---- fast path: no alive leader of a multi-leader tie group and no priority boundary in the batch.
@@ -515,6 +546,8 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
       if (!multi_alive && !npm) {
         unsigned cand = __ballot_sync(full, al && (type < 0 || myavail >= me.cnt));
         unsigned took = 0;
+        // (taking all first candidates at once when their demands fit together — match.any + a segmented reduce.add — was
+        //  measured slower than this pass: 3-4 candidates per batch, and the per-type groups serialise the reduction)
         while (cand) {
           const int F = __ffs(cand) - 1;
           cand &= cand - 1;
@@ -554,7 +587,7 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
         n_rounds++;
         __syncwarp();
         pos += nvalid;
-        cyc_fast += clock64() - tc2;
+        cyc_fast += GSW_CLK() - tc2;
         continue;
       }
     }
@@ -597,9 +630,9 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
         // (greedy.go:96-103) on the entries it left unallocated, in the order they were exhausted
         npm &= ~(1u << first);
         if (z.n_un > group_un0) {
-          const long long c0 = clock64();
+          const long long c0 = GSW_CLK();
           g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy, be_stage);
-          cyc_be += clock64() - c0; n_unalloc_be += z.n_un - group_un0;
+          cyc_be += GSW_CLK() - c0; n_unalloc_be += z.n_un - group_un0;
         }
         group_un0 = z.n_un;
         __syncwarp();
@@ -620,10 +653,10 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
         const unsigned others = __ballot_sync(full, al && (fl & GE_LEADER)) & span;
         if (!ends_here || others) {
           n_tie++;
-          const long long c0 = clock64();
+          const long long c0 = GSW_CLK();
           int np = gsw_tie_group_staged(w, g, avail, alive, z, pos + first, n_ev, tie_ev, tie_dyn);
           if (np == -2) np = gsw_tie_group(w, g, avail, alive, z, pos + first, n_ev);
-          cyc_tie += clock64() - c0;
+          cyc_tie += GSW_CLK() - c0;
           if (np >= 0) { jump = np; break; }
         }
       }
@@ -641,16 +674,16 @@ __global__ void __launch_bounds__(32, 1) gsw_sweep_kernel(SysView s, GreedyWs w,
     } else {
       pos += nvalid;
     }
-    cyc_slow += clock64() - tc2;
+    cyc_slow += GSW_CLK() - tc2;
   }
   __syncwarp();
   // the last group's (or, delayed, the whole list's) best effort
   if (z.n_un > group_un0) {
-    const long long c0 = clock64();
+    const long long c0 = GSW_CLK();
     g_best_effort(s, w, avail, w.unalloc + group_un0, z.n_un - group_un0, policy, be_stage);
-    cyc_be += clock64() - c0; n_unalloc_be += z.n_un - group_un0;
+    cyc_be += GSW_CLK() - c0; n_unalloc_be += z.n_un - group_un0;
   }
-  if (lane == 0) { w.stats[8] = cyc_be; w.stats[9] = cyc_tie; w.stats[10] = clock64() - cyc0; w.stats[11] = n_unalloc_be; w.stats[12] = z.d_fb; w.stats[13] = z.d_nact; w.stats[14] = z.d_maxact; w.stats[15] = z.d_fbev; w.stats[16] = cyc_chk; w.stats[17] = cyc_ring; w.stats[18] = cyc_dead; w.stats[19] = cyc_fast; w.stats[20] = cyc_slow; w.stats[21] = n_survivors; }
+  if (lane == 0) { w.stats[8] = cyc_be; w.stats[9] = cyc_tie; w.stats[10] = GSW_CLK() - cyc0; w.stats[11] = n_unalloc_be; w.stats[12] = z.d_fb; w.stats[13] = z.d_nact; w.stats[14] = z.d_maxact; w.stats[15] = z.d_fbev; w.stats[16] = cyc_chk; w.stats[17] = cyc_ring; w.stats[18] = cyc_dead; w.stats[19] = cyc_fast; w.stats[20] = cyc_slow; w.stats[21] = n_survivors; w.stats[23] = n_skip128; }
   if (lane == 0) { w.stats[0] = 0; w.stats[1] = z.n_active; w.stats[2] = n_batches; w.stats[3] = n_rounds; w.stats[4] = n_seq; w.stats[5] = n_tie; w.stats[6] = pos; w.stats[7] = n_ev; }
 }
 
@@ -720,13 +753,13 @@ static inline int32_t run_solve_greedy_sweep(const SysView& s, const CandView& c
   greedy_finalize_kernel<<<(unsigned)((S + 255) / 256), 256, 0, stream>>>(s, c, o, w);
   *launches += 2;
   if (stats_out) {
-    long long h[24];
-    if (cudaMemcpyAsync(h, w.stats, 192, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
+    long long h[25];
+    if (cudaMemcpyAsync(h, w.stats, 200, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WVA_ERR_CUDA;
     if (cudaStreamSynchronize(stream) != cudaSuccess) return WVA_ERR_CUDA;
     stats_out[0] = h[0]; stats_out[1] = h[1];
     if (getenv("WVA_SIZER_DEBUG"))
-      fprintf(stderr, "greedy sweep: alive events %lld, batches %lld, rounds %lld, sequential events %lld, tie-group calls %lld, stopped at %lld of %lld; cycles: best effort %lld (%lld entries), tie groups %lld, kernel %lld; tie groups: %lld over the staging size (%lld events), alive leaders %lld (max %lld); loop cycles: early-exit check %lld, ring %lld, dead batches %lld, fast path %lld, slow path %lld; entries swept on after nothing fits: %lld\n",
-              h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[11], h[9], h[10], h[12], h[15], h[13], h[14], h[16], h[17], h[18], h[19], h[20], h[21]);
+      fprintf(stderr, "greedy sweep: alive events %lld, batches %lld, rounds %lld, sequential events %lld, tie-group calls %lld, stopped at %lld of %lld; cycles: best effort %lld (%lld entries), tie groups %lld, kernel %lld; tie groups: %lld over the staging size (%lld events), alive leaders %lld (max %lld); loop cycles: early-exit check %lld, ring %lld, dead batches %lld, fast path %lld, slow path %lld; entries swept on after nothing fits: %lld; 128-event skips %lld\n",
+              h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[11], h[9], h[10], h[12], h[15], h[13], h[14], h[16], h[17], h[18], h[19], h[20], h[21], h[23]);
   }
   return cudaGetLastError() == cudaSuccess ? WVA_OK : WVA_ERR_CUDA;
 }

@@ -1,7 +1,5 @@
-// greedy_kernel.cuh — device side of the slow exact paths:
-//   (1) overflow_slow_kernel: CreateAllocation for the rare pairs whose chain overflows
-//       float64 (literal stored-p[] algorithm, one thread per pair);
-//   (2) Solver.SolveGreedy lives in greedy_solve.cuh.
+// overflow_slow_kernel.cuh — device side of the slow exact path: CreateAllocation for the rare pairs whose chain
+// overflows float64 (literal stored-p[] algorithm with the reference's rescale, one thread per pair).
 #pragma once
 #include "wva_core.cuh"
 #include "solve_kernels.cuh"

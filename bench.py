@@ -171,14 +171,20 @@ def _sample_system(n_servers):
 
 
 _ONE_THREAD = None
+_EFF = None
 
 
 def cpu_reference_leg(target_seconds: float, fixed_sample: int = 0):
     """The reference algorithm (oracle port: the reference is Go and no Go toolchain exists on the box) on a bounded
     sample of the same workload: first one thread on a few servers (also the calibration), then every usable thread on a
     sample sized for ~target_seconds."""
+    # before libgomp starts: with OMP_PROC_BIND set it pins the calling thread to its first place, and the affinity mask
+    # read afterwards would be that one core (final1 evidence run: "2 pinned threads" in the reference arm)
+    global _EFF
+    if _EFF is None:
+        _EFF = effective_cores()
+    eff, aff, quota = _EFF
     orc = _oracle()
-    eff, aff, quota = effective_cores()
     global _ONE_THREAD
     if _ONE_THREAD is None:
         _ONE_THREAD = _cpu_step(orc, _sample_system(4), 1)
@@ -380,6 +386,7 @@ def main():
         barrier()
         for _ in range(max(args.steps, 5)):
             flush.zero_()
+            torch.cuda.synchronize()      # the flush runs on torch's stream, the kernel on the library's: no overlap
             eng.saturation_run(False)
             t = eng.timing()
             ks.append(t["saturation_ms"]); xs.append(t["exchange_ms"])

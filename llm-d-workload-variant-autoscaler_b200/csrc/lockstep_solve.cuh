@@ -25,12 +25,14 @@ namespace wva {
 
 // head-table accessors -----------------------------------------------------------------------------
 struct WarpTable {   // one table per warp in shared memory: (mu_n, ~1/mu_n) as float64 pairs, broadcast reads
+  static constexpr int kChunk = 16;
   const double2* t;
   __device__ __forceinline__ void load(int n, double& mu, double& r) const { double2 v = t[n]; mu = v.x; r = v.y; }
   __device__ __forceinline__ double mu_at(int n) const { return t[n].x; }
   __device__ __forceinline__ void prepare(int) const {}
 };
 struct LaneTable {   // one float32 column per lane ([n][thread], bank = lane); 1/mu refined on the fly
+  static constexpr int kChunk = 16;
   const float* t;
   int stride;
   __device__ __forceinline__ void load(int n, double& mu, double& r) const {
@@ -44,6 +46,10 @@ struct LaneTable {   // one float32 column per lane ([n][thread], bank = lane); 
 // cp.async (row by row: each row a coalesced 128-byte access, no registers, no scoreboard) while the lanes work on
 // tile k, so the only exposed latency is the first tile of a pass.
 struct TileTable {
+#ifndef WVA_TILE_CHUNK
+#define WVA_TILE_CHUNK 16
+#endif
+  static constexpr int kChunk = WVA_TILE_CHUNK;   // states per unrolled chunk of the solver (code size vs loop overhead)
   const float* rows;      // base of the CTA's rows
   int row_stride;         // floats per row (a multiple of 32, >= N)
   int slot;               // this lane's row (any valid row for an idle lane)
@@ -226,7 +232,7 @@ __device__ __forceinline__ void lockstep_solve_inl(const PairModel& m, const Tab
   //  load-add-store per chunk on them was 10 % of the pool sizer's stall samples)
   int states;
   bool bad;
-  constexpr int CH = 16 / NC;                          // states per unrolled chunk (per chain)
+  constexpr int CH = Tab::kChunk / NC;                 // states per unrolled chunk (per chain)
   const unsigned full = 0xffffffffu;
   const int K = m.K, N = m.N, NH = N - 1;
   const double mu_l = m.mu_last, r_l = m.r_last;

@@ -276,11 +276,10 @@ extern "C" int32_t wva_saturation_run(wva_ctx* ctx, int32_t detail) {
   CK(cudaMemsetAsync(w.partials, 0, 64, ctx->stream));
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   if (st.M > 0) {
-    // per-model descriptors (the two dependent CSR look-ups), then the streaming kernel: persistent CTAs, three per SM,
-    // every warp its own cp.async.bulk pipeline (saturation_kernel.cuh)
-    CK(st.desc.reserve((size_t)st.M * sizeof(SatDesc)));
+    // per-model descriptors + group geometry (the dependent CSR look-ups), then the streaming kernel: one persistent CTA
+    // per SM, every warp its own cp.async.bulk pipeline over groups of consecutive models (saturation_kernel.cuh)
+    CK(st.desc.reserve(sat_desc_bytes(st.M)));
     SatDesc* d_desc = (SatDesc*)st.desc.p;
-    saturation_desc_kernel<<<(unsigned)((st.M + 255) / 256), 256, 0, ctx->stream>>>(st.vin, d_desc);
     CK(launch_saturation(detail, ctx->sm_count, st.M, st.vin, w, d_desc, ctx->stream));
     ctx->launches += 2;
     CK(cudaGetLastError());

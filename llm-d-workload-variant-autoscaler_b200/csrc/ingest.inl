@@ -85,7 +85,6 @@ static cudaError_t ingest_enqueue(wva_ingest* g, cudaStream_t s) {
   }
   if ((e = cudaMemsetAsync(g->vout.partials, 0, 64, s)) != cudaSuccess) return e;
   if (M > 0) {
-    saturation_desc_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(g->vin, g->d_desc);
     if ((e = launch_saturation(true, g->ctx->sm_count, M, g->vin, g->vout, g->d_desc, s)) != cudaSuccess) return e;
   }
   if ((e = cudaMemcpyAsync(g->h_out.p, g->d_out.p, g->out_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
@@ -149,7 +148,7 @@ extern "C" int32_t wva_ingest_create(wva_ctx* ctx, int64_t n_models, int64_t n_v
   g->scan_tmp_bytes = tb;
   Layout W;
   const size_t w_cnt = W.take((V + 2) * 4), w_vro = W.take((V + 2) * 4), w_rk = W.take(S * 8 + 16), w_rq = W.take(S * 8 + 16),
-               w_rs = W.take(S * 4), w_desc = W.take(M * sizeof(SatDesc)), w_tmp = W.take(tb + 256);
+               w_rs = W.take(S * 4), w_desc = W.take(sat_desc_bytes(M)), w_tmp = W.take(tb + 256);
   if (g->d_work.reserve(W.off + 256) != cudaSuccess) return fail(WVA_ERR_NOMEM);
   char* dw = (char*)g->d_work.p;
   if (cudaMemsetAsync(dw, 0, g->d_work.cap, ctx->stream) != cudaSuccess) return fail(WVA_ERR_CUDA);   // cnt[V] = 0: the scan's extra element
@@ -182,8 +181,7 @@ extern "C" int32_t wva_ingest_create(wva_ctx* ctx, int64_t n_models, int64_t n_v
   w.var_non_saturated = (int*)(dob + q_ns); w.var_avg_spare_kv = (double*)(dob + q_ak); w.var_avg_spare_queue = (double*)(dob + q_aq);
   w.mod_flags = (unsigned char*)(dob + q_mf); w.mod_total_replicas = (int*)(dob + q_mt);
   // (the kernel's shared-memory attribute is set before the capture as well: launch_saturation sets it again, harmlessly)
-  if (cudaFuncSetAttribute(saturation_kernel<true, SAT_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SatWarpSmem) * SAT_WARPS)) != cudaSuccess)
-    return fail(WVA_ERR_CUDA);
+  if (sat_prepare_attributes() != cudaSuccess) return fail(WVA_ERR_CUDA);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(WVA_ERR_CUDA);
   // ---- capture the cycle once
   if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail(WVA_ERR_CUDA);

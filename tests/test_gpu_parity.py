@@ -580,6 +580,60 @@ def test_saturation_ragged(pkg, engine, oracle):
     assert g["var_target"].size == 0 and (g["partials"] == 0).all()
 
 
+def _ragged_groups_batch(pkg, stream):
+    """A batch that drives every branch of the grouped staging (saturation_kernel.cuh): models of 0 .. 40 variants (a model
+    of more than 32 variants makes its whole group take the general path), variants of 0 .. 90 replicas (more than 64: the
+    staged group falls back; many long variants: the group exceeds the stage), an odd model count (partial last group),
+    variant ranges that start at every residue mod 4 and replica ranges at both parities."""
+    g = np.random.default_rng(stream)
+    M = 203
+    nv = g.integers(1, 33, M)
+    nv[g.random(M) < 0.05] = 0
+    nv[[17, 118]] = 40
+    V = int(nv.sum())
+    nr = g.integers(0, 9, V)
+    nr[g.random(V) < 0.01] = 90                     # > SAT_MAXCNT
+    first = np.concatenate([[0], np.cumsum(nv)[:-1]])
+    for m in (40, 41, 90):                          # long variants everywhere: the group does not fit a stage
+        nr[first[m]:first[m] + nv[m]] = 30
+    d = pkg.synth.saturation_batch(1, 1, stream=stream)
+    mvo = np.zeros(M + 1, np.int64); np.cumsum(nv, out=mvo[1:])
+    vro = np.zeros(V + 1, np.int64); np.cumsum(nr, out=vro[1:])
+    P = int(vro[-1])
+    kv = g.beta(2.0, 3.0, P); kv[g.random(P) < 0.1] = g.uniform(0.8, 1.0, int((g.random(P) < 0.1).sum()) or 1)[0]
+    cur = nr.astype(np.int32).copy()
+    des = np.zeros(V, np.int32); tv = g.integers(0, V, 12); des[tv] = cur[tv] + 1
+    hs = np.ones(V, np.uint8); hs[g.random(V) < 0.03] = 0
+    d.update(n_models=M, n_variants=V, n_replicas=P, model_variant_off=mvo.astype(np.int32),
+             variant_replica_off=vro.astype(np.int32), rep_kv=kv.astype(np.float64),
+             rep_queue=g.poisson(2.0, P).astype(np.int64), var_cost=g.choice([10.0, 20.0, 20.0, 35.5, 80.0], V),
+             var_current=cur, var_desired=des, var_pending=(g.random(V) < 0.05).astype(np.int32), var_has_state=hs,
+             cfg_kv_threshold=g.choice([0.8, 0.7], M), cfg_queue_threshold=g.choice([5.0, 3.0], M),
+             cfg_kv_trigger=np.full(M, 0.1), cfg_queue_trigger=g.choice([3.0, 1.0], M))
+    return d
+
+
+@pytest.mark.parametrize("group", [1, 2, 4])
+def test_saturation_grouped_staging_edges(pkg, engine, oracle, group, monkeypatch):
+    """Every group size of the staged kernel (WVA_SAT_GROUP; 2 is the default) on a batch that mixes staged groups,
+    groups that fall back to the general path for each of the three reasons, and a partial last group."""
+    monkeypatch.setenv("WVA_SAT_GROUP", str(group))
+    d = _ragged_groups_batch(pkg, 500 + group)
+    o = oracle.saturation_v1(d)
+    g = engine.saturation_v1(d)
+    for k in ("var_target", "var_replica_count", "var_non_saturated", "var_max_queue", "rep_saturated",
+              "mod_total_replicas", "mod_non_saturated", "mod_flags", "partials"):
+        assert np.array_equal(g[k], o[k]), k
+    for k in ("var_max_kv", "var_avg_spare_kv", "var_avg_spare_queue", "mod_avg_spare_kv", "mod_avg_spare_queue"):
+        assert _bit_equal(g[k], o[k]), k
+    engine.saturation_upload(d)
+    engine.saturation_run(detail=False)
+    r = engine.saturation_fetch(detail=False)
+    for k in ("var_target", "mod_flags", "partials"):
+        assert np.array_equal(r[k], o[k]), k
+    assert (o["mod_flags"] & 1).any() and (o["mod_flags"] & 2).any() and (o["mod_flags"] & 4).any()
+
+
 # ---- limiter -------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("D,T,stream,tight", [(5000, 8, 6, 0.6), (1, 1, 61, 0.5), (3000, 3, 62, 0.0),
                                               (4000, 16, 63, 1.5)])

@@ -508,7 +508,10 @@ __device__ __forceinline__ bool sat_group_staged(SatWarpSmem<G>* ws, const unsig
     double avgKv = 0.0, avgQ = 0.0;
     if (ns[j] > 0) {                                                       // :190-193, one reciprocal for both quotients
       const double nd = (double)ns[j];
-      if ((in_window(sumKv[j]) || sumKv[j] == 0.0) && (in_window(sumQ[j]) || sumQ[j] == 0.0)) {
+      // (a sum over ns > 0 non-saturated replicas is a sum of strictly positive terms — kv < kvThr and queue < qThr,
+      // and the difference of two distinct doubles is never zero — so it is positive or NaN, never 0: the window test
+      // alone decides; ns <= SAT_MAXCNT < 2^24)
+      if (in_window(sumKv[j]) && in_window(sumQ[j])) {
         const double rr = rcp_f32den((float)ns[j], nd);
         avgKv = div_f32den(sumKv[j], nd, rr); avgQ = div_f32den(sumQ[j], nd, rr);
       } else { avgKv = d_div(sumKv[j], nd); avgQ = d_div(sumQ[j], nd); }
@@ -609,10 +612,12 @@ __device__ __forceinline__ bool sat_group_staged(SatWarpSmem<G>* ws, const unsig
           khi = cand ? (khi ^ flip) : 0xffffffffu; klo = cand ? (klo ^ flip) : 0xffffffffu;
           const unsigned mh = __reduce_min_sync(full, khi);
           bool in_ = cand && khi == mh;
-          const unsigned ml = __reduce_min_sync(full, in_ ? klo : 0xffffffffu);
-          in_ = in_ && klo == ml;
           // (all-ones keys of non-candidates can only tie with a candidate whose key is all ones too; `in_` requires cand)
-          const unsigned wm = __ballot_sync(full, in_);
+          unsigned wm = __ballot_sync(full, in_);
+          if (wm & (wm - 1)) {                // several candidates share the high word: the low word decides
+            const unsigned ml = __reduce_min_sync(full, in_ ? klo : 0xffffffffu);
+            wm = __ballot_sync(full, in_ && klo == ml);
+          }
           const int wl = upj ? (__ffs(wm) - 1) : (31 - __clz(wm));
           moved = upj ? 1 : -1;
           adj = lane == wl ? moved : 0;

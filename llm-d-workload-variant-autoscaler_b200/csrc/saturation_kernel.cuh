@@ -4,16 +4,24 @@
 // CalculateSaturationTargets (analyzer.go:290-439).
 //
 // HBM-bound by design: 16 B per replica (kv float64 + queue int64) + 32 B per variant + 40 B per model, each read once.
-// One warp per model, every warp its own software pipeline — no block-level synchronisation anywhere:
-//   * the replica stream (the two big arrays, one contiguous range per model thanks to the CSR layout) is moved by the
-//     TMA unit: lane 0 issues two `cp.async.bulk` (1-D TMA) copies global -> shared memory per model, completing on the
-//     warp's own mbarrier, SAT_NS models ahead of the one being analysed (24 warps x ~2.3 KB in flight per SM);
-//   * the per-variant arrays (24 B per variant) are read directly, one lane per variant: perfectly coalesced;
-//   * a lane then streams its variant's replicas out of shared memory in slice order (the per-variant float64 sums are
-//     order dependent), the variant -> model accumulation runs in ascending variant index (broadcast reads, fixed
-//     32-step unrolled chain; lanes without metrics contribute an exact +0.0), and the cheapest / most-expensive
-//     variant is a two-word warp arg-min on the order-preserving bit pattern of the cost.
-// A model with more replicas than a stage holds (SAT_CAP) takes the same code over global memory instead.
+// One warp per GROUP of G = 2 consecutive models, every warp its own software pipeline over its groups — no block-level
+// synchronisation anywhere (one persistent 768-thread block per SM, 24 warps x 8.3 KB of shared memory):
+//   * consecutive models are contiguous in the CSR layout, so a group's replicas are ONE range of each replica array: lane
+//     0 issues two `cp.async.bulk` (1-D TMA) copies global -> shared memory per group (2 x ~2.3 KB), completing on the
+//     warp's own mbarrier; the per-variant columns (24 B per variant) follow as 16-byte `cp.async` chunks, one per lane and
+//     column, and the models' 48-byte descriptors go to a slot selected by trip parity;
+//   * a lane owns variant l of each model of the group — G independent dependency chains — and streams their replicas out
+//     of shared memory in slice order (the per-variant float64 sums are order dependent) in a branch-free, warp-uniform
+//     loop of four slots per round;
+//   * as soon as that loop is over everything the trip still needs is in registers, and the warp issues the copies of its
+//     NEXT group into the same stage: they land while the model-level part of this group runs (a single stage per warp —
+//     twice the warps of a double-buffered design in the same shared memory);
+//   * the variant -> model accumulation runs in ascending variant index as 2G chains (KV and queue of every model) in
+//     disjoint lane groups of one fixed 32-step pass (lanes without metrics contribute an exact +0.0); the model-level
+//     divisions are done once, every lane for its own model; the cheapest / most-expensive variant is a warp arg-min on
+//     the order-preserving bit pattern of the cost.
+// A group that does not fit a stage (more than CAP_R replicas, a model of more than 32 variants, a variant of more than 64
+// replicas) takes the general path — the same arithmetic over global memory — in a second pass of the same kernel.
 #pragma once
 #include "wva_core.cuh"
 

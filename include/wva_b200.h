@@ -418,7 +418,9 @@ int32_t wva_ingest_destroy(wva_ingest* ing);
 /* start of a cycle: no pod has reported yet */
 int32_t wva_ingest_begin(wva_ingest* ing);
 /* one Prometheus-shaped vector keyed by slot, in result order: later samples of a pod overwrite earlier ones (the
- * reference assigns into a map, replica_metrics.go:133-160); slot < 0 = no pod label / unknown pod: skipped */
+ * reference assigns into a map, replica_metrics.go:133-160); slot < 0 = no pod label / unknown pod: skipped.  A vector of
+ * 64 K samples or more that is not in registry order is binned by slot range over up to 8 host threads (same result as
+ * the serial loop; WVA_INGEST_THREADS overrides the count, 1 = always serial). */
 int32_t wva_ingest_write(wva_ingest* ing, int32_t which /* WVA_VEC_* */, int64_t n, const int32_t* slot, const double* value);
 /* metric batch -> decisions: one CUDA graph launch (wva_timing.saturation_ms = device time of the whole graph) */
 int32_t wva_ingest_commit(wva_ingest* ing);

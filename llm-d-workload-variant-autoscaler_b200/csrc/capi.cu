@@ -18,6 +18,7 @@
 #include "greedy_solve.cuh"
 #include "greedy_sweep.cuh"
 #include "mm1k_kernel.cuh"
+#include "ingest_scatter.hpp"
 
 #include <cuda_runtime.h>
 #include <cstdio>

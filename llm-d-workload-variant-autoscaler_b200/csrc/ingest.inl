@@ -69,6 +69,7 @@ struct wva_ingest {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   long long cycles = 0;
+  IngestScratch scratch;              // host scratch of wva_ingest_write
 };
 
 static cudaError_t ingest_enqueue(wva_ingest* g, cudaStream_t s) {
@@ -206,17 +207,10 @@ extern "C" int32_t wva_ingest_begin(wva_ingest* g) {
 // reference assigns into a map, replica_metrics.go:133-160); slot < 0 = sample without a pod label or of an unknown pod
 extern "C" int32_t wva_ingest_write(wva_ingest* g, int32_t which, int64_t n, const int32_t* slot, const double* value) {
   if (!g || n < 0 || (n > 0 && (!slot || !value)) || (which != WVA_VEC_KV_CACHE_USAGE && which != WVA_VEC_QUEUE_LENGTH)) return WVA_ERR_ARG;
-  const long long S = g->S;
   double* col = which == WVA_VEC_KV_CACHE_USAGE ? g->cols.kv : g->cols.queue;
   const uint8_t bit = which == WVA_VEC_KV_CACHE_USAGE ? 1 : 2;
-  for (int64_t i = 0; i < n; i++) {
-    const int32_t k = slot[i];
-    if (k < 0) continue;
-    if (k >= S) return WVA_ERR_ARG;
-    col[k] = value[i];
-    g->cols.has[k] |= bit;
-  }
-  return WVA_OK;
+  // large vectors: two-pass radix partition over host threads (ingest_scatter.hpp), same result as the serial loop
+  return ingest_scatter(col, g->cols.has, g->S, bit, n, slot, value, g->scratch) ? WVA_OK : WVA_ERR_ARG;
 }
 
 extern "C" int32_t wva_ingest_commit(wva_ingest* g) {

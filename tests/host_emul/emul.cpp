@@ -4,6 +4,7 @@
 #include "../../include/wva_b200.h"
 #include "../../llm-d-workload-variant-autoscaler_b200/csrc/wva_core.cuh"
 #include "../../llm-d-workload-variant-autoscaler_b200/csrc/sizer_probe.cuh"
+#include "../../llm-d-workload-variant-autoscaler_b200/csrc/ingest_scatter.hpp"
 #include <vector>
 #include <cstdio>
 #include <cstdlib>
@@ -325,6 +326,12 @@ extern "C" int emul_trace_pair(const wva_system* sys, int32_t* trace, int W, flo
 }
 
 extern "C" {
+
+// the host side of wva_ingest_write (csrc/ingest_scatter.hpp) on caller-provided columns
+int emul_ingest_scatter(double* col, uint8_t* has, int64_t S, int bit, int64_t n, const int32_t* slot, const double* value, int threads) {
+  static IngestScratch sc;
+  return ingest_scatter(col, has, (long long)S, (uint8_t)bit, n, slot, value, sc, threads) ? 0 : 1;
+}
 
 // System.Calculate through the lane state machine, one lane at a time.
 int emul_calculate(const wva_system* sys, wva_candidates* out, int64_t* solves, int64_t* states, int64_t* overflow) {

@@ -255,3 +255,52 @@ def test_model_sharding_is_a_partition(pkg, oracle):
         tc += s["type_count"]
         seen[idx] = True
     assert seen.all() and np.array_equal(tc, fsol["type_count"])
+
+
+@pytest.mark.parametrize("threads", [1, 2, 3, 8, 64])
+def test_ingest_scatter_threads_equal_the_serial_map_assignment(emul, threads):
+    """csrc/ingest_scatter.hpp (the host side of wva_ingest_write): split over threads by slot range, a response in any
+    order with duplicate samples, unknown pods (slot < 0) and every slot residue gives exactly what the reference's map
+    assignment gives — the LAST sample of a pod wins (internal/collector/replica_metrics.go:133-160)."""
+    g = np.random.default_rng(77 + threads)
+    S, n = 10_007, 60_000                                   # every slot reported ~6 times: duplicates everywhere
+    slot = g.integers(-3, S, n).astype(np.int32)
+    value = g.random(n)
+    col = np.full(S, -1.0); has = np.zeros(S, np.uint8)
+    has[::5] = 2                                            # bits of the other vector stay
+    want_col, want_has = col.copy(), has.copy()
+    for k, v in zip(slot.tolist(), value.tolist()):         # the serial map assignment
+        if k >= 0:
+            want_col[k] = v; want_has[k] |= 1
+    f = emul.emul_ingest_scatter
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    assert f(col.ctypes.data, has.ctypes.data, S, 1, n, slot.ctypes.data, value.ctypes.data, threads) == 0
+    assert np.array_equal(col, want_col) and np.array_equal(has, want_has)
+    # a slot past the registry is an argument error, whichever range it falls behind
+    slot[n // 2] = S + 5
+    assert f(col.ctypes.data, has.ctypes.data, S, 1, n, slot.ctypes.data, value.ctypes.data, threads) == 1
+    # tiny registries: fewer 64-slot blocks than threads
+    col2 = np.zeros(3); has2 = np.zeros(3, np.uint8)
+    s2 = np.array([2, 0, 2, -1], np.int32); v2 = np.array([1.0, 2.0, 3.0, 4.0])
+    assert f(col2.ctypes.data, has2.ctypes.data, 3, 2, 4, s2.ctypes.data, v2.ctypes.data, threads) == 0
+    assert col2.tolist() == [2.0, 0.0, 3.0] and has2.tolist() == [2, 0, 2]
+
+
+@pytest.mark.parametrize("order", ["registry", "shuffled", "mostly_sorted_with_duplicates"])
+def test_ingest_scatter_auto_mode(emul, order):
+    """threads = 0: the library chooses — the serial loop for a response in registry order, the partition otherwise."""
+    g = np.random.default_rng(5)
+    S = 70_001
+    slot = np.arange(S, dtype=np.int32)
+    if order == "shuffled":
+        slot = g.permutation(S).astype(np.int32)
+    elif order == "mostly_sorted_with_duplicates":
+        slot = np.concatenate([slot, g.integers(0, S, 3000).astype(np.int32)])
+    n = slot.size
+    value = g.random(n)
+    want = np.zeros(S); want[slot] = value                   # numpy assigns in order: the last duplicate wins
+    col = np.zeros(S); has = np.zeros(S, np.uint8)
+    f = emul.emul_ingest_scatter
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    assert f(col.ctypes.data, has.ctypes.data, S, 2, n, slot.ctypes.data, value.ctypes.data, 0) == 0
+    assert np.array_equal(col, want) and (has == 2).all()

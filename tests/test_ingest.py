@@ -28,8 +28,13 @@ def _vector_to_slots(vec, slot_of):
     return sl, va
 
 
-@pytest.mark.parametrize("n_models,vpm,seed", [(50, 6, 1), (400, 32, 2), (3, 1, 3)])
-def test_ingest_matches_collector_and_oracle(pkg, engine, oracle, n_models, vpm, seed):
+@pytest.mark.parametrize("n_models,vpm,seed,threads", [(50, 6, 1, 0), (400, 32, 2, 0), (3, 1, 3, 0), (400, 32, 4, 5),
+                                                          (50, 6, 5, 3)])
+def test_ingest_matches_collector_and_oracle(pkg, engine, oracle, n_models, vpm, seed, threads, monkeypatch):
+    """threads > 0: wva_ingest_write goes through its two-pass radix partition over that many host threads
+    (csrc/ingest_scatter.hpp) whatever the size of the vector; 0: the library chooses (serial at these sizes)."""
+    if threads:
+        monkeypatch.setenv("WVA_INGEST_THREADS", str(threads))
     fx = cr.fixture(n_models, vpm, seed=seed)
     mvo, vso, slot_of, var_names = _registry(fx)
     M, V = len(mvo) - 1, len(vso) - 1
